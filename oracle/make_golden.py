@@ -1,0 +1,146 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference):  python oracle/make_golden.py
+The reference ships no tests / golden vectors; these fixtures are outputs of the
+reference's own Python modules (imported via oracle/ref_import.py) on small seeded inputs, and are what
+pins the oracle (tests/test_oracle_golden.py) and, through it, the CUDA kernels.
+
+Fixtures
+  msda_core_{a,b}.npz   multi_scale_deformable_attn_pytorch (ms_deform_attn.py:159-212) forward and its
+                        autograd gradients (the contract of _C.ms_deform_attn_forward/backward).
+  msda_module.npz       MultiScaleDeformableAttention.forward (ms_deform_attn.py:286-377) incl. state_dict.
+  encoder_tiny_{even,ragged}.npz
+                        SalienceTransformer.forward lines 106-183 (filter + encoder) of a tiny model:
+                        inputs, encoder-half state_dict, the kwargs the filter hands to the encoder, and
+                        the encoder memory.  "even": both images full size (tie-free selection);
+                        "ragged": second image smaller (padded tokens -> ties, see SURVEY.md 8(a) notes).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_import  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+def make_msda_core(name, b, shapes, m, d, nq, p, seed):
+    ref = ref_import.load()
+    g = torch.Generator().manual_seed(seed)
+    shapes_t = torch.tensor(shapes, dtype=torch.int64)
+    nv = int(shapes_t.prod(1).sum())
+    lsi = torch.cat([shapes_t.new_zeros(1), shapes_t.prod(1).cumsum(0)[:-1]])
+    L = len(shapes)
+    value = torch.randn(b, nv, m, d, generator=g, requires_grad=True)
+    loc = (torch.rand(b, nq, m, L, p, 2, generator=g) * 1.2 - 0.1).requires_grad_(True)
+    attn = torch.randn(b, nq, m, L * p, generator=g).softmax(-1).view(b, nq, m, L, p).requires_grad_(True)
+    out = ref.msda.multi_scale_deformable_attn_pytorch(value, shapes_t, loc, attn)
+    gout = torch.randn(out.shape, generator=g)
+    gv, gl, ga = torch.autograd.grad(out, (value, loc, attn), gout)
+    np.savez_compressed(os.path.join(OUT, name), value=np_(value), shapes=np_(shapes_t), lsi=np_(lsi),
+                        loc=np_(loc), attn=np_(attn), out=np_(out), grad_out=np_(gout), grad_value=np_(gv),
+                        grad_loc=np_(gl), grad_attn=np_(ga))
+
+
+def make_msda_module(seed=3):
+    ref = ref_import.load()
+    torch.manual_seed(seed)
+    mod = ref.msda.MultiScaleDeformableAttention(64, 4, 2, 4).eval()
+    with torch.no_grad():  # non-trivial offsets / weights (init has zero weight matrices)
+        mod.sampling_offsets.weight.normal_(0, 0.05)
+        mod.attention_weights.weight.normal_(0, 0.5)
+    shapes = [(9, 12), (5, 6), (3, 3), (2, 2)]
+    shapes_t = torch.tensor(shapes)
+    nv = int(shapes_t.prod(1).sum())
+    lsi = torch.cat([shapes_t.new_zeros(1), shapes_t.prod(1).cumsum(0)[:-1]])
+    b, nq = 2, 37
+    query = torch.randn(b, nq, 64)
+    refp = torch.rand(b, nq, 4, 2)
+    value = torch.randn(b, nv, 64)
+    mask = torch.rand(b, nv) < 0.15
+    with torch.no_grad():
+        out = mod(query, refp, value, shapes_t, lsi, mask)
+    sd = {"sd." + k: np_(v) for k, v in mod.state_dict().items()}
+    np.savez_compressed(os.path.join(OUT, "msda_module.npz"), query=np_(query), ref=np_(refp), value=np_(value),
+                        shapes=np_(shapes_t), lsi=np_(lsi), mask=np_(mask), out=np_(out), **sd)
+
+
+class _Stop(Exception):
+    pass
+
+
+TINY = dict(embed_dim=64, d_ffn=128, n_heads=2, n_levels=4, n_points=4, num_layers=3, num_classes=11,
+            level_filter_ratio=(0.4, 0.8, 1.0, 1.0), layer_filter_ratio=(1.0, 0.6, 0.3), topk_sa=20,
+            max_num_embedding=40, num_proposals=30)
+
+
+def make_encoder_tiny(name, image_sizes, padded, seed):
+    tr = ref_import.build_transformer(seed=seed, **TINY)
+    with torch.no_grad():
+        for layer in tr.encoder.layers:  # exercise learned offsets/weights, not only the init ring
+            layer.self_attn.sampling_offsets.weight.normal_(0, 0.05)
+            layer.self_attn.attention_weights.weight.normal_(0, 0.5)
+    feats, masks, pos = orc.synthetic_inputs(image_sizes, padded, TINY["embed_dim"], seed=seed)
+    captured = {}
+    enc_fwd = tr.encoder.forward
+    layer_out = []
+    hooks = [l.register_forward_hook(lambda m, i, o: layer_out.append(o.detach().clone())) for l in tr.encoder.layers]
+
+    def spy(**kw):
+        captured.update(kw)
+        captured["memory"] = enc_fwd(**kw)
+        raise _Stop()
+
+    tr.encoder.forward = spy
+    try:
+        with torch.no_grad():
+            tr(feats, masks, pos, None, None, None)
+    except _Stop:
+        pass
+    for h in hooks:
+        h.remove()
+    sd = {"sd." + k: np_(v) for k, v in tr.state_dict().items()
+          if not (k.startswith("decoder") or k.startswith("tgt_embed") or k.startswith("encoder_bbox_head"))}
+    arrs = {f"feat{i}": np_(f) for i, f in enumerate(feats)}
+    arrs.update({f"mask{i}": np_(m) for i, m in enumerate(masks)})
+    arrs.update({f"pos{i}": np_(p) for i, p in enumerate(pos)})
+    arrs.update({f"layer_out{i}": np_(o) for i, o in enumerate(layer_out)})
+    np.savez_compressed(
+        os.path.join(OUT, name),
+        memory=np_(captured["memory"]),
+        foreground_score=np_(captured["foreground_score"]),
+        focus_token_nums=np_(captured["focus_token_nums"]),
+        selected_inds=np_(captured["foreground_inds"][0]),
+        layer_num_query=np.array([x.shape[1] for x in captured["foreground_inds"]]),
+        valid_ratios=np_(captured["valid_ratios"]),
+        spatial_shapes=np_(captured["spatial_shapes"]),
+        level_start_index=np_(captured["level_start_index"]),
+        cfg_keys=np.array(sorted(TINY.keys())),
+        **arrs, **sd)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    make_msda_core("msda_core_a.npz", b=2, shapes=[(10, 12), (5, 6), (3, 3), (2, 2)], m=4, d=32, nq=40, p=4, seed=1)
+    make_msda_core("msda_core_b.npz", b=1, shapes=[(7, 5), (4, 3)], m=2, d=16, nq=23, p=2, seed=2)
+    make_msda_module()
+    make_encoder_tiny("encoder_tiny_even.npz", [(96, 128), (96, 128)], (96, 128), seed=5)
+    make_encoder_tiny("encoder_tiny_ragged.npz", [(96, 128), (72, 90)], (96, 128), seed=6)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
+    print("torch", torch.__version__)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,44 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    """-> (arrays dict of torch tensors, state_dict) from tests/golden/<name>.npz"""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    arrs, sd = {}, {}
+    for k in z.files:
+        if z[k].dtype.kind in "US":
+            continue
+        t = torch.from_numpy(z[k])
+        if k.startswith("sd."):
+            sd[k[3:]] = t
+        else:
+            arrs[k] = t
+    return arrs, sd
+
+
+TINY_CFG = dict(heads=2, points=4, topk_sa=20, num_layers=3, level_filter_ratio=(0.4, 0.8, 1.0, 1.0),
+                layer_filter_ratio=(1.0, 0.6, 0.3))
