@@ -1,0 +1,187 @@
+/*
+ * sdetr_b200.h -- C-ABI of the B200-native (sm_100a) Salience-DETR encoder hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  All pointers are DEVICE
+ * pointers unless the parameter name ends in `_host`.  Every call is asynchronous on `stream`
+ * (a cudaStream_t passed as void*), allocates nothing, never synchronises, and is re-entrant across
+ * streams.  Return value: 0 on success, negative sdetr_status on error (message: sdetr_last_error(),
+ * thread-local).  Launch errors are RETURNED (the reference only printf's them:
+ * models/bricks/ops/cuda/ms_deform_im2col_cuda.cuh:937-941, 1310-1314).
+ *
+ * Citations below are relative to the reference root (xiuqhou/Salience-DETR @ 6262e05).
+ * "(b,Nq,M,L,P,2)" etc. are row-major contiguous shapes; fp32 unless stated.
+ */
+#ifndef SDETR_B200_H
+#define SDETR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *sdetr_stream_t; /* cudaStream_t */
+
+enum sdetr_status {
+    SDETR_OK = 0,
+    SDETR_ERR_INVALID_ARG = -1, /* null pointer, non-positive size, misaligned pointer */
+    SDETR_ERR_UNSUPPORTED = -2, /* shape outside the compiled kernel family */
+    SDETR_ERR_CUDA = -3,        /* cudaGetLastError() after a launch */
+    SDETR_ERR_WORKSPACE = -4    /* workspace too small */
+};
+
+/* library version (major*10000 + minor*100 + patch) and last error string of the calling thread */
+int sdetr_version(void);
+const char *sdetr_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py "gpu_launches") */
+unsigned long long sdetr_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * MSDA core forward.  Replaces `_C.ms_deform_attn_forward`
+ *   (models/bricks/ops/cuda/ms_deform_attn_cuda.cu:12-72, kernel ms_deform_im2col_cuda.cuh:226-288;
+ *    numerically the same op as multi_scale_deformable_attn_pytorch, models/bricks/ms_deform_attn.py:159-212)
+ *   out[b,q,m,:] = sum_{l,p} attn[b,q,m,l,p] * bilinear_zero_pad(value_l[b,:,m,:], loc[b,q,m,l,p])
+ *   pixel coords  x = loc_x*W_l - 0.5, y = loc_y*H_l - 0.5 (align_corners=False).
+ * value (b,Nv,M,D); spatial_shapes (L,2) int64 (H,W); level_start_index (L) int64 -- both on the device,
+ * exactly the tensors the reference op receives; sampling_loc (b,Nq,M,L,P,2); attn_weight (b,Nq,M,L,P);
+ * output (b,Nq,M*D), fully overwritten.  The reference's im2col_step batching (.cu:42-66) has no
+ * numerical effect and is not needed (one launch covers the whole batch).
+ */
+int sdetr_msda_forward(const float *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                       const float *sampling_loc, const float *attn_weight, float *output, int batch,
+                       int num_value, int num_heads, int head_dim, int num_levels, int num_query,
+                       int num_points, sdetr_stream_t stream);
+
+/* Extended form used by the encoder mirror:
+ *  - value_batch_stride / value_token_stride (in floats) let `value` be a column slice of a wider
+ *    projection buffer (the six layers' value_proj outputs share one GEMM; salience_transformer.py:452
+ *    feeds the SAME value tokens to every layer);
+ *  - query_order (b,Nq) int32, nullable: permutation giving the PROCESSING order of the queries
+ *    (spatially tiled for L1 locality; results are written to their original rows);
+ *  - schedule: 0 = query-major (4 queries x all heads per CTA), 1 = head-major chunks
+ *    (one head of `chunk` consecutive queries of the processing order per CTA). */
+int sdetr_msda_forward_ex(const float *value, int64_t value_batch_stride, int64_t value_token_stride,
+                          const int64_t *spatial_shapes, const int64_t *level_start_index,
+                          const float *sampling_loc, const float *attn_weight, float *output, int batch,
+                          int num_value, int num_heads, int head_dim, int num_levels, int num_query,
+                          int num_points, const int32_t *query_order, int schedule, sdetr_stream_t stream);
+
+/* Fused attention-weight softmax + sampling-location arithmetic + MSDA core
+ *   (models/bricks/ms_deform_attn.py:322-344 fused into the core, 2-d reference points):
+ *   proj (b,Nq,proj_stride): per query, M*L*P*2 raw sampling offsets followed by M*L*P raw attention
+ *   logits (the concatenated sampling_offsets | attention_weights Linear output);
+ *   ref_points (b,Nq,L,2);  loc = ref + off / (W_l,H_l);  attn = softmax over the L*P logits of a head.
+ *   loc_out / attn_out: nullable; when given they receive sampling_locations / attention_weights in the
+ *   reference layouts (needed by the backward).  Other arguments as sdetr_msda_forward_ex. */
+int sdetr_msda_fused_forward(const float *value, int64_t value_batch_stride, int64_t value_token_stride,
+                             const int64_t *spatial_shapes, const int64_t *level_start_index,
+                             const float *ref_points, const float *proj, int64_t proj_stride, float *output,
+                             float *loc_out, float *attn_out, int batch, int num_value, int num_heads,
+                             int head_dim, int num_levels, int num_query, int num_points,
+                             const int32_t *query_order, int schedule, sdetr_stream_t stream);
+
+/* MSDA core backward.  Replaces `_C.ms_deform_attn_backward`
+ *   (ms_deform_attn_cuda.cu:75-145; kernels ms_deform_im2col_cuda.cuh:76-148, 290-392).
+ * grad_output (b,Nq,M*D) -> grad_value (b,Nv,M,D), grad_sampling_loc, grad_attn_weight (shapes of the
+ * inputs).  All three outputs are fully written (grad_value is zeroed on `stream` first; the reference
+ * allocates zeros, .cu:113-115).  grad_value accumulates with fp32 red.global adds like the reference's
+ * atomicAdd (run-to-run order of additions is not deterministic). */
+int sdetr_msda_backward(const float *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                        const float *sampling_loc, const float *attn_weight, const float *grad_output,
+                        float *grad_value, float *grad_sampling_loc, float *grad_attn_weight, int batch,
+                        int num_value, int num_heads, int head_dim, int num_levels, int num_query,
+                        int num_points, sdetr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Hierarchical salience token filter (models/bricks/salience_transformer.py:146-168), one call:
+ *   per level l: v = where(mask, min over the whole (b,HW_l) score tensor, score)       (:146)
+ *                top-k_l of v per image, indices offset by level_start                  (:150-151)
+ *   concatenate levels, sort by score descending, reorder indices                       (:156-158)
+ *   foreground_score = where(mask, min over the whole (b,Nv) tensor, score)             (:166-168)
+ * Order of equal scores (unspecified in torch.topk/sort): larger score first, then smaller token index.
+ * raw_score (b,Nv); mask (b,Nv) uint8, 1 = padding; level_start_host / level_size_host / level_k_host:
+ * HOST int32 arrays of length num_levels (k_l = level_token_nums, :120; k_l <= size_l).
+ * -> selected_inds (b,K) int64, selected_score (b,K), foreground_score (b,Nv), K = sum k_l.
+ * tile_order (b,K) int32, nullable: positions 0..K-1 of each image's selected list ordered by the
+ * spatial cell of their token (cell_px x cell_px image pixels; level-l token = level_stride_host[l] px):
+ * the processing order handed to sdetr_msda_forward_ex after sdetr_order_prefixes().
+ * workspace: sdetr_salience_select_workspace() bytes, 256-byte aligned.
+ */
+size_t sdetr_salience_select_workspace(int batch, int num_value, int num_levels);
+int sdetr_salience_select(const float *raw_score, const uint8_t *mask, const int32_t *level_start_host,
+                          const int32_t *level_size_host, const int32_t *level_k_host,
+                          const int32_t *level_width_host, const int32_t *level_stride_host, int cell_px,
+                          int batch, int num_value, int num_levels, int64_t *selected_inds,
+                          float *selected_score, float *foreground_score, int32_t *tile_order,
+                          void *workspace, size_t workspace_bytes, sdetr_stream_t stream);
+
+/* Per-layer prefixes of the processing order: for each layer j (prefix length nq_host[j] of the selected
+ * list, salience_transformer.py:161-165) emit the positions < nq_j in tile order:
+ * out_orders + order_offset_host[j] : (b, nq_j) int32. */
+int sdetr_order_prefixes(const int32_t *tile_order, int batch, int K, int num_layers,
+                         const int32_t *nq_host, const int64_t *order_offset_host, int32_t *out_orders,
+                         sdetr_stream_t stream);
+
+/* Generic segmented top-k by score (descending; ties: smaller position first).  Used for the
+ * "top-300 most salient tokens" pre-attention selection (salience_transformer.py:366-367).
+ * score (segments, n) -> topk_index (segments, k) int64 positions within the segment.
+ * workspace: sdetr_topk_workspace() bytes. */
+size_t sdetr_topk_workspace(int segments, int n);
+int sdetr_topk_desc(const float *score, int segments, int n, int k, int64_t *topk_index, void *workspace,
+                    size_t workspace_bytes, sdetr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Token movement around the encoder layers (models/bricks/salience_transformer.py:454-495).
+ */
+
+/* Fused four-way gather (:454-461).  inds: int64, row stride inds_stride (a prefix view of selected_inds).
+ * tokens/pos (b,Nv,C), fg (b,Nv), valid_ratios (b,L,2) ->
+ * query (b,Nq,C), query_pos (b,Nq,C), fg_q (b,Nq), ref_q (b,Nq,L,2) where ref_q is the gathered row of
+ * get_reference_points (:417-432), recomputed from the token's (level,y,x) with identical fp32 arithmetic. */
+int sdetr_token_gather(const float *tokens, const float *pos, const float *fg, const float *valid_ratios,
+                       const int64_t *inds, int64_t inds_stride, const int64_t *spatial_shapes,
+                       const int64_t *level_start_index, int batch, int num_value, int channels,
+                       int num_levels, int num_query, float *query, float *query_pos, float *fg_q,
+                       float *ref_q, sdetr_stream_t stream);
+
+/* In-place scatter-back (:474-485): tokens[b, inds[b,q], :] = query[b,q,:] for q < min(focus[b], Nq).
+ * focus_token_nums (b) int32 on the device (no host sync, unlike the reference's per-image slicing). */
+int sdetr_token_scatter(float *tokens, const float *query, const int64_t *inds, int64_t inds_stride,
+                        const int32_t *focus_token_nums, int batch, int num_value, int channels,
+                        int num_query, sdetr_stream_t stream);
+
+/* Background embedding (:488-495, position_encoding.py:81-95), in place:
+ * tokens[b,t,:] += [col_embed[x] | row_embed[y]] unless mask[b,t] or t in last_inds[b,:num_last].
+ * flags: (b,Nv) uint8 scratch. */
+int sdetr_background_embed(float *tokens, const uint8_t *mask, const int64_t *last_inds, int64_t inds_stride,
+                           int num_last, const float *row_embed, const float *col_embed,
+                           const int64_t *spatial_shapes, const int64_t *level_start_index, int batch,
+                           int num_value, int channels, int num_levels, uint8_t *flags,
+                           sdetr_stream_t stream);
+
+/* Coarse-to-fine score modulation (:134-143): out = mem + mem * up * alpha[alpha_index], up = bilinear resize
+ * (align_corners=True) of the coarser level's score map (b,Hc*Wc) to (H,W).  mem/out (b,H*W,C) with row
+ * strides; alpha is read on the device. */
+int sdetr_score_modulate(const float *mem, int64_t mem_batch_stride, const float *coarse_score,
+                         int64_t coarse_batch_stride, const float *alpha, int alpha_index, int batch, int H,
+                         int W, int Hc, int Wc, int channels, float *out, sdetr_stream_t stream);
+
+/* value rows of padded tokens -> 0 (ms_deform_attn.py:318-319), only masked rows are touched.
+ * rows: (b*Nv) rows of `row_floats` contiguous floats at stride row_stride. */
+int sdetr_zero_masked_rows(float *rows, int64_t row_stride, int row_floats, const uint8_t *mask,
+                           int64_t num_rows, sdetr_stream_t stream);
+
+/* mc_score = max_c(class_logits) * fg (:366).  logits (rows, num_classes) -> out (rows). */
+int sdetr_class_max_times_fg(const float *logits, const float *fg, int64_t rows, int num_classes, float *out,
+                             sdetr_stream_t stream);
+
+/* y = LayerNorm(x + r) * gamma + beta (:390-391, :349-350); rows of `channels` (<= 1024, multiple of 4).
+ * May run in place (y == x). */
+int sdetr_add_layernorm(const float *x, const float *r, const float *gamma, const float *beta, float eps,
+                        int64_t rows, int channels, float *y, sdetr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDETR_B200_H */

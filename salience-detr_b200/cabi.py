@@ -1,0 +1,312 @@
+"""ctypes binding of the C-ABI library declared in ``include/sdetr_b200.h``.
+
+PyTorch is plumbing only here: it owns device memory and the stream; every wrapper validates its
+tensors the way the reference op does (contiguous + CUDA, ``AT_ASSERTM`` in
+models/bricks/ops/cuda/ms_deform_attn_cuda.cu:20-30), allocates the outputs with ``torch.empty`` and passes
+raw pointers plus ``torch.cuda.current_stream().cuda_stream``.  A non-zero return code becomes a
+``RuntimeError`` carrying ``sdetr_last_error()``.
+
+There is NO fallback: if the shared library is missing the import of the product path fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsdetr_b200.so")
+_lib = None
+
+_vp, _i, _i64, _sz, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_float
+
+# name -> (restype, argtypes); must list every symbol of include/sdetr_b200.h (tests check this)
+SIGNATURES = {
+    "sdetr_version": (_i, []),
+    "sdetr_last_error": (ctypes.c_char_p, []),
+    "sdetr_launch_count": (ctypes.c_ulonglong, []),
+    "sdetr_msda_forward": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
+    "sdetr_msda_forward_ex": (_i, [_vp, _i64, _i64] + [_vp] * 5 + [_i] * 7 + [_vp, _i, _vp]),
+    "sdetr_msda_fused_forward": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp] + [_i] * 7 + [_vp, _i, _vp]),
+    "sdetr_msda_backward": (_i, [_vp] * 9 + [_i] * 7 + [_vp]),
+    "sdetr_salience_select_workspace": (_sz, [_i, _i, _i]),
+    "sdetr_salience_select": (_i, [_vp] * 7 + [_i] * 4 + [_vp] * 5 + [_sz, _vp]),
+    "sdetr_order_prefixes": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "sdetr_topk_workspace": (_sz, [_i, _i]),
+    "sdetr_topk_desc": (_i, [_vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "sdetr_token_gather": (_i, [_vp] * 5 + [_i64, _vp, _vp] + [_i] * 5 + [_vp] * 5),
+    "sdetr_token_scatter": (_i, [_vp, _vp, _vp, _i64, _vp] + [_i] * 4 + [_vp]),
+    "sdetr_background_embed": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp] + [_i] * 4 + [_vp, _vp]),
+    "sdetr_score_modulate": (_i, [_vp, _i64, _vp, _i64, _vp] + [_i] * 7 + [_vp, _vp]),
+    "sdetr_zero_masked_rows": (_i, [_vp, _i64, _i, _vp, _i64, _vp]),
+    "sdetr_class_max_times_fg": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
+    "sdetr_add_layernorm": (_i, [_vp, _vp, _vp, _vp, _f, _i64, _i, _vp, _vp]),
+}
+
+
+def lib():
+    """Load (once) the sm_100a library.  Raises if it has not been built (``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU or PyTorch fallback for this path.")
+        cdll = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(cdll, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = cdll
+    return _lib
+
+
+def launch_count() -> int:
+    return int(lib().sdetr_launch_count())
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (rc={rc}): {lib().sdetr_last_error().decode()}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, name: str, dtype=None):
+    # same contract as the reference's AT_ASSERTM checks -> RuntimeError
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} tensor has to be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def _host_i32(xs: Sequence[int]):
+    return (ctypes.c_int32 * len(xs))(*[int(x) for x in xs])
+
+
+def _host_i64(xs: Sequence[int]):
+    return (ctypes.c_int64 * len(xs))(*[int(x) for x in xs])
+
+
+# ---- MSDA core ------------------------------------------------------------------------------------------
+def msda_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, query_order=None, schedule=0):
+    """`_C.ms_deform_attn_forward` contract: value (b,Nv,M,D) f32 -> (b,Nq,M*D), fresh tensor."""
+    b, nv, m, d = value.shape
+    nq, L, P = sampling_loc.shape[1], sampling_loc.shape[3], sampling_loc.shape[4]
+    out = torch.empty(b, nq, m * d, device=value.device, dtype=torch.float32)
+    rc = lib().sdetr_msda_forward_ex(
+        _req(value, "value", torch.float32), nv * m * d, m * d, _req(spatial_shapes, "spatial_shapes", torch.int64),
+        _req(level_start_index, "level_start_index", torch.int64), _req(sampling_loc, "sampling_loc", torch.float32),
+        _req(attn_weight, "attn_weight", torch.float32), out.data_ptr(), b, nv, m, d, L, nq, P,
+        _req(query_order, "query_order", torch.int32) if query_order is not None else None, schedule, _stream())
+    _check(rc, "sdetr_msda_forward_ex")
+    return out
+
+
+def msda_forward_plain(value, spatial_shapes, level_start_index, sampling_loc, attn_weight):
+    """The plain entry point (no strides / order), same result as :func:`msda_forward`."""
+    b, nv, m, d = value.shape
+    nq, L, P = sampling_loc.shape[1], sampling_loc.shape[3], sampling_loc.shape[4]
+    out = torch.empty(b, nq, m * d, device=value.device, dtype=torch.float32)
+    rc = lib().sdetr_msda_forward(
+        _req(value, "value", torch.float32), _req(spatial_shapes, "spatial_shapes", torch.int64),
+        _req(level_start_index, "level_start_index", torch.int64), _req(sampling_loc, "sampling_loc", torch.float32),
+        _req(attn_weight, "attn_weight", torch.float32), out.data_ptr(), b, nv, m, d, L, nq, P, _stream())
+    _check(rc, "sdetr_msda_forward")
+    return out
+
+
+def msda_fused_forward(value_buf, value_batch_stride, value_token_stride, value_offset, spatial_shapes,
+                       level_start_index, ref_points, proj, heads, head_dim, levels, points, num_value,
+                       query_order=None, schedule=0, want_loc_attn=False):
+    """softmax + sampling locations + core in one launch.  ``value_buf`` may be a wide projection buffer;
+    ``value_offset`` (floats) selects this layer's column slice.  proj: (b,Nq,>=3*M*L*P) last-dim contiguous."""
+    b, nq = proj.shape[0], proj.shape[1]
+    if not (proj.is_cuda and proj.stride(2) == 1 and proj.stride(0) == nq * proj.stride(1)):
+        raise RuntimeError("proj must be a CUDA tensor with contiguous rows")
+    out = torch.empty(b, nq, heads * head_dim, device=proj.device, dtype=torch.float32)
+    loc = attn = None
+    if want_loc_attn:
+        loc = torch.empty(b, nq, heads, levels, points, 2, device=proj.device, dtype=torch.float32)
+        attn = torch.empty(b, nq, heads, levels, points, device=proj.device, dtype=torch.float32)
+    if not value_buf.is_cuda or value_buf.dtype != torch.float32:
+        raise RuntimeError("value must be a CUDA float32 tensor")
+    rc = lib().sdetr_msda_fused_forward(
+        value_buf.data_ptr() + 4 * value_offset, value_batch_stride, value_token_stride,
+        _req(spatial_shapes, "spatial_shapes", torch.int64), _req(level_start_index, "level_start_index", torch.int64),
+        _req(ref_points, "reference_points", torch.float32), proj.data_ptr(), proj.stride(1), out.data_ptr(),
+        loc.data_ptr() if loc is not None else None, attn.data_ptr() if attn is not None else None, b, num_value,
+        heads, head_dim, levels, nq, points,
+        _req(query_order, "query_order", torch.int32) if query_order is not None else None, schedule, _stream())
+    _check(rc, "sdetr_msda_fused_forward")
+    return (out, loc, attn) if want_loc_attn else out
+
+
+def msda_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output):
+    """`_C.ms_deform_attn_backward` contract -> (grad_value, grad_sampling_loc, grad_attn_weight)."""
+    b, nv, m, d = value.shape
+    nq, L, P = sampling_loc.shape[1], sampling_loc.shape[3], sampling_loc.shape[4]
+    gv = torch.empty_like(value)
+    gl = torch.empty_like(sampling_loc)
+    ga = torch.empty_like(attn_weight)
+    rc = lib().sdetr_msda_backward(
+        _req(value, "value", torch.float32), _req(spatial_shapes, "spatial_shapes", torch.int64),
+        _req(level_start_index, "level_start_index", torch.int64), _req(sampling_loc, "sampling_loc", torch.float32),
+        _req(attn_weight, "attn_weight", torch.float32), _req(grad_output, "grad_output", torch.float32),
+        gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), b, nv, m, d, L, nq, P, _stream())
+    _check(rc, "sdetr_msda_backward")
+    return gv, gl, ga
+
+
+# ---- salience filter --------------------------------------------------------------------------------------
+def salience_select(raw_score, mask_u8, level_start: Sequence[int], level_size: Sequence[int],
+                    level_k: Sequence[int], level_width: Optional[Sequence[int]] = None,
+                    level_stride: Optional[Sequence[int]] = None, cell_px: int = 0, workspace=None):
+    """-> selected_inds (b,K) i64, selected_score (b,K), foreground_score (b,Nv), tile_order (b,K) i32 | None."""
+    b, nv = raw_score.shape
+    L = len(level_k)
+    K = int(sum(level_k))
+    dev = raw_score.device
+    inds = torch.empty(b, K, device=dev, dtype=torch.int64)
+    score = torch.empty(b, K, device=dev, dtype=torch.float32)
+    fg = torch.empty(b, nv, device=dev, dtype=torch.float32)
+    want_order = level_width is not None and K > 0
+    order = torch.empty(b, K, device=dev, dtype=torch.int32) if want_order else None
+    need = lib().sdetr_salience_select_workspace(b, nv, L)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, device=dev, dtype=torch.uint8)
+    rc = lib().sdetr_salience_select(
+        _req(raw_score, "raw_score", torch.float32), _req(mask_u8, "mask", torch.uint8), _host_i32(level_start),
+        _host_i32(level_size), _host_i32(level_k), _host_i32(level_width) if want_order else None,
+        _host_i32(level_stride) if want_order else None, cell_px, b, nv, L, inds.data_ptr(), score.data_ptr(),
+        fg.data_ptr(), order.data_ptr() if want_order else None, workspace.data_ptr(), workspace.numel(), _stream())
+    _check(rc, "sdetr_salience_select")
+    return inds, score, fg, order
+
+
+def order_prefixes(tile_order, nq_list: Sequence[int]):
+    """-> list of (b, nq_j) int32 processing orders, one per encoder layer."""
+    b, K = tile_order.shape
+    offs, tot = [], 0
+    for n in nq_list:
+        offs.append(tot)
+        tot += b * int(n)
+    out = torch.empty(max(tot, 1), device=tile_order.device, dtype=torch.int32)
+    rc = lib().sdetr_order_prefixes(_req(tile_order, "tile_order", torch.int32), b, K, len(nq_list),
+                                    _host_i32(nq_list), _host_i64(offs), out.data_ptr(), _stream())
+    _check(rc, "sdetr_order_prefixes")
+    return [out[o:o + b * int(n)].view(b, int(n)) for o, n in zip(offs, nq_list)]
+
+
+def topk_desc(score, k: int, workspace=None):
+    """(segments, n) -> (segments, k) int64 positions of the k largest (ties: smaller position first)."""
+    seg, n = score.shape
+    out = torch.empty(seg, k, device=score.device, dtype=torch.int64)
+    need = lib().sdetr_topk_workspace(seg, n)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, device=score.device, dtype=torch.uint8)
+    rc = lib().sdetr_topk_desc(_req(score, "score", torch.float32), seg, n, k, out.data_ptr(), workspace.data_ptr(),
+                               workspace.numel(), _stream())
+    _check(rc, "sdetr_topk_desc")
+    return out
+
+
+# ---- token movement -----------------------------------------------------------------------------------------
+def _inds_view(inds, num_query):
+    if not (inds.is_cuda and inds.dtype == torch.int64 and inds.stride(1) == 1 and inds.shape[1] >= num_query):
+        raise RuntimeError("inds must be a CUDA int64 tensor with unit column stride")
+    return inds.data_ptr(), inds.stride(0)
+
+
+def token_gather(tokens, pos, fg, valid_ratios, inds, spatial_shapes, level_start_index, num_query):
+    b, nv, c = tokens.shape
+    L = spatial_shapes.shape[0]
+    dev = tokens.device
+    q = torch.empty(b, num_query, c, device=dev, dtype=torch.float32)
+    qp = torch.empty(b, num_query, c, device=dev, dtype=torch.float32)
+    fq = torch.empty(b, num_query, device=dev, dtype=torch.float32)
+    rq = torch.empty(b, num_query, L, 2, device=dev, dtype=torch.float32)
+    ip, istride = _inds_view(inds, num_query)
+    rc = lib().sdetr_token_gather(
+        _req(tokens, "tokens", torch.float32), _req(pos, "pos", torch.float32), _req(fg, "fg", torch.float32),
+        _req(valid_ratios, "valid_ratios", torch.float32), ip, istride, _req(spatial_shapes, "spatial_shapes", torch.int64),
+        _req(level_start_index, "level_start_index", torch.int64), b, nv, c, L, num_query, q.data_ptr(), qp.data_ptr(),
+        fq.data_ptr(), rq.data_ptr(), _stream())
+    _check(rc, "sdetr_token_gather")
+    return q, qp, fq, rq
+
+
+def token_scatter_(tokens, query, inds, focus_token_nums):
+    b, nv, c = tokens.shape
+    nq = query.shape[1]
+    ip, istride = _inds_view(inds, nq)
+    rc = lib().sdetr_token_scatter(_req(tokens, "tokens", torch.float32), _req(query, "query", torch.float32), ip,
+                                   istride, _req(focus_token_nums, "focus_token_nums", torch.int32), b, nv, c, nq,
+                                   _stream())
+    _check(rc, "sdetr_token_scatter")
+    return tokens
+
+
+def background_embed_(tokens, mask_u8, last_inds, row_embed, col_embed, spatial_shapes, level_start_index, flags=None):
+    b, nv, c = tokens.shape
+    num_last = last_inds.shape[1]
+    ip, istride = _inds_view(last_inds, num_last)
+    if flags is None:
+        flags = torch.empty(b, nv, device=tokens.device, dtype=torch.uint8)
+    rc = lib().sdetr_background_embed(
+        _req(tokens, "tokens", torch.float32), _req(mask_u8, "mask", torch.uint8), ip, istride, num_last,
+        _req(row_embed, "row_embed", torch.float32), _req(col_embed, "col_embed", torch.float32),
+        _req(spatial_shapes, "spatial_shapes", torch.int64), _req(level_start_index, "level_start_index", torch.int64),
+        b, nv, c, spatial_shapes.shape[0], _req(flags, "flags", torch.uint8), _stream())
+    _check(rc, "sdetr_background_embed")
+    return tokens
+
+
+def score_modulate(mem_all, level_start: int, H: int, W: int, coarse_score, Hc: int, Wc: int, alpha, alpha_index: int):
+    """mem_all (b,Nv,C) contiguous; the level slice starts at token ``level_start``.  coarse_score (b,Hc*Wc) rows
+    (any batch stride).  -> (b,H*W,C)."""
+    b, nv, c = mem_all.shape
+    out = torch.empty(b, H * W, c, device=mem_all.device, dtype=torch.float32)
+    if not (coarse_score.is_cuda and coarse_score.stride(1) == 1 and coarse_score.dtype == torch.float32):
+        raise RuntimeError("coarse_score rows must be contiguous CUDA float32")
+    rc = lib().sdetr_score_modulate(
+        _req(mem_all, "mem", torch.float32) + 4 * level_start * c, nv * c, coarse_score.data_ptr(),
+        coarse_score.stride(0), _req(alpha, "alpha", torch.float32), alpha_index, b, H, W, Hc, Wc, c, out.data_ptr(),
+        _stream())
+    _check(rc, "sdetr_score_modulate")
+    return out
+
+
+def zero_masked_rows_(buf, row_stride: int, row_floats: int, mask_u8, num_rows: int, offset_floats: int = 0):
+    rc = lib().sdetr_zero_masked_rows(buf.data_ptr() + 4 * offset_floats, row_stride, row_floats,
+                                      _req(mask_u8, "mask", torch.uint8), num_rows, _stream())
+    _check(rc, "sdetr_zero_masked_rows")
+    return buf
+
+
+def class_max_times_fg(logits, fg):
+    rows = fg.numel()
+    out = torch.empty_like(fg)
+    rc = lib().sdetr_class_max_times_fg(_req(logits, "logits", torch.float32), _req(fg, "fg", torch.float32), rows,
+                                        logits.shape[-1], out.data_ptr(), _stream())
+    _check(rc, "sdetr_class_max_times_fg")
+    return out
+
+
+def add_layernorm(x, r, gamma, beta, eps: float = 1e-5, out=None):
+    """LayerNorm(x + r); r may be None; out may alias x."""
+    c = x.shape[-1]
+    rows = x.numel() // c
+    if out is None:
+        out = torch.empty_like(x)
+    rc = lib().sdetr_add_layernorm(_req(x, "x", torch.float32), _req(r, "r", torch.float32) if r is not None else None,
+                                   _req(gamma, "gamma", torch.float32), _req(beta, "beta", torch.float32), eps, rows, c,
+                                   out.data_ptr(), _stream())
+    _check(rc, "sdetr_add_layernorm")
+    return out

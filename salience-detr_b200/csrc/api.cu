@@ -1,0 +1,23 @@
+// Library-level entry points: version, thread-local error string, launch counter.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace sdetr {
+static thread_local char g_error[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+}  // namespace sdetr
+
+extern "C" int sdetr_version(void) { return 100; }  // 0.1.0
+extern "C" const char *sdetr_last_error(void) { return sdetr::g_error; }
+extern "C" unsigned long long sdetr_launch_count(void) { return sdetr::g_launches.load(std::memory_order_relaxed); }

@@ -1,0 +1,381 @@
+// Hierarchical salience token filter for sm_100a -- sdetr_salience_select, sdetr_order_prefixes,
+// sdetr_topk_desc.
+//
+// Reference semantics: models/bricks/salience_transformer.py:146-168 (masked_fill with the batch-global
+// minimum, per-level topk, concatenate + descending sort + gather, foreground score) and :366-367
+// (top-k of the pre-attention).  The reference expands this into ~25 ATen launches per level plus
+// host synchronisations (`topk(k=tensor)`); here the whole filter is five small kernels with no host
+// round trip.
+//
+// Core primitive: a segmented LSD radix sort, one 1024-thread CTA per segment, 8-bit digits, keys are
+// fp32 scores mapped to uint32 so that ascending key order == descending score order.  The sort is
+// STABLE and the initial order is the token index, so equal scores come out by ascending index -- the
+// canonical tie order shared with the oracle (torch leaves it unspecified).  Ranking inside a warp
+// uses __match_any_sync; per-warp digit histograms live in shared memory; data ping-pongs through
+// global (L2-resident) buffers, so any segment length works (level 0 of the 5-scale config: 67 200).
+#include "common.cuh"
+
+namespace sdetr {
+
+constexpr int kSortThreads = 1024;
+constexpr int kSortWarps = kSortThreads / 32;
+
+struct LevelTable {
+    int L;
+    int start[kMaxLevels], size[kMaxLevels], k[kMaxLevels], koff[kMaxLevels + 1];
+    int width[kMaxLevels], stride[kMaxLevels];
+};
+
+struct SortSmem {
+    uint32_t hist[256 * kSortWarps];  // [digit][warp]
+    uint32_t warp_tot[kSortWarps];
+};
+
+// One radix pass over `n` elements.  load(i) -> (key, val);  results to (dk, dv).
+template <class Load>
+__device__ __forceinline__ void radix_pass(Load load, int n, int shift, uint32_t *dk, uint32_t *dv, SortSmem &sm) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunk = (((n + kSortWarps - 1) / kSortWarps) + 31) & ~31;
+    const int begin = warp * chunk, end = min(n, begin + chunk);
+    for (int i = tid; i < 256 * kSortWarps; i += kSortThreads) sm.hist[i] = 0;
+    __syncthreads();
+    // A: per-warp digit histogram
+    for (int base = begin; base < end; base += 32) {
+        const int i = base + lane;
+        const bool valid = i < end;
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            uint32_t key, val;
+            load(i, key, val);
+            const uint32_t d = (key >> shift) & 255u;
+            const unsigned peers = __match_any_sync(act, d);
+            if (lane == __ffs(peers) - 1) sm.hist[d * kSortWarps + warp] += __popc(peers);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    // B: exclusive scan over hist in (digit, warp) order; thread t owns entries [8t, 8t+8)
+    {
+        uint32_t v[8], s = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = sm.hist[tid * 8 + j], s += v[j];
+        uint32_t inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) sm.warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = sm.warp_tot[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            sm.warp_tot[lane] = winc - w;
+        }
+        __syncthreads();
+        uint32_t run = sm.warp_tot[warp] + inc - s;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sm.hist[tid * 8 + j] = run, run += v[j];
+    }
+    __syncthreads();
+    // C: stable scatter
+    for (int base = begin; base < end; base += 32) {
+        const int i = base + lane;
+        const bool valid = i < end;
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            uint32_t key, val;
+            load(i, key, val);
+            const uint32_t d = (key >> shift) & 255u;
+            const unsigned peers = __match_any_sync(act, d);
+            const uint32_t pos = sm.hist[d * kSortWarps + warp] + __popc(peers & ((1u << lane) - 1u));
+            dk[pos] = key, dv[pos] = val;
+            __syncwarp(peers);
+            if (lane == __ffs(peers) - 1) sm.hist[d * kSortWarps + warp] += __popc(peers);
+        }
+        __syncwarp();
+    }
+    __syncthreads();  // also makes the global writes of this pass visible to the whole CTA
+}
+
+// Full 32-bit sort: load0 -> a -> b -> a -> b.  Result in (kb, vb).
+template <class Load0>
+__device__ __forceinline__ void block_radix_sort(Load0 load0, int n, uint32_t *ka, uint32_t *va, uint32_t *kb,
+                                                 uint32_t *vb, SortSmem &sm) {
+    radix_pass(load0, n, 0, ka, va, sm);
+    // plain (coherent) loads: these buffers are written by this same kernel
+    auto from_a = [=](int i, uint32_t &k, uint32_t &v) { k = ((volatile uint32_t *)ka)[i], v = ((volatile uint32_t *)va)[i]; };
+    auto from_b = [=](int i, uint32_t &k, uint32_t &v) { k = ((volatile uint32_t *)kb)[i], v = ((volatile uint32_t *)vb)[i]; };
+    radix_pass(from_a, n, 8, kb, vb, sm);
+    radix_pass(from_b, n, 16, ka, va, sm);
+    radix_pass(from_a, n, 24, kb, vb, sm);
+}
+
+// ---- kernels ---------------------------------------------------------------------------------------------
+
+// per-level minimum over the whole (batch, HW_l) score tensor (salience_transformer.py:146 `score.min()`)
+__global__ void __launch_bounds__(1024) level_min_kernel(const float *__restrict__ raw, LevelTable tb, int batch,
+                                                         int nv, float *__restrict__ lmin) {
+    __shared__ float red[32];
+    const int l = blockIdx.x;
+    float m = INFINITY;
+    const int total = batch * tb.size[l];
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int b = i / tb.size[l], t = i - b * tb.size[l];
+        m = fminf(m, __ldg(raw + (int64_t)b * nv + tb.start[l] + t));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = red[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) lmin[l] = m;
+    }
+}
+
+// foreground_score = where(mask, global min, raw)  (salience_transformer.py:166-168)
+__global__ void foreground_kernel(const float *__restrict__ raw, const uint8_t *__restrict__ mask,
+                                  const float *__restrict__ lmin, int L, int64_t total, float *__restrict__ fg) {
+    float g = INFINITY;
+    for (int l = 0; l < L; ++l) g = fminf(g, __ldg(lmin + l));
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        fg[i] = mask[i] ? g : raw[i];
+}
+
+// segment = (image, level): sort every token of the level by (filled score desc, index asc)
+__global__ void __launch_bounds__(kSortThreads) level_sort_kernel(const float *__restrict__ raw,
+                                                                  const uint8_t *__restrict__ mask,
+                                                                  const float *__restrict__ lmin, LevelTable tb, int nv,
+                                                                  uint32_t *ka, uint32_t *va, uint32_t *kb,
+                                                                  uint32_t *vb) {
+    __shared__ SortSmem sm;
+    const int b = blockIdx.x / tb.L, l = blockIdx.x % tb.L;
+    const int64_t off = (int64_t)b * nv + tb.start[l];
+    const float fill = __ldg(lmin + l);
+    const int start = tb.start[l];
+    auto load0 = [=](int i, uint32_t &k, uint32_t &v) {
+        const float s = __ldg(mask + off + i) ? fill : __ldg(raw + off + i);
+        k = desc_key(s), v = (uint32_t)(start + i);
+    };
+    block_radix_sort(load0, tb.size[l], ka + off, va + off, kb + off, vb + off, sm);
+}
+
+// segment = image: merge the per-level top-k_l prefixes by one more sort (cat + sort + gather, :156-158),
+// then emit selected_inds / selected_score.
+__global__ void __launch_bounds__(kSortThreads) merge_sort_kernel(const uint32_t *lk, const uint32_t *lv, LevelTable tb,
+                                                                  int nv, int K, uint32_t *ka, uint32_t *va,
+                                                                  uint32_t *kb, uint32_t *vb,
+                                                                  int64_t *__restrict__ sel_inds,
+                                                                  float *__restrict__ sel_score) {
+    __shared__ SortSmem sm;
+    const int b = blockIdx.x;
+    const int64_t src = (int64_t)b * nv, dst = (int64_t)b * K;
+    auto load0 = [=](int j, uint32_t &k, uint32_t &v) {
+        int l = 0;
+#pragma unroll
+        for (int t = 1; t < kMaxLevels; ++t)
+            if (t < tb.L && j >= tb.koff[t]) l = t;
+        const int64_t s = src + tb.start[l] + (j - tb.koff[l]);
+        k = lk[s], v = lv[s];
+    };
+    block_radix_sort(load0, K, ka + dst, va + dst, kb + dst, vb + dst, sm);
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+        sel_inds[dst + j] = (int64_t)((volatile uint32_t *)vb)[dst + j];
+        sel_score[dst + j] = desc_key_inv(((volatile uint32_t *)kb)[dst + j]);
+    }
+}
+
+// segment = image: order the K selected positions by the spatial cell of their token
+__global__ void __launch_bounds__(kSortThreads) tile_order_kernel(const uint32_t *sel_tok /* (b,K) token index */,
+                                                                  LevelTable tb, int K, int cell_px, int cells_x,
+                                                                  uint32_t *ka, uint32_t *va, uint32_t *kb,
+                                                                  uint32_t *vb, int32_t *__restrict__ tile_order) {
+    __shared__ SortSmem sm;
+    const int b = blockIdx.x;
+    const int64_t dst = (int64_t)b * K;
+    auto load0 = [=](int j, uint32_t &k, uint32_t &v) {
+        const int t = (int)sel_tok[dst + j];
+        int l = 0;
+#pragma unroll
+        for (int u = 1; u < kMaxLevels; ++u)
+            if (u < tb.L && t >= tb.start[u]) l = u;
+        const int r = t - tb.start[l];
+        const int y = r / tb.width[l], x = r - y * tb.width[l];
+        const int cy = (y * tb.stride[l] + tb.stride[l] / 2) / cell_px;
+        const int cx = (x * tb.stride[l] + tb.stride[l] / 2) / cell_px;
+        k = ((uint32_t)(cy * cells_x + cx) << 3) | (uint32_t)l;
+        v = (uint32_t)j;
+    };
+    block_radix_sort(load0, K, ka + dst, va + dst, kb + dst, vb + dst, sm);
+    for (int j = threadIdx.x; j < K; j += blockDim.x) tile_order[dst + j] = (int32_t)((volatile uint32_t *)vb)[dst + j];
+}
+
+// (image, layer): positions < nq_j of tile_order, order preserved (stream compaction)
+struct PrefixTable {
+    int layers;
+    int nq[16];
+    int64_t off[16];
+};
+__global__ void __launch_bounds__(1024) order_prefix_kernel(const int32_t *__restrict__ tile_order, int K,
+                                                            PrefixTable pt, int32_t *__restrict__ out) {
+    __shared__ int warp_cnt[32];
+    __shared__ int base_s;
+    const int b = blockIdx.x, j = blockIdx.y;
+    const int nq = pt.nq[j];
+    int32_t *dst = out + pt.off[j] + (int64_t)b * nq;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();
+    for (int s = 0; s < K; s += blockDim.x) {
+        const int i = s + threadIdx.x;
+        const int pos = i < K ? __ldg(tile_order + (int64_t)b * K + i) : K;
+        const bool keep = pos < nq;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, tot = 0;
+        for (int w = 0; w < 32; ++w) {
+            const int c = warp_cnt[w];
+            before += (w < warp) ? c : 0;
+            tot += c;
+        }
+        const int base = base_s;
+        if (keep) dst[base + before + __popc(bal & ((1u << lane) - 1u))] = pos;
+        __syncthreads();
+        if (threadIdx.x == 0) base_s = base + tot;
+        __syncthreads();
+    }
+}
+
+// generic segmented top-k (descending, ties by position): salience_transformer.py:366-367
+__global__ void __launch_bounds__(kSortThreads) topk_kernel(const float *__restrict__ score, int n, int k, uint32_t *ka,
+                                                            uint32_t *va, uint32_t *kb, uint32_t *vb,
+                                                            int64_t *__restrict__ out) {
+    __shared__ SortSmem sm;
+    const int64_t off = (int64_t)blockIdx.x * n;
+    auto load0 = [=](int i, uint32_t &key, uint32_t &v) { key = desc_key(__ldg(score + off + i)), v = (uint32_t)i; };
+    block_radix_sort(load0, n, ka + off, va + off, kb + off, vb + off, sm);
+    for (int j = threadIdx.x; j < k; j += blockDim.x)
+        out[(int64_t)blockIdx.x * k + j] = (int64_t)((volatile uint32_t *)vb)[off + j];
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace sdetr
+
+using namespace sdetr;
+
+extern "C" size_t sdetr_salience_select_workspace(int batch, int num_value, int num_levels) {
+    (void)num_levels;
+    // level minima + 4 level-sort buffers (b*Nv u32) + 4 merge/tile-sort buffers (b*K <= b*Nv u32)
+    return 256 + 8 * align256((size_t)batch * num_value * sizeof(uint32_t));
+}
+
+extern "C" int sdetr_salience_select(const float *raw_score, const uint8_t *mask, const int32_t *level_start_host,
+                                     const int32_t *level_size_host, const int32_t *level_k_host,
+                                     const int32_t *level_width_host, const int32_t *level_stride_host, int cell_px,
+                                     int batch, int num_value, int num_levels, int64_t *selected_inds,
+                                     float *selected_score, float *foreground_score, int32_t *tile_order,
+                                     void *workspace, size_t workspace_bytes, sdetr_stream_t stream) {
+    SDETR_REQUIRE(raw_score && mask && level_start_host && level_size_host && level_k_host && selected_inds &&
+                      selected_score && foreground_score && workspace,
+                  SDETR_ERR_INVALID_ARG, "salience_select: null pointer");
+    SDETR_REQUIRE(batch > 0 && num_value > 0 && num_levels > 0 && num_levels <= kMaxLevels, SDETR_ERR_INVALID_ARG,
+                  "salience_select: bad sizes (batch %d, num_value %d, levels %d)", batch, num_value, num_levels);
+    SDETR_REQUIRE(workspace_bytes >= sdetr_salience_select_workspace(batch, num_value, num_levels),
+                  SDETR_ERR_WORKSPACE, "salience_select: workspace too small");
+    SDETR_REQUIRE(!tile_order || (level_width_host && level_stride_host && cell_px > 0), SDETR_ERR_INVALID_ARG,
+                  "salience_select: tile_order needs level widths/strides and cell_px");
+    LevelTable tb{};
+    tb.L = num_levels;
+    int K = 0, cover = 0, max_w_px = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        tb.start[l] = level_start_host[l], tb.size[l] = level_size_host[l], tb.k[l] = level_k_host[l];
+        tb.koff[l] = K;
+        SDETR_REQUIRE(tb.k[l] >= 0 && tb.k[l] <= tb.size[l] && tb.start[l] == cover, SDETR_ERR_INVALID_ARG,
+                      "salience_select: level %d: k=%d size=%d start=%d", l, tb.k[l], tb.size[l], tb.start[l]);
+        K += tb.k[l];
+        cover += tb.size[l];
+        if (tile_order) {
+            tb.width[l] = level_width_host[l], tb.stride[l] = level_stride_host[l];
+            SDETR_REQUIRE(tb.width[l] > 0 && tb.stride[l] > 0, SDETR_ERR_INVALID_ARG, "salience_select: bad width/stride");
+            if (tb.width[l] * tb.stride[l] > max_w_px) max_w_px = tb.width[l] * tb.stride[l];
+        }
+    }
+    tb.koff[num_levels] = K;
+    SDETR_REQUIRE(cover == num_value, SDETR_ERR_INVALID_ARG, "salience_select: levels cover %d of %d tokens", cover,
+                  num_value);
+    cudaStream_t s = (cudaStream_t)stream;
+    char *ws = (char *)workspace;
+    float *lmin = (float *)ws;
+    const size_t bufsz = align256((size_t)batch * num_value * sizeof(uint32_t));
+    uint32_t *buf[8];
+    for (int i = 0; i < 8; ++i) buf[i] = (uint32_t *)(ws + 256 + i * bufsz);
+
+    level_min_kernel<<<num_levels, 1024, 0, s>>>(raw_score, tb, batch, num_value, lmin);
+    int rc = check_launch("salience_select/level_min");
+    if (rc) return rc;
+    const int64_t total = (int64_t)batch * num_value;
+    const int64_t fg_blocks = (total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8;
+    foreground_kernel<<<(unsigned)fg_blocks, 256, 0, s>>>(raw_score, mask, lmin, num_levels, total, foreground_score);
+    if ((rc = check_launch("salience_select/foreground"))) return rc;
+    level_sort_kernel<<<batch * num_levels, kSortThreads, 0, s>>>(raw_score, mask, lmin, tb, num_value, buf[0], buf[1],
+                                                                  buf[2], buf[3]);
+    if ((rc = check_launch("salience_select/level_sort"))) return rc;
+    if (K == 0) return SDETR_OK;
+    merge_sort_kernel<<<batch, kSortThreads, 0, s>>>(buf[2], buf[3], tb, num_value, K, buf[4], buf[5], buf[6], buf[7],
+                                                     selected_inds, selected_score);
+    if ((rc = check_launch("salience_select/merge_sort"))) return rc;
+    if (tile_order) {
+        const int cells_x = (max_w_px + cell_px - 1) / cell_px + 1;
+        // sorted token indices are in buf[7]; reuse the level-sort buffers as ping-pong space
+        tile_order_kernel<<<batch, kSortThreads, 0, s>>>(buf[7], tb, K, cell_px, cells_x, buf[0], buf[1], buf[2], buf[3],
+                                                         tile_order);
+        if ((rc = check_launch("salience_select/tile_order"))) return rc;
+    }
+    return SDETR_OK;
+}
+
+extern "C" int sdetr_order_prefixes(const int32_t *tile_order, int batch, int K, int num_layers,
+                                    const int32_t *nq_host, const int64_t *order_offset_host, int32_t *out_orders,
+                                    sdetr_stream_t stream) {
+    SDETR_REQUIRE(tile_order && nq_host && order_offset_host && out_orders, SDETR_ERR_INVALID_ARG,
+                  "order_prefixes: null pointer");
+    SDETR_REQUIRE(batch > 0 && K > 0 && num_layers > 0 && num_layers <= 16, SDETR_ERR_INVALID_ARG,
+                  "order_prefixes: bad sizes");
+    PrefixTable pt{};
+    pt.layers = num_layers;
+    for (int j = 0; j < num_layers; ++j) {
+        SDETR_REQUIRE(nq_host[j] >= 0 && nq_host[j] <= K, SDETR_ERR_INVALID_ARG, "order_prefixes: nq[%d]=%d > K=%d", j,
+                      nq_host[j], K);
+        pt.nq[j] = nq_host[j], pt.off[j] = order_offset_host[j];
+    }
+    order_prefix_kernel<<<dim3(batch, num_layers), 1024, 0, (cudaStream_t)stream>>>(tile_order, K, pt, out_orders);
+    return check_launch("order_prefixes");
+}
+
+extern "C" size_t sdetr_topk_workspace(int segments, int n) {
+    return 4 * align256((size_t)segments * n * sizeof(uint32_t));
+}
+
+extern "C" int sdetr_topk_desc(const float *score, int segments, int n, int k, int64_t *topk_index, void *workspace,
+                               size_t workspace_bytes, sdetr_stream_t stream) {
+    SDETR_REQUIRE(score && topk_index && workspace, SDETR_ERR_INVALID_ARG, "topk_desc: null pointer");
+    SDETR_REQUIRE(segments > 0 && n > 0 && k >= 0 && k <= n, SDETR_ERR_INVALID_ARG, "topk_desc: k=%d n=%d", k, n);
+    SDETR_REQUIRE(workspace_bytes >= sdetr_topk_workspace(segments, n), SDETR_ERR_WORKSPACE,
+                  "topk_desc: workspace too small");
+    const size_t bufsz = align256((size_t)segments * n * sizeof(uint32_t));
+    char *ws = (char *)workspace;
+    topk_kernel<<<segments, kSortThreads, 0, (cudaStream_t)stream>>>(score, n, k, (uint32_t *)ws,
+                                                                     (uint32_t *)(ws + bufsz),
+                                                                     (uint32_t *)(ws + 2 * bufsz),
+                                                                     (uint32_t *)(ws + 3 * bufsz), topk_index);
+    return check_launch("topk_desc");
+}

@@ -1,0 +1,361 @@
+// Token movement and small fused elementwise kernels around the encoder layers (sm_100a).
+//
+// Reference semantics: models/bricks/salience_transformer.py:134-143 (score modulation), :366 (mc score),
+// :390-391/:349-350 (residual + LayerNorm), :417-432 + :454-461 (reference points + four gathers),
+// :474-485 (scatter back), :488-495 + position_encoding.py:81-95 (background embedding),
+// models/bricks/ms_deform_attn.py:318-319 (zero the value rows of padded tokens).
+//
+// All kernels are HBM-streaming: one warp owns one token row and moves it with 128-bit loads/stores,
+// several independent loads in flight per lane; index/mask lookups are warp-uniform.
+#include "common.cuh"
+
+namespace sdetr {
+
+constexpr int kRowThreads = 256;  // 8 warps = 8 rows per CTA
+
+struct LevelsDev {
+    int L;
+    int H[kMaxLevels], W[kMaxLevels];
+    int64_t start[kMaxLevels];
+};
+
+__device__ __forceinline__ void load_levels(LevelsDev &lv, const int64_t *shapes, const int64_t *lsi, int L) {
+    lv.L = L;
+#pragma unroll
+    for (int l = 0; l < kMaxLevels; ++l)
+        if (l < L) {
+            lv.H[l] = (int)__ldg(shapes + 2 * l), lv.W[l] = (int)__ldg(shapes + 2 * l + 1);
+            lv.start[l] = __ldg(lsi + l);
+        }
+}
+__device__ __forceinline__ void token_to_lyx(const LevelsDev &lv, int64_t t, int &l, int &y, int &x) {
+    l = 0;
+#pragma unroll
+    for (int u = 1; u < kMaxLevels; ++u)
+        if (u < lv.L && t >= lv.start[u]) l = u;
+    int Wl = lv.W[0];
+    int64_t st = lv.start[0];
+#pragma unroll
+    for (int u = 1; u < kMaxLevels; ++u)
+        if (u == l) Wl = lv.W[u], st = lv.start[u];
+    const int r = (int)(t - st);
+    y = r / Wl, x = r - y * Wl;
+}
+
+// ---- gather (:454-461) ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowThreads) token_gather_kernel(
+    const float *__restrict__ tokens, const float *__restrict__ pos, const float *__restrict__ fg,
+    const float *__restrict__ vr, const int64_t *__restrict__ inds, int64_t inds_stride,
+    const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi, int batch, int nv, int C, int L, int nq,
+    float *__restrict__ query, float *__restrict__ query_pos, float *__restrict__ fg_q, float *__restrict__ ref_q) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+    if (row >= (int64_t)batch * nq) return;
+    const int b = (int)(row / nq), q = (int)(row - (int64_t)b * nq);
+    const int64_t t = __ldg(inds + (int64_t)b * inds_stride + q);
+    const float *src_t = tokens + ((int64_t)b * nv + t) * C;
+    const float *src_p = pos + ((int64_t)b * nv + t) * C;
+    float *dst_t = query + row * C, *dst_p = query_pos + row * C;
+    for (int c = lane * 4; c < C; c += 256) {  // two rows x two 128-bit loads in flight per lane
+        const bool two = c + 128 < C;
+        const float4 a0 = ld_stream_f4(src_t + c), p0 = ld_stream_f4(src_p + c);
+        float4 a1, p1;
+        if (two) a1 = ld_stream_f4(src_t + c + 128), p1 = ld_stream_f4(src_p + c + 128);
+        st_stream_f4(dst_t + c, a0), st_stream_f4(dst_p + c, p0);
+        if (two) st_stream_f4(dst_t + c + 128, a1), st_stream_f4(dst_p + c + 128, p1);
+    }
+    if (lane == 0) fg_q[row] = __ldg(fg + (int64_t)b * nv + t);
+    // reference points (:417-432): ((x+.5)/(vr_x*W), (y+.5)/(vr_y*H)) of the token's own level, times every
+    // level's valid ratio -- same fp32 operations in the same order as the reference
+    LevelsDev lv;
+    load_levels(lv, shapes, lsi, L);
+    int l, y, x;
+    token_to_lyx(lv, t, l, y, x);
+    int Hl = lv.H[0], Wl = lv.W[0];
+#pragma unroll
+    for (int u = 1; u < kMaxLevels; ++u)
+        if (u == l) Hl = lv.H[u], Wl = lv.W[u];
+    const float *v = vr + (int64_t)b * L * 2;
+    const float rx = ((float)x + 0.5f) / (__ldg(v + 2 * l) * (float)Wl);
+    const float ry = ((float)y + 0.5f) / (__ldg(v + 2 * l + 1) * (float)Hl);
+    if (lane < L)
+        *reinterpret_cast<float2 *>(ref_q + (row * L + lane) * 2) =
+            make_float2(rx * __ldg(v + 2 * lane), ry * __ldg(v + 2 * lane + 1));
+}
+
+// ---- scatter back (:474-485) ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowThreads) token_scatter_kernel(float *__restrict__ tokens,
+                                                                    const float *__restrict__ query,
+                                                                    const int64_t *__restrict__ inds,
+                                                                    int64_t inds_stride,
+                                                                    const int32_t *__restrict__ focus, int batch,
+                                                                    int nv, int C, int nq) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+    if (row >= (int64_t)batch * nq) return;
+    const int b = (int)(row / nq), q = (int)(row - (int64_t)b * nq);
+    if (q >= __ldg(focus + b)) return;  // only the first focus_token_nums[b] rows are written back
+    const int64_t t = __ldg(inds + (int64_t)b * inds_stride + q);
+    const float *src = query + row * C;
+    float *dst = tokens + ((int64_t)b * nv + t) * C;
+    for (int c = lane * 4; c < C; c += 256) {
+        const bool two = c + 128 < C;
+        const float4 a0 = ld_stream_f4(src + c);
+        float4 a1;
+        if (two) a1 = ld_stream_f4(src + c + 128);
+        st_stream_f4(dst + c, a0);
+        if (two) st_stream_f4(dst + c + 128, a1);
+    }
+}
+
+// ---- background embedding (:488-495) --------------------------------------------------------------------
+__global__ void mark_flags_kernel(const int64_t *__restrict__ inds, int64_t inds_stride, int num, int batch, int nv,
+                                  uint8_t *__restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)batch * num) return;
+    const int b = (int)(i / num), q = (int)(i - (int64_t)b * num);
+    flags[(int64_t)b * nv + __ldg(inds + (int64_t)b * inds_stride + q)] = 1;
+}
+
+__global__ void __launch_bounds__(kRowThreads) background_embed_kernel(
+    float *__restrict__ tokens, const uint8_t *__restrict__ mask, const uint8_t *__restrict__ flags,
+    const float *__restrict__ row_embed, const float *__restrict__ col_embed, const int64_t *__restrict__ shapes,
+    const int64_t *__restrict__ lsi, int batch, int nv, int C, int L) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+    if (row >= (int64_t)batch * nv) return;
+    if (__ldg(mask + row) || flags[row]) return;
+    const int t = (int)(row % nv);
+    LevelsDev lv;
+    load_levels(lv, shapes, lsi, L);
+    int l, y, x;
+    token_to_lyx(lv, t, l, y, x);
+    const int half = C / 2;
+    float *dst = tokens + row * C;
+    for (int c = lane * 4; c < C; c += 128) {
+        const float *e = c < half ? col_embed + (int64_t)x * half + c : row_embed + (int64_t)y * half + (c - half);
+        const float4 ev = ldg_f4(e);
+        float4 v = *reinterpret_cast<float4 *>(dst + c);
+        v.x += ev.x, v.y += ev.y, v.z += ev.z, v.w += ev.w;
+        *reinterpret_cast<float4 *>(dst + c) = v;
+    }
+}
+
+// ---- coarse-to-fine score modulation (:134-143) -----------------------------------------------------------
+__global__ void __launch_bounds__(kRowThreads) score_modulate_kernel(const float *__restrict__ mem, int64_t mem_bs,
+                                                                     const float *__restrict__ coarse, int64_t coarse_bs,
+                                                                     const float *__restrict__ alpha, int alpha_index,
+                                                                     int batch, int H, int W, int Hc, int Wc, int C,
+                                                                     float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+    const int HW = H * W;
+    if (row >= (int64_t)batch * HW) return;
+    const int b = (int)(row / HW), r = (int)(row - (int64_t)b * HW);
+    const int y = r / W, x = r - y * W;
+    // ATen upsample_bilinear2d, align_corners=True: src = dst * (in-1)/(out-1)
+    const float sy = H > 1 ? (float)(Hc - 1) / (float)(H - 1) : 0.f;
+    const float sx = W > 1 ? (float)(Wc - 1) / (float)(W - 1) : 0.f;
+    const float fy = sy * (float)y, fx = sx * (float)x;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < Hc - 1 ? 1 : 0), x1 = x0 + (x0 < Wc - 1 ? 1 : 0);
+    const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+    const float *cs = coarse + (int64_t)b * coarse_bs;
+    const float up = hy * (hx * __ldg(cs + y0 * Wc + x0) + lx * __ldg(cs + y0 * Wc + x1)) +
+                     ly * (hx * __ldg(cs + y1 * Wc + x0) + lx * __ldg(cs + y1 * Wc + x1));
+    const float a = __ldg(alpha + alpha_index);
+    const float *src = mem + (int64_t)b * mem_bs + (int64_t)r * C;
+    float *dst = out + row * C;
+    for (int c = lane * 4; c < C; c += 128) {
+        const float4 m = ld_stream_f4(src + c);
+        float4 o;
+        o.x = m.x + m.x * up * a, o.y = m.y + m.y * up * a, o.z = m.z + m.z * up * a, o.w = m.w + m.w * up * a;
+        *reinterpret_cast<float4 *>(dst + c) = o;
+    }
+}
+
+// ---- zero the value rows of padded tokens (ms_deform_attn.py:318-319) ------------------------------------
+__global__ void __launch_bounds__(kRowThreads) zero_masked_rows_kernel(float *__restrict__ rows, int64_t row_stride,
+                                                                       int row_floats,
+                                                                       const uint8_t *__restrict__ mask,
+                                                                       int64_t num_rows) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+    if (row >= num_rows || !__ldg(mask + row)) return;
+    float *dst = rows + row * row_stride;
+    for (int c = lane * 4; c < row_floats; c += 128) *reinterpret_cast<float4 *>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// ---- mc_score = max_c(logits) * fg (:366) ---------------------------------------------------------------
+__global__ void __launch_bounds__(kRowThreads) class_max_kernel(const float *__restrict__ logits,
+                                                                const float *__restrict__ fg, int64_t rows, int nc,
+                                                                float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float m = -INFINITY;
+    for (int c = lane; c < nc; c += 32) m = fmaxf(m, __ldg(logits + row * nc + c));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) out[row] = m * __ldg(fg + row);
+}
+
+// ---- y = LayerNorm(x + r) (:390-391, :349-350) ------------------------------------------------------------
+__global__ void __launch_bounds__(kRowThreads) add_layernorm_kernel(const float *x /* may alias y */,
+                                                                    const float *r,
+                                                                    const float *__restrict__ gamma,
+                                                                    const float *__restrict__ beta, float eps,
+                                                                    int64_t rows, int C, float *y) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float4 v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = i * 128 + lane * 4;
+        if (c < C) {
+            const float4 a = *reinterpret_cast<const float4 *>(x + row * C + c);
+            const float4 bb = r ? *reinterpret_cast<const float4 *>(r + row * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[i] = make_float4(a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w);
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = i * 128 + lane * 4;
+        if (c < C) {
+            const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+            ss += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = i * 128 + lane * 4;
+        if (c < C) {
+            const float4 g = ldg_f4(gamma + c), bt = ldg_f4(beta + c);
+            float4 o;
+            o.x = (v[i].x - mean) * rstd * g.x + bt.x, o.y = (v[i].y - mean) * rstd * g.y + bt.y;
+            o.z = (v[i].z - mean) * rstd * g.z + bt.z, o.w = (v[i].w - mean) * rstd * g.w + bt.w;
+            *reinterpret_cast<float4 *>(y + row * C + c) = o;
+        }
+    }
+}
+
+static inline unsigned row_blocks(int64_t rows) { return (unsigned)((rows + (kRowThreads / 32) - 1) / (kRowThreads / 32)); }
+
+}  // namespace sdetr
+
+using namespace sdetr;
+
+extern "C" int sdetr_token_gather(const float *tokens, const float *pos, const float *fg, const float *valid_ratios,
+                                  const int64_t *inds, int64_t inds_stride, const int64_t *spatial_shapes,
+                                  const int64_t *level_start_index, int batch, int num_value, int channels,
+                                  int num_levels, int num_query, float *query, float *query_pos, float *fg_q,
+                                  float *ref_q, sdetr_stream_t stream) {
+    SDETR_REQUIRE(tokens && pos && fg && valid_ratios && inds && spatial_shapes && level_start_index && query &&
+                      query_pos && fg_q && ref_q,
+                  SDETR_ERR_INVALID_ARG, "token_gather: null pointer");
+    SDETR_REQUIRE(batch > 0 && num_value > 0 && num_query >= 0 && num_levels > 0 && num_levels <= kMaxLevels,
+                  SDETR_ERR_INVALID_ARG, "token_gather: bad sizes");
+    SDETR_REQUIRE(channels % 4 == 0 && aligned16(tokens) && aligned16(pos) && aligned16(query) && aligned16(query_pos),
+                  SDETR_ERR_INVALID_ARG, "token_gather: rows must be 16-byte aligned, channels %% 4 == 0");
+    if (num_query == 0) return SDETR_OK;
+    token_gather_kernel<<<row_blocks((int64_t)batch * num_query), kRowThreads, 0, (cudaStream_t)stream>>>(
+        tokens, pos, fg, valid_ratios, inds, inds_stride, spatial_shapes, level_start_index, batch, num_value, channels,
+        num_levels, num_query, query, query_pos, fg_q, ref_q);
+    return check_launch("token_gather");
+}
+
+extern "C" int sdetr_token_scatter(float *tokens, const float *query, const int64_t *inds, int64_t inds_stride,
+                                   const int32_t *focus_token_nums, int batch, int num_value, int channels,
+                                   int num_query, sdetr_stream_t stream) {
+    SDETR_REQUIRE(tokens && query && inds && focus_token_nums, SDETR_ERR_INVALID_ARG, "token_scatter: null pointer");
+    SDETR_REQUIRE(batch > 0 && num_value > 0 && num_query >= 0, SDETR_ERR_INVALID_ARG, "token_scatter: bad sizes");
+    SDETR_REQUIRE(channels % 4 == 0 && aligned16(tokens) && aligned16(query), SDETR_ERR_INVALID_ARG,
+                  "token_scatter: rows must be 16-byte aligned, channels %% 4 == 0");
+    if (num_query == 0) return SDETR_OK;
+    token_scatter_kernel<<<row_blocks((int64_t)batch * num_query), kRowThreads, 0, (cudaStream_t)stream>>>(
+        tokens, query, inds, inds_stride, focus_token_nums, batch, num_value, channels, num_query);
+    return check_launch("token_scatter");
+}
+
+extern "C" int sdetr_background_embed(float *tokens, const uint8_t *mask, const int64_t *last_inds,
+                                      int64_t inds_stride, int num_last, const float *row_embed,
+                                      const float *col_embed, const int64_t *spatial_shapes,
+                                      const int64_t *level_start_index, int batch, int num_value, int channels,
+                                      int num_levels, uint8_t *flags, sdetr_stream_t stream) {
+    SDETR_REQUIRE(tokens && mask && last_inds && row_embed && col_embed && spatial_shapes && level_start_index && flags,
+                  SDETR_ERR_INVALID_ARG, "background_embed: null pointer");
+    SDETR_REQUIRE(batch > 0 && num_value > 0 && num_last >= 0 && num_levels > 0 && num_levels <= kMaxLevels,
+                  SDETR_ERR_INVALID_ARG, "background_embed: bad sizes");
+    SDETR_REQUIRE(channels % 8 == 0 && aligned16(tokens) && aligned16(row_embed) && aligned16(col_embed),
+                  SDETR_ERR_INVALID_ARG, "background_embed: channels %% 8 == 0 and 16-byte alignment required");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)batch * num_value, s);
+    SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "background_embed: memset: %s", cudaGetErrorString(e));
+    if (num_last > 0) {
+        const int64_t n = (int64_t)batch * num_last;
+        mark_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(last_inds, inds_stride, num_last, batch, num_value,
+                                                                      flags);
+        int rc = check_launch("background_embed/mark");
+        if (rc) return rc;
+    }
+    background_embed_kernel<<<row_blocks((int64_t)batch * num_value), kRowThreads, 0, s>>>(
+        tokens, mask, flags, row_embed, col_embed, spatial_shapes, level_start_index, batch, num_value, channels,
+        num_levels);
+    return check_launch("background_embed");
+}
+
+extern "C" int sdetr_score_modulate(const float *mem, int64_t mem_batch_stride, const float *coarse_score,
+                                    int64_t coarse_batch_stride, const float *alpha, int alpha_index, int batch,
+                                    int H, int W, int Hc, int Wc, int channels, float *out, sdetr_stream_t stream) {
+    SDETR_REQUIRE(mem && coarse_score && alpha && out, SDETR_ERR_INVALID_ARG, "score_modulate: null pointer");
+    SDETR_REQUIRE(batch > 0 && H > 0 && W > 0 && Hc > 0 && Wc > 0 && alpha_index >= 0, SDETR_ERR_INVALID_ARG,
+                  "score_modulate: bad sizes");
+    SDETR_REQUIRE(channels % 4 == 0 && aligned16(mem) && aligned16(out) && mem_batch_stride % 4 == 0,
+                  SDETR_ERR_INVALID_ARG, "score_modulate: 16-byte alignment required");
+    score_modulate_kernel<<<row_blocks((int64_t)batch * H * W), kRowThreads, 0, (cudaStream_t)stream>>>(
+        mem, mem_batch_stride, coarse_score, coarse_batch_stride, alpha, alpha_index, batch, H, W, Hc, Wc, channels, out);
+    return check_launch("score_modulate");
+}
+
+extern "C" int sdetr_zero_masked_rows(float *rows, int64_t row_stride, int row_floats, const uint8_t *mask,
+                                      int64_t num_rows, sdetr_stream_t stream) {
+    SDETR_REQUIRE(rows && mask, SDETR_ERR_INVALID_ARG, "zero_masked_rows: null pointer");
+    SDETR_REQUIRE(num_rows >= 0 && row_floats > 0 && row_floats % 4 == 0 && row_stride % 4 == 0 && aligned16(rows),
+                  SDETR_ERR_INVALID_ARG, "zero_masked_rows: bad sizes / alignment");
+    if (num_rows == 0) return SDETR_OK;
+    zero_masked_rows_kernel<<<row_blocks(num_rows), kRowThreads, 0, (cudaStream_t)stream>>>(rows, row_stride, row_floats,
+                                                                                           mask, num_rows);
+    return check_launch("zero_masked_rows");
+}
+
+extern "C" int sdetr_class_max_times_fg(const float *logits, const float *fg, int64_t rows, int num_classes, float *out,
+                                        sdetr_stream_t stream) {
+    SDETR_REQUIRE(logits && fg && out, SDETR_ERR_INVALID_ARG, "class_max_times_fg: null pointer");
+    SDETR_REQUIRE(rows >= 0 && num_classes > 0, SDETR_ERR_INVALID_ARG, "class_max_times_fg: bad sizes");
+    if (rows == 0) return SDETR_OK;
+    class_max_kernel<<<row_blocks(rows), kRowThreads, 0, (cudaStream_t)stream>>>(logits, fg, rows, num_classes, out);
+    return check_launch("class_max_times_fg");
+}
+
+extern "C" int sdetr_add_layernorm(const float *x, const float *r, const float *gamma, const float *beta, float eps,
+                                   int64_t rows, int channels, float *y, sdetr_stream_t stream) {
+    SDETR_REQUIRE(x && gamma && beta && y, SDETR_ERR_INVALID_ARG, "add_layernorm: null pointer");
+    SDETR_REQUIRE(rows >= 0 && channels > 0 && channels <= 1024 && channels % 4 == 0, SDETR_ERR_UNSUPPORTED,
+                  "add_layernorm: channels %d must be a multiple of 4 and <= 1024", channels);
+    SDETR_REQUIRE(aligned16(x) && aligned16(y) && (!r || aligned16(r)) && aligned16(gamma) && aligned16(beta),
+                  SDETR_ERR_INVALID_ARG, "add_layernorm: 16-byte alignment required");
+    if (rows == 0) return SDETR_OK;
+    add_layernorm_kernel<<<row_blocks(rows), kRowThreads, 0, (cudaStream_t)stream>>>(x, r, gamma, beta, eps, rows,
+                                                                                     channels, y);
+    return check_launch("add_layernorm");
+}

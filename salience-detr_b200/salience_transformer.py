@@ -1,0 +1,430 @@
+"""Drop-in mirror of the ENCODER HALF of the reference's ``models/bricks/salience_transformer.py``.
+
+Same class names, constructor arguments, sub-module / parameter names and ``forward`` signatures
+(``MaskPredictor`` :16-47, ``SalienceTransformerEncoderLayer`` :298-396, ``SalienceTransformerEncoder``
+:399-497, the encoder half of ``SalienceTransformer`` :50-183), so a reference ``state_dict`` loads
+(``strict=False`` skips the decoder keys) and reference configs can instantiate these classes in place
+of the originals.  The decoder half (:194-295, :500-674) is out of scope for this round.
+
+How the path is laid out for a B200 (none of this is a translation of the reference's op chain):
+
+* one ``EncoderPlan`` per batch geometry holds everything derived from the padding masks (token budgets,
+  level tables, valid ratios, keep mask).  Building it costs ONE host round trip; the reference syncs
+  ~40 times per forward.  With a plan the forward is sync-free and CUDA-graph
+  capturable.
+* the salience filter is a single C-ABI call after the coarse-to-fine score loop;
+* ``value`` never changes across encoder layers (:452), so the six ``value_proj`` GEMMs are ONE GEMM over
+  the concatenated weights, the padded rows are zeroed once, and every layer samples its column slice;
+* per layer: one fused four-way gather, one GEMM for offsets|logits, one fused
+  softmax+locations+sampling kernel (spatially tiled processing order), fused residual+LayerNorm,
+  in-place prefix-limited scatter.  Dense GEMMs / the 300-token MHA stay on cuBLAS / SDPA.
+"""
+from __future__ import annotations
+
+import copy
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor, nn
+from torch.nn import functional as F
+
+from . import cabi
+from .ms_deform_attn import MultiScaleDeformableAttention
+
+TILE_CELL_PX = 128  # edge (image pixels) of the spatial cells that define the MSDA processing order
+MSDA_SCHEDULE = 0   # 0 = query-major, 1 = head-major chunks (see include/sdetr_b200.h)
+
+
+class MaskPredictor(nn.Module):
+    """Per-token salience score (reference :16-47): LN -> Linear -> GELU, global half = token mean."""
+
+    def __init__(self, in_dim, h_dim):
+        super().__init__()
+        self.h_dim = h_dim
+        self.layer1 = nn.Sequential(nn.LayerNorm(in_dim), nn.Linear(in_dim, h_dim), nn.GELU())
+        self.layer2 = nn.Sequential(nn.Linear(h_dim, h_dim // 2), nn.GELU(), nn.Linear(h_dim // 2, h_dim // 4),
+                                    nn.GELU(), nn.Linear(h_dim // 4, 1))
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                nn.init.constant_(m.bias, 0)
+
+    def forward(self, x):
+        z = self.layer1(x)
+        half = self.h_dim // 2
+        z = torch.cat([z[..., :half], z[..., half:].mean(dim=1, keepdim=True).expand(-1, z.shape[1], -1)], dim=-1)
+        return self.layer2(z)
+
+
+class PositionEmbeddingLearned(nn.Module):
+    """Learned row/col embedding used as the encoder's background embedding (position_encoding.py:68-95)."""
+
+    def __init__(self, num_embeddings: int = 50, num_pos_feats: int = 256):
+        super().__init__()
+        self.row_embed = nn.Embedding(num_embeddings, num_pos_feats)
+        self.col_embed = nn.Embedding(num_embeddings, num_pos_feats)
+        nn.init.uniform_(self.row_embed.weight)
+        nn.init.uniform_(self.col_embed.weight)
+
+    def forward(self, mask: Tensor):
+        h, w = mask.shape[-2:]
+        x = self.col_embed.weight[:w][None].expand(h, -1, -1)
+        y = self.row_embed.weight[:h][:, None].expand(-1, w, -1)
+        return torch.cat([x, y], -1).permute(2, 0, 1)[None].expand(mask.shape[0], -1, -1, -1)
+
+
+# ------------------------------------------------------------------------------------------------------------
+@dataclass
+class EncoderPlan:
+    """Everything the path derives from the padding masks (one host sync to build, none to use)."""
+    shapes_list: List[Tuple[int, int]]
+    spatial_shapes: Tensor      # (L,2) int64, device
+    level_start_index: Tensor   # (L,) int64, device
+    level_start: List[int]
+    level_size: List[int]
+    level_width: List[int]
+    level_stride: List[int]     # image pixels per token, for the processing-order cells
+    mask_flat: Tensor           # (b,Nv) bool
+    mask_u8: Tensor             # (b,Nv) uint8
+    keep: Tensor                # (b,Nv,1) float: ~padding & proposal-valid (base_transformer.py:100-108)
+    valid_ratios: Tensor        # (b,L,2)
+    level_token_nums: List[int]
+    focus_token_nums: Tensor    # (b,) int32, device
+    focus_host: List[int]
+    num_selected: int           # K
+    layer_num_query: List[int]
+    scratch: Dict[str, Tensor] = field(default_factory=dict)
+
+
+def flatten_levels(xs: Sequence[Tensor]) -> Tensor:
+    """(b,[C],H_l,W_l) per level -> (b,Nv,[C]) tokens (base_transformer.py:21-26)."""
+    y = torch.cat([e.flatten(-2) for e in xs], -1)
+    return y.transpose(1, 2).contiguous() if y.ndim == 3 else y
+
+
+class SalienceTransformerEncoderLayer(nn.Module):
+    def __init__(self, embed_dim=256, d_ffn=1024, dropout=0.1, n_heads=8, activation=nn.ReLU(inplace=True), n_levels=4,
+                 n_points=4, topk_sa=300):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.topk_sa = topk_sa
+        self.n_heads = n_heads
+        self.pre_attention = nn.MultiheadAttention(embed_dim, n_heads, dropout, batch_first=True)
+        self.pre_dropout = nn.Dropout(dropout)
+        self.pre_norm = nn.LayerNorm(embed_dim)
+        self.self_attn = MultiScaleDeformableAttention(embed_dim, n_levels, n_heads, n_points)
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(embed_dim)
+        self.linear1 = nn.Linear(embed_dim, d_ffn)
+        self.activation = activation
+        self.dropout2 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, embed_dim)
+        self.dropout3 = nn.Dropout(dropout)
+        self.norm2 = nn.LayerNorm(embed_dim)
+        self.init_weights()
+
+    def init_weights(self):
+        nn.init.xavier_uniform_(self.pre_attention.in_proj_weight)
+        nn.init.xavier_uniform_(self.pre_attention.out_proj.weight)
+        nn.init.xavier_uniform_(self.linear1.weight)
+        nn.init.xavier_uniform_(self.linear2.weight)
+
+    # -- reference-signature forward (autograd friendly; used for training) ---------------------------------
+    def forward(self, query, query_pos, value, reference_points, spatial_shapes, level_start_index,
+                query_key_padding_mask=None, score_tgt=None, foreground_pre_layer=None):
+        mc = score_tgt.max(-1)[0] * foreground_pre_layer
+        top = cabi.topk_desc(mc.detach().float().contiguous(), min(self.topk_sa, mc.shape[1]))
+        ix = top.unsqueeze(-1).expand(-1, -1, self.embed_dim)
+        t, tp = torch.gather(query, 1, ix), torch.gather(query_pos, 1, ix)
+        x = t + tp
+        t = self.pre_norm(t + self.pre_dropout(self.pre_attention(x, x, t)[0]))
+        query = query.scatter(1, ix, t)
+        a = self.self_attn(query=query + query_pos, reference_points=reference_points, value=value,
+                           spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                           key_padding_mask=query_key_padding_mask)
+        query = self.norm1(query + self.dropout1(a))
+        f = self.linear2(self.dropout2(self.activation(self.linear1(query))))
+        return self.norm2(query + self.dropout3(f))
+
+    # -- inference fast path ------------------------------------------------------------------------------------
+    def _pre_attention_fast(self, q, qp, mc):
+        b, nq, c = q.shape
+        k = min(self.topk_sa, nq)
+        top = cabi.topk_desc(mc, k)
+        ix = top.unsqueeze(-1).expand(-1, -1, c)
+        t, tp = torch.gather(q, 1, ix), torch.gather(qp, 1, ix)
+        x = t + tp
+        w, bias = self.pre_attention.in_proj_weight, self.pre_attention.in_proj_bias
+        h, d = self.n_heads, c // self.n_heads
+        qk = F.linear(x, w[:2 * c], bias[:2 * c]).view(b, k, 2, h, d)
+        v = F.linear(t, w[2 * c:], bias[2 * c:]).view(b, k, h, d)
+        o = F.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2), v.transpose(1, 2))
+        o = self.pre_attention.out_proj(o.transpose(1, 2).reshape(b, k, c))
+        t = cabi.add_layernorm(t, o, self.pre_norm.weight, self.pre_norm.bias, self.pre_norm.eps)
+        q.scatter_(1, ix, t)  # q is this layer's private gather buffer
+        return q
+
+    def forward_fast(self, q, qp, mc, ref_q, vbuf, v_bstride, v_tstride, v_off, num_value, spatial_shapes,
+                     level_start_index, order=None, schedule=MSDA_SCHEDULE):
+        q = self._pre_attention_fast(q, qp, mc)
+        a = self.self_attn.forward_projected(q + qp, ref_q, vbuf, v_bstride, v_tstride, v_off, num_value, spatial_shapes,
+                                             level_start_index, order, schedule)
+        q = cabi.add_layernorm(q, a, self.norm1.weight, self.norm1.bias, self.norm1.eps, out=q)
+        f = self.linear2(F.relu(self.linear1(q), inplace=True))
+        return cabi.add_layernorm(q, f, self.norm2.weight, self.norm2.bias, self.norm2.eps, out=q)
+
+
+class SalienceTransformerEncoder(nn.Module):
+    def __init__(self, encoder_layer: nn.Module, num_layers: int = 6, max_num_embedding=200):
+        super().__init__()
+        self.layers = nn.ModuleList([copy.deepcopy(encoder_layer) for _ in range(num_layers)])
+        self.num_layers = num_layers
+        self.embed_dim = encoder_layer.embed_dim
+        self.background_embedding = PositionEmbeddingLearned(max_num_embedding, num_pos_feats=self.embed_dim // 2)
+        self.enhance_mcsp: Optional[nn.Module] = None  # injected by SalienceTransformer (reference :79)
+        self._vproj_key = None
+        self._vproj = None
+        for layer in self.layers:
+            layer.init_weights()
+
+    @staticmethod
+    def get_reference_points(spatial_shapes, valid_ratios, device):
+        """(b,Nv,L,2) table of the reference (:417-432); the fast path never materialises it (the gather
+        kernel recomputes the needed rows), this exists for API parity and the training path."""
+        refs = []
+        for lvl, (h, w) in enumerate(spatial_shapes.tolist() if torch.is_tensor(spatial_shapes) else spatial_shapes):
+            ys = torch.arange(h, dtype=torch.float32, device=device) + 0.5
+            xs = torch.arange(w, dtype=torch.float32, device=device) + 0.5
+            ry = ys[None, :, None].expand(1, h, w).reshape(1, -1) / (valid_ratios[:, None, lvl, 1] * h)
+            rx = xs[None, None, :].expand(1, h, w).reshape(1, -1) / (valid_ratios[:, None, lvl, 0] * w)
+            refs.append(torch.stack((rx, ry), -1))
+        return torch.cat(refs, 1)[:, :, None] * valid_ratios[:, None]
+
+    def _value_projection(self):
+        """[6*C, C] weight / [6*C] bias of all layers' value_proj (rebuilt when any of them changes)."""
+        ps = [(l.self_attn.value_proj.weight, l.self_attn.value_proj.bias) for l in self.layers]
+        key = tuple((w.data_ptr(), w._version, b._version) for w, b in ps)
+        if self._vproj_key != key:
+            with torch.no_grad():
+                self._vproj = (torch.cat([w for w, _ in ps], 0).contiguous(), torch.cat([b for _, b in ps], 0).contiguous())
+            self._vproj_key = key
+        return self._vproj
+
+    def forward(self, query, spatial_shapes, level_start_index, valid_ratios, query_pos=None,
+                query_key_padding_mask=None, foreground_score=None, focus_token_nums=None, foreground_inds=None,
+                multi_level_masks=None, query_orders=None):
+        """Reference signature (:434-447) + optional ``query_orders`` (per-layer int32 processing orders).
+
+        query/query_pos (b,Nv,C); foreground_inds: list of (b,Nq_j) int64 (prefix views of one selected_inds);
+        focus_token_nums (b,) int; -> encoder memory (b,Nv,C)."""
+        if torch.is_grad_enabled() and (query.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return self._forward_autograd(query, spatial_shapes, level_start_index, valid_ratios, query_pos,
+                                          query_key_padding_mask, foreground_score, focus_token_nums, foreground_inds,
+                                          multi_level_masks)
+        b, nv, c = query.shape
+        L = spatial_shapes.shape[0]
+        M = self.layers[0].self_attn.num_heads
+        mask_u8 = query_key_padding_mask.to(torch.uint8).contiguous()
+        focus = focus_token_nums.to(torch.int32).contiguous()
+        # one GEMM for the value projections of all layers; zero the padded rows once
+        wv, bv = self._value_projection()
+        vbuf = F.linear(query, wv, bv)  # (b,Nv,layers*C)
+        wide = vbuf.shape[-1]
+        cabi.zero_masked_rows_(vbuf, wide, wide, mask_u8, b * nv)
+        out = query.clone()  # `value` stays the original tokens (:452); `out` is updated in place
+        pos = query_pos.contiguous()
+        fg = foreground_score.contiguous()
+        vr = valid_ratios.contiguous()
+        inds = None
+        for j, layer in enumerate(self.layers):
+            inds = foreground_inds[j]
+            nq = inds.shape[1]
+            q, qp, fq, rq = cabi.token_gather(out, pos, fg, vr, inds, spatial_shapes, level_start_index, nq)
+            mc = cabi.class_max_times_fg(self.enhance_mcsp(q), fq)
+            q = layer.forward_fast(q, qp, mc, rq, vbuf, nv * wide, wide, j * c, nv, spatial_shapes, level_start_index,
+                                   None if query_orders is None else query_orders[j])
+            cabi.token_scatter_(out, q, inds, focus)
+        if multi_level_masks is not None:
+            cabi.background_embed_(out, mask_u8, inds, self.background_embedding.row_embed.weight,
+                                   self.background_embedding.col_embed.weight, spatial_shapes, level_start_index)
+        return out
+
+    def _forward_autograd(self, query, spatial_shapes, level_start_index, valid_ratios, query_pos,
+                          query_key_padding_mask, foreground_score, focus_token_nums, foreground_inds, multi_level_masks):
+        """Training path: torch autograd around the custom MSDA Function (forward + backward kernels)."""
+        b, nv, c = query.shape
+        ref = self.get_reference_points(spatial_shapes, valid_ratios, query.device)
+        L = ref.shape[2]
+        value = output = query
+        focus = focus_token_nums.tolist()
+        inds = None
+        for j, layer in enumerate(self.layers):
+            inds = foreground_inds[j]
+            nq = inds.shape[1]
+            ix = inds.unsqueeze(-1).expand(-1, -1, c)
+            q, qp = torch.gather(output, 1, ix), torch.gather(query_pos, 1, ix)
+            fq = torch.gather(foreground_score, 1, inds)
+            rq = torch.gather(ref.view(b, nv, -1), 1, inds.unsqueeze(-1).expand(-1, -1, L * 2)).view(b, nq, L, 2)
+            q = layer(q, qp, value, rq, spatial_shapes, level_start_index, query_key_padding_mask, self.enhance_mcsp(q), fq)
+            rows = []
+            for i in range(b):
+                n = min(int(focus[i]), nq)
+                rows.append(output[i].scatter(0, inds[i, :n].unsqueeze(-1).expand(-1, c), q[i, :n]))
+            output = torch.stack(rows)
+        if multi_level_masks is not None:
+            bg = torch.cat([self.background_embedding(m).flatten(2).transpose(1, 2) for m in multi_level_masks], 1).clone()
+            bg.scatter_(1, inds.unsqueeze(-1).expand(-1, -1, c), 0)
+            output = output + bg * (~query_key_padding_mask).unsqueeze(-1)
+        return output
+
+
+class SalienceTransformer(nn.Module):
+    """Encoder half of the reference ``SalienceTransformer`` (:50-183): salience filter + encoder.
+
+    Constructor signature follows the reference (:51-61); ``neck`` / ``decoder`` may be ``None`` (they are
+    outside this round's path).  Parameters of the path keep the reference names: ``level_embeds``,
+    ``enc_output``, ``enc_output_norm``, ``alpha``, ``level_filter_ratio``, ``layer_filter_ratio``,
+    ``encoder_class_head``, ``enc_mask_predictor``, ``encoder.*``."""
+
+    def __init__(self, encoder: nn.Module, neck: Optional[nn.Module] = None, decoder: Optional[nn.Module] = None,
+                 num_classes: int = 91, num_feature_levels: int = 4, two_stage_num_proposals: int = 900,
+                 level_filter_ratio: Tuple = (0.25, 0.5, 1.0, 1.0),
+                 layer_filter_ratio: Tuple = (1.0, 0.8, 0.6, 0.6, 0.4, 0.2), level_strides: Sequence[int] = (8, 16, 32, 64)):
+        super().__init__()
+        self.embed_dim = encoder.embed_dim
+        self.num_feature_levels = num_feature_levels
+        self.two_stage_num_proposals = two_stage_num_proposals
+        self.num_classes = num_classes
+        self.level_strides = list(level_strides)
+        self.level_embeds = nn.Parameter(torch.empty(num_feature_levels, self.embed_dim))
+        self.enc_output = nn.Linear(self.embed_dim, self.embed_dim)
+        self.enc_output_norm = nn.LayerNorm(self.embed_dim)
+        self.register_buffer("level_filter_ratio", torch.tensor(level_filter_ratio, dtype=torch.float32))
+        self.register_buffer("layer_filter_ratio", torch.tensor(layer_filter_ratio, dtype=torch.float32))
+        self.alpha = nn.Parameter(torch.empty(3), requires_grad=True)
+        self.encoder = encoder
+        self.neck = neck
+        self.decoder = decoder
+        self.encoder_class_head = nn.Linear(self.embed_dim, num_classes)
+        self.encoder.enhance_mcsp = self.encoder_class_head
+        self.enc_mask_predictor = MaskPredictor(self.embed_dim, self.embed_dim)
+        self.init_weights()
+
+    def init_weights(self):
+        import math
+        nn.init.normal_(self.level_embeds)
+        nn.init.xavier_uniform_(self.enc_output.weight)
+        nn.init.constant_(self.enc_output.bias, 0.0)
+        nn.init.constant_(self.encoder_class_head.bias, -math.log((1 - 0.01) / 0.01))
+        self.alpha.data.uniform_(-0.3, 0.3)
+
+    # -- plan ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def make_plan(self, multi_level_masks: Sequence[Tensor]) -> EncoderPlan:
+        """Token budgets (:117-121, :161-165), level tables (base_transformer.py:34-56) and the proposal keep
+        mask (base_transformer.py:74-110) from the padding masks.  One device->host copy."""
+        dev = multi_level_masks[0].device
+        b = multi_level_masks[0].shape[0]
+        shapes_list = [tuple(int(s) for s in m.shape[-2:]) for m in multi_level_masks]
+        L = len(shapes_list)
+        sizes = [h * w for h, w in shapes_list]
+        starts = [sum(sizes[:i]) for i in range(L)]
+        spatial_shapes = torch.tensor(shapes_list, dtype=torch.int64, device=dev)
+        level_start_index = torch.tensor(starts, dtype=torch.int64, device=dev)
+        mask_flat = flatten_levels(multi_level_masks)
+        valid = torch.stack([(~m).sum((1, 2)) for m in multi_level_masks], -1)           # (b,L) int64
+        focus = (valid * self.level_filter_ratio).int()                                  # fp32 multiply, truncate
+        vr, keep = [], []
+        for lvl, m in enumerate(multi_level_masks):
+            h, w = shapes_list[lvl]
+            vh, vw = (~m[:, :, 0]).sum(1), (~m[:, 0, :]).sum(1)
+            vr.append(torch.stack([vw.float() / w, vh.float() / h], -1))
+            gy = (torch.arange(h, dtype=torch.float32, device=dev) + 0.5)[None, :, None] / vh[:, None, None]
+            gx = (torch.arange(w, dtype=torch.float32, device=dev) + 0.5)[None, None, :] / vw[:, None, None]
+            ok = (gy > 0.01) & (gy < 0.99) & (gx > 0.01) & (gx < 0.99) & (0.01 < 0.05 * 2.0 ** lvl < 0.99)
+            keep.append((ok & ~m).flatten(1))
+        host = torch.cat([focus.max(0)[0].flatten(), focus.sum(-1).flatten()]).cpu().tolist()  # the one sync
+        level_token_nums, focus_host = host[:L], host[L:]
+        K = sum(level_token_nums)
+        ratios = self.layer_filter_ratio.detach().float().cpu()
+        layer_nq = (K * ratios).to(torch.int64).tolist()                                 # :164
+        return EncoderPlan(
+            shapes_list=shapes_list, spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+            level_start=starts, level_size=sizes, level_width=[w for _, w in shapes_list],
+            level_stride=(self.level_strides + [self.level_strides[-1] * 2] * L)[:L], mask_flat=mask_flat,
+            mask_u8=mask_flat.to(torch.uint8).contiguous(), keep=torch.cat(keep, 1).unsqueeze(-1).float(),
+            valid_ratios=torch.stack(vr, 1).contiguous(), level_token_nums=level_token_nums,
+            focus_token_nums=focus.sum(-1).to(torch.int32).contiguous(), focus_host=focus_host, num_selected=K,
+            layer_num_query=layer_nq)
+
+    # -- salience filter (:112-168) ------------------------------------------------------------------------------
+    def salience_filter(self, feat: Tensor, lpos: Tensor, plan: EncoderPlan, want_order: bool = True):
+        b, nv, c = feat.shape
+        L = len(plan.shapes_list)
+        # training keeps the scores differentiable (salience supervision): plain torch ops instead of the fused kernels
+        grad = torch.is_grad_enabled() and (feat.requires_grad or any(p.requires_grad for p in self.parameters()))
+        x = (feat + lpos) * plan.keep
+        mem = self.enc_output(x)
+        if grad:
+            mem = self.enc_output_norm(mem)
+        else:
+            mem = cabi.add_layernorm(mem, None, self.enc_output_norm.weight, self.enc_output_norm.bias,
+                                     self.enc_output_norm.eps, out=mem)
+        raw = torch.empty(b, nv, device=feat.device, dtype=torch.float32)
+        prev = None
+        for lvl in range(L - 1, -1, -1):
+            h, w = plan.shapes_list[lvl]
+            s0 = plan.level_start[lvl]
+            m_l = mem[:, s0:s0 + h * w]
+            if lvl != L - 1:
+                hc, wc = plan.shapes_list[lvl + 1]
+                s1 = plan.level_start[lvl + 1]
+                if grad:
+                    up = F.interpolate(prev.transpose(1, 2).reshape(b, 1, hc, wc), size=(h, w), mode="bilinear",
+                                       align_corners=True)
+                    m_l = m_l + m_l * up.view(b, 1, h * w).transpose(1, 2) * self.alpha[lvl]
+                else:
+                    m_l = cabi.score_modulate(mem, s0, h, w, raw[:, s1:s1 + hc * wc], hc, wc, self.alpha, lvl)
+            prev = self.enc_mask_predictor(m_l)
+            raw[:, s0:s0 + h * w] = prev.squeeze(-1)
+        sel_in = raw.detach() if grad else raw
+        inds, score, fg, order = cabi.salience_select(
+            sel_in, plan.mask_u8, plan.level_start, plan.level_size, plan.level_token_nums,
+            plan.level_width if want_order else None, plan.level_stride if want_order else None, TILE_CELL_PX)
+        return raw, inds, score, fg, order
+
+    # -- encoder half ---------------------------------------------------------------------------------------------
+    def forward_encoder(self, multi_level_feats, multi_level_masks, multi_level_pos_embeds,
+                        plan: Optional[EncoderPlan] = None, use_order: bool = True):
+        """(b,C,H_l,W_l) feats, (b,H_l,W_l) bool masks, (b,C,H_l,W_l) pos -> memory (b,Nv,C) + aux dict.
+
+        Reference lines 106-183.  Pass a cached ``plan`` (``make_plan``) to run with no host sync."""
+        if plan is None:
+            plan = self.make_plan(multi_level_masks)
+        feat = flatten_levels(multi_level_feats)
+        lpos = flatten_levels([p + e.view(1, -1, 1, 1) for p, e in zip(multi_level_pos_embeds, self.level_embeds)])
+        grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        raw, inds, score, fg, order = self.salience_filter(feat, lpos, plan, want_order=use_order and not grad)
+        layer_inds = [inds[:, :n] for n in plan.layer_num_query]
+        orders = cabi.order_prefixes(order, plan.layer_num_query) if order is not None else None
+        memory = self.encoder(
+            query=feat, query_pos=lpos, query_key_padding_mask=plan.mask_flat, spatial_shapes=plan.spatial_shapes,
+            level_start_index=plan.level_start_index, valid_ratios=plan.valid_ratios, foreground_score=fg,
+            focus_token_nums=plan.focus_token_nums, foreground_inds=layer_inds, multi_level_masks=multi_level_masks,
+            query_orders=orders)
+        aux = dict(raw_score=raw, selected_inds=inds, selected_score=score, foreground_score=fg, plan=plan)
+        return memory, aux
+
+    def forward(self, multi_level_feats, multi_level_masks, multi_level_pos_embeds, noised_label_query=None,
+                noised_box_query=None, attn_mask=None):
+        """Reference call signature (:97-105).  Only the encoder half exists in this round: returns
+        (memory, salience_score maps) when no decoder is attached."""
+        memory, aux = self.forward_encoder(multi_level_feats, multi_level_masks, multi_level_pos_embeds)
+        if self.decoder is not None or self.neck is not None:
+            raise NotImplementedError("neck / decoder half are outside this round's hot path (SURVEY.md 8(f))")
+        b = memory.shape[0]
+        plan = aux["plan"]
+        salience = [aux["raw_score"][:, s:s + h * w].reshape(b, 1, h, w)
+                    for s, (h, w) in zip(plan.level_start, plan.shapes_list)]
+        return memory, salience

@@ -1,0 +1,70 @@
+"""CPU tests of the host-side logic above the C-ABI: the EncoderPlan (token budgets, level tables, keep mask,
+valid ratios) against the oracle and the reference-made golden fixtures.  Pure torch, no kernels."""
+import torch
+
+from conftest import load_golden
+from oracle import oracle as orc
+
+
+def _model(pkg, cfg_levels=(0.4, 0.8, 1.0, 1.0), layers=(1.0, 0.6, 0.3)):
+    enc = pkg.SalienceTransformerEncoder(pkg.SalienceTransformerEncoderLayer(64, 128, 0.0, 2, topk_sa=20), len(layers), 40)
+    return pkg.SalienceTransformer(enc, num_classes=11, level_filter_ratio=cfg_levels, layer_filter_ratio=layers).eval()
+
+
+def test_plan_matches_reference_golden():
+    import salience_detr_b200 as pkg
+    for name in ("encoder_tiny_even", "encoder_tiny_ragged"):
+        g, sd = load_golden(name)
+        tr = _model(pkg)
+        masks = [g[f"mask{i}"] for i in range(4)]
+        plan = tr.make_plan(masks)
+        assert torch.equal(plan.spatial_shapes, g["spatial_shapes"])
+        assert torch.equal(plan.level_start_index, g["level_start_index"])
+        assert torch.equal(plan.valid_ratios, g["valid_ratios"])
+        assert torch.equal(plan.focus_token_nums.long(), g["focus_token_nums"].long())
+        assert plan.layer_num_query == g["layer_num_query"].tolist()
+        assert plan.num_selected == g["selected_inds"].shape[1]
+        mask_flat = orc.flatten_levels(masks)
+        keep = orc.proposal_keep_mask(mask_flat, plan.shapes_list)
+        assert torch.equal(plan.keep[..., 0].bool(), keep)
+
+
+def test_plan_budgets_config2_fp32_truncation():
+    """800x1333 padded to 800x1344: K = 11363, Nq = [11363, 9090, 6817, 6817, 4545, 2272]."""
+    import salience_detr_b200 as pkg
+    enc = pkg.SalienceTransformerEncoder(pkg.SalienceTransformerEncoderLayer(64, 128, 0.0, 2), 6, 200)
+    tr = pkg.SalienceTransformer(enc, level_filter_ratio=(0.4, 0.8, 1.0, 1.0),
+                                 layer_filter_ratio=(1.0, 0.8, 0.6, 0.6, 0.4, 0.2))
+    _, masks, _ = orc.synthetic_inputs([(800, 1333)] * 2, (800, 1344), embed_dim=8)
+    plan = tr.make_plan(masks)
+    assert plan.shapes_list == [(100, 168), (50, 84), (25, 42), (13, 21)]
+    assert plan.level_token_nums == [6680, 3360, 1050, 273]
+    assert plan.focus_host == [11363, 11363]
+    assert plan.layer_num_query == [11363, 9090, 6817, 6817, 4545, 2272]
+    mask_flat = orc.flatten_levels(masks)
+    ltn, ftn, lnq = orc.c_token_budgets(mask_flat, plan.level_start_index, torch.tensor(plan.level_size),
+                                        (0.4, 0.8, 1.0, 1.0), (1.0, 0.8, 0.6, 0.6, 0.4, 0.2))
+    assert ltn.tolist() == plan.level_token_nums and ftn.tolist() == plan.focus_host
+    assert lnq.tolist() == plan.layer_num_query
+    # ragged second image: focus = [11363, 6832]
+    _, masks, _ = orc.synthetic_inputs([(800, 1333), (640, 1000)], (800, 1344), embed_dim=8)
+    assert tr.make_plan(masks).focus_host == [11363, 6832]
+
+
+def test_state_dict_names_match_reference():
+    """A reference state_dict (encoder-half keys) loads with no missing and no unexpected key."""
+    import salience_detr_b200 as pkg
+    g, sd = load_golden("encoder_tiny_even")
+    res = _model(pkg).load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    # optimizer/param_dict.py:80 matches `sampling_offsets` by name
+    assert any("self_attn.sampling_offsets.weight" in k for k in sd)
+
+
+def test_msda_module_init_matches_reference_golden_shapes():
+    import salience_detr_b200 as pkg
+    m = pkg.MultiScaleDeformableAttention(256, 4, 8, 4)
+    b = m.sampling_offsets.bias.view(8, 4, 4, 2)
+    assert torch.allclose(b[0, 0, :, 0], torch.tensor([1.0, 2.0, 3.0, 4.0])) and b[0, 0, :, 1].abs().max() < 1e-6
+    assert m.sampling_offsets.weight.abs().max() == 0 and m.attention_weights.weight.abs().max() == 0
+    assert m.im2col_step == 64
