@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- images/s of the Salience-DETR encoder forward (salience filter + 6 encoder layers) on B200.
+
+Workload (BASELINE.json configs[1]): salience_detr_resnet50_800_1333, bs=2 per GPU, synthetic COCO-shape inputs
+(800x1333 padded to 800x1344 -> levels 100x168, 50x84, 25x42, 13x21; Nv=22323, K=11363), fp32, eval, random-init
+weights.  A "step" is one encoder-half forward (salience_transformer.py:106-183 of the reference) over one batch.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's sm_100a path
+  python bench.py --impl reference ...                           # the reference's CPU path (oracle port), rank 0 only
+  torchrun --nproc-per-node N bench.py --gpus N ...              # one process per GPU, weak scaling (replicas)
+
+Prints ONE JSON line (rank 0).  value = device-resident throughput (CUDA-graph replay, inputs in HBM); e2e =
+same metric through EncoderRunner.run_host with pinned HOST buffers (H2D + forward + D2H inside the timed region);
+roofline = the dominant kernel (fused MSDA forward) timed alone with CUDA events; cpu_baseline = the oracle port of
+the reference's PyTorch CPU path on this host.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOAD = "resnet50_800_1333_bs2"
+METRIC = "images/sec encoder-fwd @ 800x1333 bs=2/GPU"
+L2_FLUSH_BYTES = 256 << 20
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = [int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def msda_algorithmic_bytes(batch, nv, c, heads, levels, points, nq):
+    """C_msda = 4*Nv*C + Nq*(12*M*L*P + 4*C) bytes per image (value in; loc+attn in; out)."""
+    return batch * (4 * nv * c + nq * (12 * heads * levels * points + 4 * c))
+
+
+def time_msda_kernels(pkg, runner, reps=20):
+    """Roofline leg: the fused MSDA forward launches of one step, timed alone with CUDA events on their stream."""
+    cabi = pkg.cabi
+    calls = []
+    orig = cabi.msda_fused_forward
+
+    def spy(*a, **k):
+        calls.append((a, k))
+        return orig(*a, **k)
+
+    cabi.msda_fused_forward = spy
+    try:
+        with torch.no_grad():
+            runner.model.forward_encoder(runner.feats, runner.masks, runner.pos, plan=runner.plan,
+                                         use_order=runner.use_order)
+    finally:
+        cabi.msda_fused_forward = orig
+    torch.cuda.synchronize()
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=runner.dev)
+    per_layer = [[] for _ in calls]
+    for _ in range(reps):
+        flush.zero_()  # evict L2 so the value slice comes from HBM as it does after the projection GEMM
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(calls) + 1)]
+        evs[0].record()
+        for i, (a, k) in enumerate(calls):
+            orig(*a, **k)
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        for i in range(len(calls)):
+            per_layer[i].append(evs[i].elapsed_time(evs[i + 1]))
+    med = [statistics.median(x) for x in per_layer]  # ms
+    plan = runner.plan
+    b, nv = runner.plan.mask_flat.shape
+    m = runner.model.encoder.layers[0].self_attn
+    byts = [msda_algorithmic_bytes(b, nv, m.embed_dim, m.num_heads, m.num_levels, m.num_points, nq)
+            for nq in plan.layer_num_query]
+    return med, byts
+
+
+def cpu_port_step(state_dict, feats, masks, pos, cfg):
+    from oracle import oracle as orc  # CPU baseline leg only
+    with torch.no_grad():
+        mem, _ = orc.encoder_half_forward(state_dict, feats, masks, pos, cfg, core="torch")
+    return mem
+
+
+def cpu_baseline(pkg, model, budget_s=20.0):
+    """The oracle port of the reference's PyTorch CPU path on this host's cores, bounded sample."""
+    from salience_detr_b200.synthetic import make_inputs
+    feats, masks, pos = make_inputs(WORKLOAD, seed=0)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    m = model.encoder.layers[0]
+    cfg = dict(heads=m.n_heads, points=m.self_attn.num_points, topk_sa=m.topk_sa, num_layers=model.encoder.num_layers,
+               level_filter_ratio=model.level_filter_ratio.tolist(), layer_filter_ratio=model.layer_filter_ratio.tolist())
+    cpu_port_step(sd, feats, masks, pos, cfg)  # warm-up
+    times = []
+    t_end = time.time() + budget_s
+    while len(times) < 2 or (time.time() < t_end and len(times) < 10):
+        t0 = time.time()
+        cpu_port_step(sd, feats, masks, pos, cfg)
+        times.append(time.time() - t0)
+    b = feats[0].shape[0]
+    return {"value": round(b / statistics.median(times), 4), "unit": "images/s", "cores": torch.get_num_threads(),
+            "kind": "port", "sample": f"{len(times)} full bs={b} encoder forwards of {WORKLOAD} (median), torch CPU fp32"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), rank 0 only."""
+    if rank != 0:
+        return
+    import salience_detr_b200 as pkg
+    from salience_detr_b200.synthetic import build_model, make_inputs
+    model = build_model()
+    feats, masks, pos = make_inputs(WORKLOAD, seed=0)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    m = model.encoder.layers[0]
+    cfg = dict(heads=m.n_heads, points=m.self_attn.num_points, topk_sa=m.topk_sa, num_layers=model.encoder.num_layers,
+               level_filter_ratio=model.level_filter_ratio.tolist(), layer_filter_ratio=model.layer_filter_ratio.tolist())
+    for _ in range(args.warmup):
+        cpu_port_step(sd, feats, masks, pos, cfg)
+    t0 = time.time()
+    for _ in range(args.steps):
+        cpu_port_step(sd, feats, masks, pos, cfg)
+    dt = time.time() - t0
+    b = feats[0].shape[0]
+    val = round(args.steps * b / dt, 4)
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1000 * dt / args.steps, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "impl": "oracle port of the reference PyTorch CPU path "
+                       "(grid_sample MSDA, ms_deform_attn.py:159-212); the reference is Python and does not travel"},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} full bs={b} encoder forwards"},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-order", action="store_true")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm", default="3xtf32", choices=["3xtf32", "fp32", "tf32"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        args.steps = args.steps if args.steps is not None else 5
+        args.warmup = args.warmup if args.warmup is not None else 1
+        return run_reference(args, rank, world)
+    args.steps = args.steps if args.steps is not None else 50
+    args.warmup = max(3, args.warmup if args.warmup is not None else 10)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the sm_100a path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import salience_detr_b200 as pkg
+    from salience_detr_b200.runner import EncoderRunner
+    from salience_detr_b200.synthetic import build_model, make_inputs
+
+    torch.backends.cuda.matmul.allow_tf32 = False  # torch default; gemm.linear enables TF32 only for split operands
+    pkg.gemm.MODE = args.gemm
+    model = build_model().to(dev)
+    feats_h, masks_h, pos_h = make_inputs(WORKLOAD, seed=rank)  # every rank its own batch (weak scaling, replicas)
+    feats = [t.to(dev) for t in feats_h]
+    masks = [t.to(dev) for t in masks_h]
+    pos = [t.to(dev) for t in pos_h]
+    runner = EncoderRunner(model, feats, masks, pos, use_graph=not args.no_graph, use_order=not args.no_order)
+    bsz = feats[0].shape[0]
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    stream = runner.stream
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        """W untimed + K timed steps; per-step CUDA events on the launching stream; L2 flushed between steps
+        (outside the events).  Returns total ms of the K steps (max over ranks)."""
+        with torch.cuda.stream(stream):
+            for _ in range(warmup):
+                fn()
+        barrier()
+        pairs = []
+        with torch.cuda.stream(stream):
+            for _ in range(steps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                fn()
+                e1.record(stream)
+                pairs.append((e0, e1))
+        barrier()
+        total = sum(a.elapsed_time(b) for a, b in pairs)
+        if world > 1:
+            t = torch.tensor([total], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total = float(t.item())
+        return total
+
+    with ClockSampler(local) as clk:
+        total_ms = timed(runner.step, args.steps, args.warmup)
+    clocks = clk.summary()
+    value = args.steps * bsz * world / (total_ms / 1000.0)
+
+    # end to end through the public host-buffer API
+    runner.bind_host(feats_h, pos_h)
+    e2e_ms = timed(runner.run_host, args.steps, 3)
+    e2e_val = args.steps * bsz * world / (e2e_ms / 1000.0)
+
+    line = None
+    if rank == 0:
+        med, byts = time_msda_kernels(pkg, runner)
+        peak, peak_src = peaks()
+        achieved = sum(byts) / (sum(med) / 1000.0) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "msda_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch_mean")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": bsz, "global_batch": bsz * world,
+                       "parallelism": f"dp{world} (independent replicas, no forward collective)",
+                       "weights": "random init (seed 0) + N(0,0.02) sampling-offset weights",
+                       "gemm": {"3xtf32": "cuBLAS TF32 tensor cores on 3-way split operands (3xTF32, fp32-class accuracy)",
+                                "fp32": "cuBLAS fp32 SIMT", "tf32": "cuBLAS TF32 (reduced precision)"}[pkg.gemm.MODE], "cuda_graph": runner.graph is not None,
+                       "msda_order": "spatial tiles" if runner.use_order else "score order",
+                       "l2": "256 MiB flush between timed steps (outside the events)"},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_val, 2), "unit": "images/s", "h2d_bytes_per_step": runner.h2d_bytes,
+                    "d2h_bytes_per_step": runner.d2h_bytes, "ms_per_step": round(e2e_ms / args.steps, 4),
+                    "api": "salience_detr_b200.runner.EncoderRunner.run_host (pinned host buffers)"},
+            "gpu_launches": runner.launches_per_step * args.steps,
+            "gpu_launches_per_step": runner.launches_per_step,
+            "roofline": {"bound": "hbm", "kernel": "sdetr::msda_fwd_kernel<32,4,4,fused> (6 launches/step)",
+                         "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": traffic,
+                         "algorithmic_bytes_per_step": int(sum(byts)), "kernel_ms_per_step": round(sum(med), 4),
+                         "per_layer_us": [round(1000 * x, 1) for x in med]},
+        }
+        if world == 1 and not args.skip_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(pkg, model)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -37,6 +37,10 @@ const char *sdetr_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py "gpu_launches") */
 unsigned long long sdetr_launch_count(void);
 
+/* process-wide tuning knobs (benchmark sweeps): "msda_min_blocks" (2..4 resident CTAs/SM the specialised
+ * MSDA kernel is compiled for), "msda_chunk" (queries per CTA in the head-major schedule). */
+int sdetr_set_option(const char *name, int value);
+
 /* ------------------------------------------------------------------------------------------------
  * MSDA core forward.  Replaces `_C.ms_deform_attn_forward`
  *   (models/bricks/ops/cuda/ms_deform_attn_cuda.cu:12-72, kernel ms_deform_im2col_cuda.cuh:226-288;
@@ -180,6 +184,14 @@ int sdetr_class_max_times_fg(const float *logits, const float *fg, int64_t rows,
  * May run in place (y == x). */
 int sdetr_add_layernorm(const float *x, const float *r, const float *gamma, const float *beta, float eps,
                         int64_t rows, int channels, float *y, sdetr_stream_t stream);
+
+/* 3xTF32 operand split for the dense projections (tensor cores with fp32-class accuracy):
+ * x (rows, K) with row stride x_row_stride -> out (rows, 3K) = [hi | hi | lo] (layout_b = 0, activations) or
+ * [hi | lo | hi] (layout_b = 1, weights), hi = tf32(x), lo = tf32(x - hi); relu != 0 applies max(x, 0) first
+ * (fuses the FFN activation, salience_transformer.py:348).  One TF32 GEMM over K' = 3K of the two layouts
+ * yields A_hi.B_hi + A_hi.B_lo + A_lo.B_hi accumulated in fp32. */
+int sdetr_split_tf32(const float *x, int64_t x_row_stride, int64_t rows, int K, int layout_b, int relu, float *out,
+                     sdetr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,7 @@ SIGNATURES = {
     "sdetr_version": (_i, []),
     "sdetr_last_error": (ctypes.c_char_p, []),
     "sdetr_launch_count": (ctypes.c_ulonglong, []),
+    "sdetr_set_option": (_i, [ctypes.c_char_p, _i]),
     "sdetr_msda_forward": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
     "sdetr_msda_forward_ex": (_i, [_vp, _i64, _i64] + [_vp] * 5 + [_i] * 7 + [_vp, _i, _vp]),
     "sdetr_msda_fused_forward": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp] + [_i] * 7 + [_vp, _i, _vp]),
@@ -43,6 +44,7 @@ SIGNATURES = {
     "sdetr_zero_masked_rows": (_i, [_vp, _i64, _i, _vp, _i64, _vp]),
     "sdetr_class_max_times_fg": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
     "sdetr_add_layernorm": (_i, [_vp, _vp, _vp, _vp, _f, _i64, _i, _vp, _vp]),
+    "sdetr_split_tf32": (_i, [_vp, _i64, _i64, _i, _i, _i, _vp, _vp]),
 }
 
 
@@ -60,6 +62,10 @@ def lib():
             fn.restype, fn.argtypes = res, args
         _lib = cdll
     return _lib
+
+
+def set_option(name: str, value: int):
+    _check(lib().sdetr_set_option(name.encode(), int(value)), "sdetr_set_option")
 
 
 def launch_count() -> int:
@@ -309,4 +315,18 @@ def add_layernorm(x, r, gamma, beta, eps: float = 1e-5, out=None):
                                    _req(gamma, "gamma", torch.float32), _req(beta, "beta", torch.float32), eps, rows, c,
                                    out.data_ptr(), _stream())
     _check(rc, "sdetr_add_layernorm")
+    return out
+
+
+def split_tf32(x, layout_b: bool = False, relu: bool = False):
+    """(..., K) fp32 with contiguous rows -> (rows, 3K) 3xTF32 operand ([hi|hi|lo] or, for weights, [hi|lo|hi])."""
+    K = x.shape[-1]
+    if not (x.is_cuda and x.dtype == torch.float32 and x.stride(-1) == 1):
+        raise RuntimeError("split_tf32 needs a CUDA float32 tensor with unit last stride")
+    x2 = x if x.dim() == 2 else x.reshape(-1, K)  # view when rows are uniformly strided
+    rows = x2.shape[0]
+    out = torch.empty(rows, 3 * K, device=x.device, dtype=torch.float32)
+    rc = lib().sdetr_split_tf32(x2.data_ptr(), x2.stride(0) if rows > 1 else K, rows, K, int(layout_b), int(relu),
+                                out.data_ptr(), _stream())
+    _check(rc, "sdetr_split_tf32")
     return out

@@ -36,53 +36,11 @@ struct MsdaFwdParams {
 
 constexpr int kThreads = 256;
 
-// ---- lane-distributed small arrays -----------------------------------------------------------------
-// N floats spread over LANES lanes, PER = ceil(N/LANES) contiguous elements per lane.
-template <int N, int LANES>
-struct GroupArray {
-    static constexpr int PER = (N + LANES - 1) / LANES;
-    float r[PER];
-
-    __device__ __forceinline__ void load(const float *base, int lane) {
-        if constexpr (N % LANES == 0 && PER % 4 == 0) {
-#pragma unroll
-            for (int i = 0; i < PER / 4; ++i) {
-                float4 v = ld_stream_f4(base + lane * PER + 4 * i);
-                r[4 * i] = v.x, r[4 * i + 1] = v.y, r[4 * i + 2] = v.z, r[4 * i + 3] = v.w;
-            }
-        } else if constexpr (N % LANES == 0 && PER % 2 == 0) {
-#pragma unroll
-            for (int i = 0; i < PER / 2; ++i) {
-                float2 v = __ldg(reinterpret_cast<const float2 *>(base + lane * PER + 2 * i));
-                r[2 * i] = v.x, r[2 * i + 1] = v.y;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < PER; ++i) r[i] = (lane * PER + i < N) ? __ldg(base + lane * PER + i) : 0.f;
-        }
-    }
-    __device__ __forceinline__ void store(float *base, int lane) const {
-        if constexpr (N % LANES == 0 && PER % 4 == 0) {
-#pragma unroll
-            for (int i = 0; i < PER / 4; ++i)
-                st_stream_f4(base + lane * PER + 4 * i, make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]));
-        } else if constexpr (N % LANES == 0 && PER % 2 == 0) {
-#pragma unroll
-            for (int i = 0; i < PER / 2; ++i)
-                *reinterpret_cast<float2 *>(base + lane * PER + 2 * i) = make_float2(r[2 * i], r[2 * i + 1]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < PER; ++i)
-                if (lane * PER + i < N) base[lane * PER + i] = r[i];
-        }
-    }
-    // broadcast element E (compile time) to every lane of the group
-    template <int E>
-    __device__ __forceinline__ float get() const {
-        return __shfl_sync(0xffffffffu, r[E % PER], E / PER, LANES);
-    }
-};
-
+// ---- per-point setup, spread over the lanes of a group ----------------------------------------------------
+// Point e (= level*P + point) of a (query, head) is owned by lane e % LANES, slot e / LANES.  The owner turns
+// its sampling location into everything the gather needs -- top-left token index, two "has a neighbour" bits
+// and the four corner weights (already multiplied by the attention weight, zero for corners outside the map)
+// -- exactly once; the other lanes receive it with five shuffles instead of redoing ~50 instructions each.
 template <int LANES>
 __device__ __forceinline__ float group_max(float v) {
 #pragma unroll
@@ -102,70 +60,122 @@ struct LevelGeom {
     int64_t start;  // level_start_index
 };
 
-// one sampling point of one level: issue the (up to) four corner loads
-struct Corner4 {
-    float4 v00, v01, v10, v11;
+struct PointSetup {
+    uint32_t packed;  // bits 0..29 token index (row-major) of the clamped top-left corner, bit 30 dx, bit 31 dy
     float w00, w01, w10, w11;
 };
 
-__device__ __forceinline__ void fetch_point(Corner4 &c, const float *__restrict__ lvl_base, int64_t tstride,
-                                            const LevelGeom &g, float x, float y, float a) {
-    const float h_im = fmaf(y, g.Hf, -0.5f), w_im = fmaf(x, g.Wf, -0.5f);  // .cuh:274-275
-    const bool in = h_im > -1.f && w_im > -1.f && h_im < g.Hf && w_im < g.Wf;  // .cuh:277
+__device__ __forceinline__ PointSetup make_setup(float x, float y, float a, int H, int W, float Hf, float Wf) {
+    PointSetup s;
+    const float h_im = fmaf(y, Hf, -0.5f), w_im = fmaf(x, Wf, -0.5f);           // .cuh:274-275
+    const bool in = h_im > -1.f && w_im > -1.f && h_im < Hf && w_im < Wf;        // .cuh:277
     const float hf = floorf(h_im), wf = floorf(w_im);
     const int y0 = (int)hf, x0 = (int)wf;
     const float ly = h_im - hf, lx = w_im - wf, hy = 1.f - ly, hx = 1.f - lx;
-    const bool top = in && y0 >= 0, bot = in && y0 + 1 <= g.H - 1;
-    const bool lef = x0 >= 0, rig = x0 + 1 <= g.W - 1;
-    const float *p = lvl_base + (int64_t)(y0 * g.W + x0) * tstride;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    c.v00 = (top && lef) ? ldg_f4(p) : z;
-    c.v01 = (top && rig) ? ldg_f4(p + tstride) : z;
-    c.v10 = (bot && lef) ? ldg_f4(p + (int64_t)g.W * tstride) : z;
-    c.v11 = (bot && rig) ? ldg_f4(p + (int64_t)(g.W + 1) * tstride) : z;
-    c.w00 = a * hy * hx, c.w01 = a * hy * lx, c.w10 = a * ly * hx, c.w11 = a * ly * lx;
+    const bool top = y0 >= 0, bot = y0 + 1 <= H - 1, lef = x0 >= 0, rig = x0 + 1 <= W - 1;
+    const float at = in ? a : 0.f;
+    s.w00 = (top && lef) ? at * hy * hx : 0.f;
+    s.w01 = (top && rig) ? at * hy * lx : 0.f;
+    s.w10 = (bot && lef) ? at * ly * hx : 0.f;
+    s.w11 = (bot && rig) ? at * ly * lx : 0.f;
+    // clamped corner rows/cols: every address is inside the level, invalid corners carry weight 0
+    const int rt = max(y0, 0), rb = min(y0 + 1, H - 1), cl = max(x0, 0), cr = min(x0 + 1, W - 1);
+    const uint32_t idx = (uint32_t)(rt * W + cl), dx = (uint32_t)(cr - cl), dy = (uint32_t)(rb - rt);
+    s.packed = in ? (idx | (dx << 30) | (dy << 31)) : 0u;
+    return s;
 }
 
-__device__ __forceinline__ void accumulate(float4 &acc, const Corner4 &c) {
-    acc.x = fmaf(c.w00, c.v00.x, fmaf(c.w01, c.v01.x, fmaf(c.w10, c.v10.x, fmaf(c.w11, c.v11.x, acc.x))));
-    acc.y = fmaf(c.w00, c.v00.y, fmaf(c.w01, c.v01.y, fmaf(c.w10, c.v10.y, fmaf(c.w11, c.v11.y, acc.y))));
-    acc.z = fmaf(c.w00, c.v00.z, fmaf(c.w01, c.v01.z, fmaf(c.w10, c.v10.z, fmaf(c.w11, c.v11.z, acc.z))));
-    acc.w = fmaf(c.w00, c.v00.w, fmaf(c.w01, c.v01.w, fmaf(c.w10, c.v10.w, fmaf(c.w11, c.v11.w, acc.w))));
+// address = base + index * stride_bytes in ONE mad.wide.u32
+__device__ __forceinline__ const float *row_ptr(const char *base, uint32_t index, uint32_t stride_bytes) {
+    uint64_t r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(index), "r"(stride_bytes), "l"(reinterpret_cast<uint64_t>(base)));
+    return reinterpret_cast<const float *>(r);
 }
 
-// compile-time loops over levels / points
-template <int L, int P, int LANES, int LVL = 0>
+__device__ __forceinline__ void fma4(float4 &acc, float w, const float4 &v) {
+    acc.x = fmaf(w, v.x, acc.x), acc.y = fmaf(w, v.y, acc.y), acc.z = fmaf(w, v.z, acc.z), acc.w = fmaf(w, v.w, acc.w);
+}
+
+// gather of one level: the P points are fetched together (4*P independent 128-bit loads per lane).
+// Addresses are base64 + token_index * stride with ONE IMAD.WIDE.U32 each (32-bit index and stride).
+template <int L, int P, int LANES, int SLOTS, int LVL = 0>
 struct LevelLoop {
-    template <class LocArr, class AttArr>
-    static __device__ __forceinline__ void run(float4 &acc, const LocArr &loc, const AttArr &att,
-                                               const LevelGeom (&geo)[L], const float *__restrict__ vbase,
-                                               int64_t tstride) {
-        Corner4 c[P];
-        const float *lvl_base = vbase + geo[LVL].start * tstride;
-        fetch_all<0>(c, loc, att, geo[LVL], lvl_base, tstride);
+    static __device__ __forceinline__ void run(float4 &acc, const PointSetup (&st)[SLOTS], const LevelGeom (&geo)[L],
+                                               const float *__restrict__ vbase, uint32_t ts) {
+        // byte arithmetic on purpose: address = 64-bit level base + (32-bit token index) * (32-bit byte stride)
+        const char *lvl_base = reinterpret_cast<const char *>(vbase + geo[LVL].start * (int64_t)ts);
+        const uint32_t tsb = ts * 4u;
+        const uint32_t W = (uint32_t)geo[LVL].W;
+        float4 v[P][4];
+        float w[P][4];
 #pragma unroll
-        for (int p = 0; p < P; ++p) accumulate(acc, c[p]);
-        if constexpr (LVL + 1 < L) LevelLoop<L, P, LANES, LVL + 1>::run(acc, loc, att, geo, vbase, tstride);
+        for (int pt = 0; pt < P; ++pt) {
+            const int e = LVL * P + pt;  // compile-time after unrolling
+            const int src = e % LANES, slot = e / LANES;
+            const uint32_t pk = __shfl_sync(0xffffffffu, st[slot].packed, src, LANES);
+            w[pt][0] = __shfl_sync(0xffffffffu, st[slot].w00, src, LANES);
+            w[pt][1] = __shfl_sync(0xffffffffu, st[slot].w01, src, LANES);
+            w[pt][2] = __shfl_sync(0xffffffffu, st[slot].w10, src, LANES);
+            w[pt][3] = __shfl_sync(0xffffffffu, st[slot].w11, src, LANES);
+            const uint32_t i00 = pk & 0x3fffffffu;
+            const uint32_t i01 = i00 + ((pk >> 30) & 1u);
+            const uint32_t i10 = i00 + (pk >> 31) * W;
+            const uint32_t i11 = i10 + ((pk >> 30) & 1u);
+            v[pt][0] = ldg_f4(row_ptr(lvl_base, i00, tsb));
+            v[pt][1] = ldg_f4(row_ptr(lvl_base, i01, tsb));
+            v[pt][2] = ldg_f4(row_ptr(lvl_base, i10, tsb));
+            v[pt][3] = ldg_f4(row_ptr(lvl_base, i11, tsb));
+        }
+#pragma unroll
+        for (int pt = 0; pt < P; ++pt) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) fma4(acc, w[pt][c], v[pt][c]);
+        }
+        if constexpr (LVL + 1 < L) LevelLoop<L, P, LANES, SLOTS, LVL + 1>::run(acc, st, geo, vbase, ts);
     }
-    template <int PT, class LocArr, class AttArr>
-    static __device__ __forceinline__ void fetch_all(Corner4 (&c)[P], const LocArr &loc, const AttArr &att,
-                                                     const LevelGeom &g, const float *__restrict__ lvl_base,
-                                                     int64_t tstride) {
-        constexpr int E = LVL * P + PT;
-        const float x = loc.template get<2 * E>();
-        const float y = loc.template get<2 * E + 1>();
-        const float a = att.template get<E>();
-        fetch_point(c[PT], lvl_base, tstride, g, x, y, a);
-        if constexpr (PT + 1 < P) fetch_all<PT + 1>(c, loc, att, g, lvl_base, tstride);
+};
+
+// level geometry of the point owned by (slot, lane): only the levels a slot can span are tested
+template <int L, int P, int LANES, int SLOT>
+__device__ __forceinline__ void slot_geom(const LevelGeom (&geo)[L], int lane, int &l, int &H, int &W, float &Hf, float &Wf) {
+    constexpr int lo = (SLOT * LANES) / P < L - 1 ? (SLOT * LANES) / P : L - 1;
+    constexpr int hi = (SLOT * LANES + LANES - 1) / P < L - 1 ? (SLOT * LANES + LANES - 1) / P : L - 1;
+    const int e = SLOT * LANES + lane;
+    l = min(e / P, L - 1);
+    H = geo[lo].H, W = geo[lo].W, Hf = geo[lo].Hf, Wf = geo[lo].Wf;
+#pragma unroll
+    for (int k = lo + 1; k <= hi; ++k)
+        if (l == k) H = geo[k].H, W = geo[k].W, Hf = geo[k].Hf, Wf = geo[k].Wf;
+}
+
+template <int L, int P, int LANES, int SLOTS, bool FUSED, int SLOT = 0>
+struct SlotLoop {
+    // FUSED: (lx, ly) raw offsets -> locations (needs ref), la normalised; then the setup of every slot
+    static __device__ __forceinline__ void run(PointSetup (&st)[SLOTS], float (&lx)[SLOTS], float (&ly)[SLOTS],
+                                               float (&la)[SLOTS], const LevelGeom (&geo)[L], int lane,
+                                               const float *__restrict__ rrow, float inv_sum) {
+        int l, H, W;
+        float Hf, Wf;
+        slot_geom<L, P, LANES, SLOT>(geo, lane, l, H, W, Hf, Wf);
+        if constexpr (FUSED) {
+            const float2 r = __ldg(reinterpret_cast<const float2 *>(rrow) + l);
+            lx[SLOT] = r.x + __fdividef(lx[SLOT], Wf);  // loc = ref + off / (W_l, H_l) (ms_deform_attn.py:339-344)
+            ly[SLOT] = r.y + __fdividef(ly[SLOT], Hf);
+            la[SLOT] = la[SLOT] * inv_sum;
+        }
+        st[SLOT] = make_setup(lx[SLOT], ly[SLOT], la[SLOT], H, W, Hf, Wf);
+        if constexpr (SLOT + 1 < SLOTS)
+            SlotLoop<L, P, LANES, SLOTS, FUSED, SLOT + 1>::run(st, lx, ly, la, geo, lane, rrow, inv_sum);
     }
 };
 
 // ---- the specialised kernel -------------------------------------------------------------------------
-template <int D, int L, int P, bool FUSED, bool HEAD_MAJOR>
-__global__ void __launch_bounds__(kThreads, 2) msda_fwd_kernel(const MsdaFwdParams p) {
+template <int D, int L, int P, bool FUSED, bool HEAD_MAJOR, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) msda_fwd_kernel(const MsdaFwdParams p) {
     constexpr int LANES = D / 4;
     constexpr int GROUPS = kThreads / LANES;
     constexpr int NP = L * P;
+    constexpr int SLOTS = (NP + LANES - 1) / LANES;
     const int lane = threadIdx.x % LANES;
     const int grp = threadIdx.x / LANES;
 
@@ -189,13 +199,12 @@ __global__ void __launch_bounds__(kThreads, 2) msda_fwd_kernel(const MsdaFwdPara
         q_step = GROUPS;
         iters = (p.chunk + GROUPS - 1) / GROUPS;
     } else {
-        int64_t item = (int64_t)blockIdx.x * GROUPS + grp;
-        in_range = item < (int64_t)p.batch * p.nq * p.heads;
+        b = blockIdx.y;
+        uint32_t item = blockIdx.x * GROUPS + grp;  // (query, head) of this image
+        in_range = item < (uint32_t)p.nq * (uint32_t)p.heads;
         if (!in_range) item = 0;
-        m = (int)(item % p.heads);
-        const int64_t bq = item / p.heads;
-        q_first = q_last = (int)(bq % p.nq);
-        b = (int)(bq / p.nq);
+        q_first = q_last = (int)(item / (uint32_t)p.heads);
+        m = (int)(item - (uint32_t)q_first * (uint32_t)p.heads);
         q_step = 0;
         iters = 1;
     }
@@ -206,52 +215,63 @@ __global__ void __launch_bounds__(kThreads, 2) msda_fwd_kernel(const MsdaFwdPara
         qi = min(qi, q_last);
         const int q = p.order ? __ldg(p.order + (int64_t)b * p.nq + qi) : qi;
         const int64_t row = (int64_t)b * p.nq + q;  // (image, query) row of every per-query tensor
+        const int64_t qm = row * p.heads + m;
 
-        GroupArray<2 * NP, LANES> loc;
-        GroupArray<NP, LANES> att;
+        // ---- phase 1: each lane prepares its own points -----------------------------------------------------
+        float lx[SLOTS], ly[SLOTS], la[SLOTS];
+        float inv_sum = 1.f;
+        const float *rrow = nullptr;
         if constexpr (FUSED) {
             const float *prow = p.proj + row * p.proj_stride;
-            loc.load(prow + (int64_t)m * 2 * NP, lane);              // raw offsets of this head
-            att.load(prow + (int64_t)p.heads * 2 * NP + (int64_t)m * NP, lane);  // raw logits of this head
-            // softmax over the L*P logits (ms_deform_attn.py:326-329)
+            const float *offs = prow + (int64_t)m * 2 * NP;                      // raw offsets of this head
+            const float *logit = prow + (int64_t)p.heads * 2 * NP + (int64_t)m * NP;  // raw logits of this head
             float mx = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < att.PER; ++i)
-                if (lane * att.PER + i < NP) mx = fmaxf(mx, att.r[i]);
-            mx = group_max<LANES>(mx);
+            for (int s = 0; s < SLOTS; ++s) {
+                const int e = s * LANES + lane;
+                const bool ok = (NP % LANES == 0) || e < NP;
+                const float2 o = ok ? __ldg(reinterpret_cast<const float2 *>(offs) + e) : make_float2(0.f, 0.f);
+                lx[s] = o.x, ly[s] = o.y;
+                la[s] = ok ? __ldg(logit + e) : -INFINITY;
+                mx = fmaxf(mx, la[s]);
+            }
+            mx = group_max<LANES>(mx);  // softmax over the L*P logits (ms_deform_attn.py:326-329)
             float sum = 0.f;
 #pragma unroll
-            for (int i = 0; i < att.PER; ++i) {
-                att.r[i] = (lane * att.PER + i < NP) ? expf(att.r[i] - mx) : 0.f;
-                sum += att.r[i];
-            }
+            for (int s = 0; s < SLOTS; ++s) la[s] = __expf(la[s] - mx), sum += la[s];
             sum = group_sum<LANES>(sum);
-#pragma unroll
-            for (int i = 0; i < att.PER; ++i) att.r[i] = att.r[i] / sum;
-            // loc = ref + off / (W_l, H_l) (ms_deform_attn.py:339-344)
-            const float *rrow = p.ref + row * (2 * L);
-#pragma unroll
-            for (int i = 0; i < loc.PER; ++i) {
-                const int e = lane * loc.PER + i;  // element = (l*P + pt)*2 + xy
-                const int l = min(e / (2 * P), L - 1);
-                const int xy = e & 1;
-                float norm = xy ? geo[0].Hf : geo[0].Wf;
-#pragma unroll
-                for (int k = 1; k < L; ++k)
-                    if (l == k) norm = xy ? geo[k].Hf : geo[k].Wf;
-                loc.r[i] = __ldg(rrow + 2 * l + xy) + loc.r[i] / norm;
-            }
-            if (p.loc_out && active) loc.store(p.loc_out + (row * p.heads + m) * (2 * NP), lane);
-            if (p.attn_out && active) att.store(p.attn_out + (row * p.heads + m) * NP, lane);
+            inv_sum = __frcp_rn(sum);
+            rrow = p.ref + row * (2 * L);
         } else {
-            loc.load(p.loc + (row * p.heads + m) * (2 * NP), lane);
-            att.load(p.attn + (row * p.heads + m) * NP, lane);
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                const int e = s * LANES + lane;
+                const bool ok = (NP % LANES == 0) || e < NP;
+                const float2 o = ok ? __ldg(reinterpret_cast<const float2 *>(p.loc + qm * (2 * NP)) + e) : make_float2(0.f, 0.f);
+                lx[s] = o.x, ly[s] = o.y;
+                la[s] = ok ? __ldg(p.attn + qm * NP + e) : 0.f;
+            }
+        }
+        PointSetup st[SLOTS];
+        SlotLoop<L, P, LANES, SLOTS, FUSED>::run(st, lx, ly, la, geo, lane, rrow, inv_sum);
+        if constexpr (FUSED) {
+            if (active) {
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) {
+                    const int e = s * LANES + lane;
+                    if ((NP % LANES == 0) || e < NP) {
+                        if (p.loc_out) reinterpret_cast<float2 *>(p.loc_out + qm * (2 * NP))[e] = make_float2(lx[s], ly[s]);
+                        if (p.attn_out) p.attn_out[qm * NP + e] = la[s];
+                    }
+                }
+            }
         }
 
+        // ---- phase 2: gather ------------------------------------------------------------------------------------
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         const float *vbase = p.value + (int64_t)b * p.v_bstride + (int64_t)m * D + lane * 4;
-        LevelLoop<L, P, LANES>::run(acc, loc, att, geo, vbase, p.v_tstride);
-        if (active) st_stream_f4(p.out + (row * p.heads + m) * D + lane * 4, acc);
+        LevelLoop<L, P, LANES, SLOTS>::run(acc, st, geo, vbase, (uint32_t)p.v_tstride);
+        if (active) st_stream_f4(p.out + qm * D + lane * 4, acc);
     }
 }
 
@@ -304,36 +324,46 @@ __global__ void __launch_bounds__(kThreads) msda_fwd_generic_kernel(const MsdaFw
                 x = __ldg(lp), y = __ldg(lp + 1);
                 a = __ldg(p.attn + (row * p.heads + m) * NP + e);
             }
-            Corner4 c;
-            fetch_point(c, lvl_base, p.v_tstride, g, x, y, a);
-            accumulate(acc, c);
+            const PointSetup st = make_setup(x, y, a, g.H, g.W, g.Hf, g.Wf);
+            const float *p00 = lvl_base + (int64_t)(st.packed & 0x3fffffffu) * p.v_tstride;
+            const int64_t dx = (st.packed & 0x40000000u) ? p.v_tstride : 0;
+            const int64_t dy = (st.packed & 0x80000000u) ? (int64_t)g.W * p.v_tstride : 0;
+            fma4(acc, st.w00, ldg_f4(p00));
+            fma4(acc, st.w01, ldg_f4(p00 + dx));
+            fma4(acc, st.w10, ldg_f4(p00 + dy));
+            fma4(acc, st.w11, ldg_f4(p00 + dy + dx));
         }
     }
     *reinterpret_cast<float4 *>(p.out + (row * p.heads + m) * D + lane * 4) = acc;
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
-template <int D, int L, int P>
+static int g_minb = 4;    // tuning knobs (sdetr_set_option)
+static int g_chunk = 64;
+
+template <int D, int L, int P, int MINB>
 static void launch_special(const MsdaFwdParams &p, bool fused, int schedule, cudaStream_t s) {
     constexpr int GROUPS = kThreads / (D / 4);
     if (schedule == 1) {
         dim3 grid((p.nq + p.chunk - 1) / p.chunk, p.heads, p.batch);
         if (fused)
-            msda_fwd_kernel<D, L, P, true, true><<<grid, kThreads, 0, s>>>(p);
+            msda_fwd_kernel<D, L, P, true, true, MINB><<<grid, kThreads, 0, s>>>(p);
         else
-            msda_fwd_kernel<D, L, P, false, true><<<grid, kThreads, 0, s>>>(p);
+            msda_fwd_kernel<D, L, P, false, true, MINB><<<grid, kThreads, 0, s>>>(p);
     } else {
-        const int64_t items = (int64_t)p.batch * p.nq * p.heads;
-        dim3 grid((unsigned)((items + GROUPS - 1) / GROUPS));
+        const int64_t items = (int64_t)p.nq * p.heads;
+        dim3 grid((unsigned)((items + GROUPS - 1) / GROUPS), p.batch);
         if (fused)
-            msda_fwd_kernel<D, L, P, true, false><<<grid, kThreads, 0, s>>>(p);
+            msda_fwd_kernel<D, L, P, true, false, MINB><<<grid, kThreads, 0, s>>>(p);
         else
-            msda_fwd_kernel<D, L, P, false, false><<<grid, kThreads, 0, s>>>(p);
+            msda_fwd_kernel<D, L, P, false, false, MINB><<<grid, kThreads, 0, s>>>(p);
     }
 }
 
 static int msda_forward_dispatch(MsdaFwdParams p, bool fused, int head_dim, int levels, int points, int schedule,
                                  cudaStream_t s) {
+    SDETR_REQUIRE(p.nq >= 0, SDETR_ERR_INVALID_ARG, "msda_forward: negative num_query");
+    if (p.nq == 0) return SDETR_OK;  // empty query set: nothing to do (empty tensors have null data pointers)
     SDETR_REQUIRE(p.value && p.shapes && p.lsi && p.out, SDETR_ERR_INVALID_ARG, "msda_forward: null pointer");
     SDETR_REQUIRE(fused ? (p.ref && p.proj) : (p.loc && p.attn), SDETR_ERR_INVALID_ARG,
                   "msda_forward: null sampling input");
@@ -345,17 +375,19 @@ static int msda_forward_dispatch(MsdaFwdParams p, bool fused, int head_dim, int 
     SDETR_REQUIRE(aligned16(p.value) && aligned16(p.out) && p.v_tstride % 4 == 0 && p.v_bstride % 4 == 0,
                   SDETR_ERR_INVALID_ARG, "msda_forward: value/output must be 16-byte aligned");
     SDETR_REQUIRE(schedule == 0 || schedule == 1, SDETR_ERR_INVALID_ARG, "msda_forward: bad schedule %d", schedule);
-    if (p.nq == 0) return SDETR_OK;
-    p.chunk = 64;
+    p.chunk = g_chunk;
+    SDETR_REQUIRE(p.batch <= 65535, SDETR_ERR_UNSUPPORTED, "msda_forward: batch > 65535");
     bool special = true;
     if (fused) special = (p.proj_stride % 4 == 0) && aligned16(p.proj);
     else special = aligned16(p.loc) && aligned16(p.attn);
-    if (special && head_dim == 32 && levels == 4 && points == 4)
-        launch_special<32, 4, 4>(p, fused, schedule, s);
-    else if (special && head_dim == 32 && levels == 5 && points == 4)
-        launch_special<32, 5, 4>(p, fused, schedule, s);
+    if (special && head_dim == 32 && levels == 4 && points == 4) {
+        if (g_minb == 3) launch_special<32, 4, 4, 3>(p, fused, schedule, s);
+        else if (g_minb == 4) launch_special<32, 4, 4, 4>(p, fused, schedule, s);
+        else launch_special<32, 4, 4, 2>(p, fused, schedule, s);
+    } else if (special && head_dim == 32 && levels == 5 && points == 4)
+        launch_special<32, 5, 4, 2>(p, fused, schedule, s);
     else if (special && head_dim == 64 && levels == 4 && points == 4)
-        launch_special<64, 4, 4>(p, fused, schedule, s);
+        launch_special<64, 4, 4, 2>(p, fused, schedule, s);
     else {
         const int64_t threads = (int64_t)p.batch * p.nq * p.heads * (head_dim / 4);
         msda_fwd_generic_kernel<<<(unsigned)((threads + kThreads - 1) / kThreads), kThreads, 0, s>>>(
@@ -367,6 +399,21 @@ static int msda_forward_dispatch(MsdaFwdParams p, bool fused, int head_dim, int 
 }  // namespace sdetr
 
 using namespace sdetr;
+
+extern "C" int sdetr_set_option(const char *name, int value) {
+    SDETR_REQUIRE(name, SDETR_ERR_INVALID_ARG, "set_option: null name");
+    const auto eq = [&](const char *k) { int i = 0; while (k[i] && k[i] == name[i]) ++i; return k[i] == 0 && name[i] == 0; };
+    if (eq("msda_min_blocks")) {
+        SDETR_REQUIRE(value >= 2 && value <= 4, SDETR_ERR_INVALID_ARG, "set_option: msda_min_blocks in 2..4");
+        g_minb = value;
+    } else if (eq("msda_chunk")) {
+        SDETR_REQUIRE(value >= 8 && value <= 4096, SDETR_ERR_INVALID_ARG, "set_option: msda_chunk in 8..4096");
+        g_chunk = value;
+    } else {
+        SDETR_REQUIRE(false, SDETR_ERR_INVALID_ARG, "set_option: unknown option %s", name);
+    }
+    return SDETR_OK;
+}
 
 extern "C" int sdetr_msda_forward_ex(const float *value, int64_t value_batch_stride, int64_t value_token_stride,
                                      const int64_t *spatial_shapes, const int64_t *level_start_index,

@@ -115,6 +115,141 @@ __device__ __forceinline__ void block_radix_sort(Load0 load0, int n, uint32_t *k
     radix_pass(from_a, n, 24, kb, vb, sm);
 }
 
+
+// ---- radix select + stable compaction + bitonic sort (the fast path) ------------------------------------------
+// A full LSD sort of a 16 800-token level costs ~200 us in one CTA (latency-bound passes).  Selection does
+// not need it: (1) find the k-th best key with four 8-bit histogram passes (all 1024 threads, per-warp private
+// histograms), (2) emit the winners in index order with one block-wide scan (ties at the threshold: lowest
+// indices first), (3) order the <= 16 384 survivors of an image with a shared-memory bitonic sort on unique
+// 64-bit (key, index) composites.  Same canonical order as the LSD path, ~10x less time.
+struct SelectSmem {
+    alignas(8) uint32_t hist[kSortWarps * 256];  // [warp][digit]
+    uint32_t total[256];
+    uint32_t scan[kSortWarps * 2];
+    uint32_t prefix, kth, need;
+};
+
+// k-th smallest key (1-based k, 1 <= k <= n) over key(i), i < n.  Returns T and how many keys == T belong
+// to the k smallest (the rest of them are cut).  All threads of the CTA must call it.
+template <class KeyFn>
+__device__ __forceinline__ void radix_select(KeyFn key, int n, int k, uint32_t &T, uint32_t &need_eq, SelectSmem &sm) {
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint32_t prefix = 0, mask = 0, remaining = (uint32_t)k;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = tid; i < kSortWarps * 256; i += kSortThreads) sm.hist[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += kSortThreads) {
+            const uint32_t kv = key(i);
+            if ((kv & mask) == prefix) atomicAdd(&sm.hist[warp * 256 + ((kv >> shift) & 255u)], 1u);
+        }
+        __syncthreads();
+        if (tid < 256) {
+            uint32_t t = 0;
+#pragma unroll 8
+            for (int w = 0; w < kSortWarps; ++w) t += sm.hist[w * 256 + tid];
+            sm.total[tid] = t;
+        }
+        __syncthreads();
+        if (warp == 0) {  // 256 bins: each lane scans 8 consecutive bins
+            const int lane = tid;
+            uint32_t v[8], s = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = sm.total[lane * 8 + j], s += v[j];
+            uint32_t inc = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            uint32_t before = inc - s;  // keys in bins below lane*8
+            if (remaining > before && remaining <= inc) {  // the k-th key falls into this lane's bins
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (remaining > before && remaining <= before + v[j]) {
+                        sm.prefix = prefix | ((uint32_t)(lane * 8 + j) << shift);
+                        sm.need = remaining - before;
+                    }
+                    before += v[j];
+                }
+            }
+        }
+        __syncthreads();
+        prefix = sm.prefix, remaining = sm.need;
+        mask |= 255u << shift;
+        __syncthreads();
+    }
+    T = prefix, need_eq = remaining;
+}
+
+// block-wide exclusive scan of a pair of counters (one value pair per thread)
+__device__ __forceinline__ void block_scan_pair(uint32_t a, uint32_t b, uint32_t &ea, uint32_t &eb, SelectSmem &sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t ia = a, ib = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) ia += ta, ib += tb;
+    }
+    if (lane == 31) sm.scan[warp * 2] = ia, sm.scan[warp * 2 + 1] = ib;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t wa = sm.scan[lane * 2], wb = sm.scan[lane * 2 + 1];
+        uint32_t xa = wa, xb = wb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t ta = __shfl_up_sync(0xffffffffu, xa, o), tb = __shfl_up_sync(0xffffffffu, xb, o);
+            if (lane >= o) xa += ta, xb += tb;
+        }
+        sm.scan[lane * 2] = xa - wa, sm.scan[lane * 2 + 1] = xb - wb;
+    }
+    __syncthreads();
+    ea = sm.scan[warp * 2] + ia - a, eb = sm.scan[warp * 2 + 1] + ib - b;
+    __syncthreads();
+}
+
+// Emit, in index order, the k best of key(i): all keys < T plus the first need_eq keys == T.
+// emit(position, i, key).  Each thread owns a contiguous run of indices.
+template <class KeyFn, class Emit>
+__device__ __forceinline__ void stable_compact(KeyFn key, int n, uint32_t T, uint32_t need_eq, Emit emit, SelectSmem &sm) {
+    const int ipt = (n + kSortThreads - 1) / kSortThreads;
+    const int begin = min(n, (int)threadIdx.x * ipt), end = min(n, begin + ipt);
+    uint32_t better = 0, equal = 0;
+    for (int i = begin; i < end; ++i) {
+        const uint32_t kv = key(i);
+        better += kv < T, equal += kv == T;
+    }
+    uint32_t eb, ee;
+    block_scan_pair(better, equal, eb, ee, sm);
+    for (int i = begin; i < end; ++i) {
+        const uint32_t kv = key(i);
+        if (kv < T) {
+            emit(eb + min(ee, need_eq), i, kv);
+            ++eb;
+        } else if (kv == T) {
+            if (ee < need_eq) emit(eb + ee, i, kv);
+            ++ee;
+        }
+    }
+}
+
+// in-place ascending bitonic sort of N (power of two) 64-bit keys in shared memory, 1024 threads
+__device__ __forceinline__ void bitonic_sort_smem(unsigned long long *a, int N) {
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < (N >> 1); i += kSortThreads) {
+                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                const int hi = lo | j;
+                const unsigned long long x = a[lo], y = a[hi];
+                const bool up = (lo & k) == 0;
+                if ((x > y) == up) a[lo] = y, a[hi] = x;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+constexpr int kBitonicMax = 16384;  // 128 KB of shared memory
+
 // ---- kernels ---------------------------------------------------------------------------------------------
 
 // per-level minimum over the whole (batch, HW_l) score tensor (salience_transformer.py:146 `score.min()`)
@@ -266,6 +401,99 @@ __global__ void __launch_bounds__(kSortThreads) topk_kernel(const float *__restr
         out[(int64_t)blockIdx.x * k + j] = (int64_t)((volatile uint32_t *)vb)[off + j];
 }
 
+
+// ---- fast-path kernels ---------------------------------------------------------------------------------------
+// (image, level): top-k_l selection -> candidates (key, token) in index order at [b*K + koff[l] ...)
+__global__ void __launch_bounds__(kSortThreads) level_select_kernel(const float *__restrict__ raw,
+                                                                    const uint8_t *__restrict__ mask,
+                                                                    const float *__restrict__ lmin, LevelTable tb, int nv,
+                                                                    int K, uint32_t *__restrict__ ck,
+                                                                    uint32_t *__restrict__ cv) {
+    __shared__ SelectSmem sm;
+    const int b = blockIdx.x / tb.L, l = blockIdx.x % tb.L;
+    const int k = tb.k[l];
+    if (k == 0) return;
+    const int64_t off = (int64_t)b * nv + tb.start[l];
+    const float fill = __ldg(lmin + l);
+    auto key = [=](int i) { return desc_key(__ldg(mask + off + i) ? fill : __ldg(raw + off + i)); };
+    uint32_t T, need;
+    radix_select(key, tb.size[l], k, T, need, sm);
+    const int64_t dst = (int64_t)b * K + tb.koff[l];
+    const uint32_t start = (uint32_t)tb.start[l];
+    stable_compact(key, tb.size[l], T, need,
+                   [=](uint32_t pos, int i, uint32_t kv) { ck[dst + pos] = kv, cv[dst + pos] = start + (uint32_t)i; }, sm);
+}
+
+// image: order the K candidates by (score desc, token asc) and emit selected_inds / selected_score; then, if
+// requested, the spatial-cell processing order of the sorted list.  K <= kBitonicMax.
+__global__ void __launch_bounds__(kSortThreads) merge_bitonic_kernel(const uint32_t *__restrict__ ck,
+                                                                     const uint32_t *__restrict__ cv, LevelTable tb,
+                                                                     int K, int N, int cell_px, int cells_x,
+                                                                     int64_t *__restrict__ sel_inds,
+                                                                     float *__restrict__ sel_score,
+                                                                     int32_t *__restrict__ tile_order) {
+    extern __shared__ unsigned long long keys[];
+    const int b = blockIdx.x;
+    const int64_t base = (int64_t)b * K;
+    for (int j = threadIdx.x; j < N; j += kSortThreads)
+        keys[j] = j < K ? ((unsigned long long)ck[base + j] << 32) | cv[base + j] : ~0ull;
+    __syncthreads();
+    bitonic_sort_smem(keys, N);
+    for (int j = threadIdx.x; j < K; j += kSortThreads) {
+        const unsigned long long e = keys[j];
+        sel_inds[base + j] = (int64_t)(e & 0xffffffffull);
+        sel_score[base + j] = desc_key_inv((uint32_t)(e >> 32));
+    }
+    if (!tile_order) return;
+    __syncthreads();
+    for (int j = threadIdx.x; j < N; j += kSortThreads) {
+        unsigned long long e = ~0ull;
+        if (j < K) {
+            const int t = (int)(keys[j] & 0xffffffffull);
+            int l = 0;
+#pragma unroll
+            for (int u = 1; u < kMaxLevels; ++u)
+                if (u < tb.L && t >= tb.start[u]) l = u;
+            const int r = t - tb.start[l];
+            const int y = r / tb.width[l], x = r - y * tb.width[l];
+            const int cy = (y * tb.stride[l] + tb.stride[l] / 2) / cell_px;
+            const int cx = (x * tb.stride[l] + tb.stride[l] / 2) / cell_px;
+            e = ((unsigned long long)(((uint32_t)(cy * cells_x + cx) << 3) | (uint32_t)l) << 32) | (uint32_t)j;
+        }
+        __syncthreads();  // every thread has read keys[j] of this round before anyone overwrites it
+        keys[j] = e;
+    }
+    __syncthreads();
+    bitonic_sort_smem(keys, N);
+    for (int j = threadIdx.x; j < K; j += kSortThreads) tile_order[base + j] = (int32_t)(keys[j] & 0xffffffffull);
+}
+
+// segment: top-k (k <= 2048) by radix select + compaction + bitonic sort of the winners
+constexpr int kTopkFast = 2048;
+__global__ void __launch_bounds__(kSortThreads) topk_select_kernel(const float *__restrict__ score, int n, int k, int N,
+                                                                   int64_t *__restrict__ out) {
+    __shared__ SelectSmem sm;
+    static_assert(sizeof(sm.hist) >= kTopkFast * sizeof(unsigned long long), "winner buffer aliases the histograms");
+    unsigned long long *win = reinterpret_cast<unsigned long long *>(sm.hist);  // free once radix_select returned
+    const int64_t off = (int64_t)blockIdx.x * n;
+    auto key = [=](int i) { return desc_key(__ldg(score + off + i)); };
+    uint32_t T, need;
+    radix_select(key, n, k, T, need, sm);
+    for (int j = threadIdx.x; j < N; j += kSortThreads) win[j] = ~0ull;
+    __syncthreads();
+    stable_compact(key, n, T, need,
+                   [&](uint32_t pos, int i, uint32_t kv) { win[pos] = ((unsigned long long)kv << 32) | (uint32_t)i; }, sm);
+    __syncthreads();
+    bitonic_sort_smem(win, N);
+    for (int j = threadIdx.x; j < k; j += kSortThreads) out[(int64_t)blockIdx.x * k + j] = (int64_t)(win[j] & 0xffffffffull);
+}
+
+static int next_pow2(int x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace sdetr
@@ -326,10 +554,30 @@ extern "C" int sdetr_salience_select(const float *raw_score, const uint8_t *mask
     const int64_t fg_blocks = (total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8;
     foreground_kernel<<<(unsigned)fg_blocks, 256, 0, s>>>(raw_score, mask, lmin, num_levels, total, foreground_score);
     if ((rc = check_launch("salience_select/foreground"))) return rc;
+    if (K == 0) return SDETR_OK;
+    if (K <= kBitonicMax) {
+        // fast path: radix select per (image, level) -> bitonic merge per image (+ processing order)
+        level_select_kernel<<<batch * num_levels, kSortThreads, 0, s>>>(raw_score, mask, lmin, tb, num_value, K, buf[0],
+                                                                        buf[1]);
+        if ((rc = check_launch("salience_select/level_select"))) return rc;
+        const int N = next_pow2(K);
+        const size_t smem = (size_t)N * sizeof(unsigned long long);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(merge_bitonic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 kBitonicMax * (int)sizeof(unsigned long long));
+            SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "salience_select: smem attribute: %s", cudaGetErrorString(e));
+            attr_set = true;
+        }
+        const int cells_x = tile_order ? (max_w_px + cell_px - 1) / cell_px + 1 : 1;
+        merge_bitonic_kernel<<<batch, kSortThreads, smem, s>>>(buf[0], buf[1], tb, K, N, tile_order ? cell_px : 1,
+                                                               cells_x, selected_inds, selected_score, tile_order);
+        return check_launch("salience_select/merge_bitonic");
+    }
+    // large-K fallback (e.g. the 5-scale geometry, K = 45 570): segmented LSD radix sorts through global memory
     level_sort_kernel<<<batch * num_levels, kSortThreads, 0, s>>>(raw_score, mask, lmin, tb, num_value, buf[0], buf[1],
                                                                   buf[2], buf[3]);
     if ((rc = check_launch("salience_select/level_sort"))) return rc;
-    if (K == 0) return SDETR_OK;
     merge_sort_kernel<<<batch, kSortThreads, 0, s>>>(buf[2], buf[3], tb, num_value, K, buf[4], buf[5], buf[6], buf[7],
                                                      selected_inds, selected_score);
     if ((rc = check_launch("salience_select/merge_sort"))) return rc;
@@ -371,6 +619,11 @@ extern "C" int sdetr_topk_desc(const float *score, int segments, int n, int k, i
     SDETR_REQUIRE(segments > 0 && n > 0 && k >= 0 && k <= n, SDETR_ERR_INVALID_ARG, "topk_desc: k=%d n=%d", k, n);
     SDETR_REQUIRE(workspace_bytes >= sdetr_topk_workspace(segments, n), SDETR_ERR_WORKSPACE,
                   "topk_desc: workspace too small");
+    if (k == 0) return SDETR_OK;
+    if (k <= kTopkFast) {
+        topk_select_kernel<<<segments, kSortThreads, 0, (cudaStream_t)stream>>>(score, n, k, next_pow2(k), topk_index);
+        return check_launch("topk_desc/select");
+    }
     const size_t bufsz = align256((size_t)segments * n * sizeof(uint32_t));
     char *ws = (char *)workspace;
     topk_kernel<<<segments, kSortThreads, 0, (cudaStream_t)stream>>>(score, n, k, (uint32_t *)ws,

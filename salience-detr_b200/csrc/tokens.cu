@@ -359,3 +359,45 @@ extern "C" int sdetr_add_layernorm(const float *x, const float *r, const float *
                                                                                      channels, y);
     return check_launch("add_layernorm");
 }
+
+// ---- 3xTF32 operand split --------------------------------------------------------------------------------
+// The dense projections run on the tensor cores with fp32-class accuracy: x = hi + lo with hi = tf32(x),
+// lo = tf32(x - hi); A' = [A_hi | A_hi | A_lo], B' = [B_hi | B_lo | B_hi] so that one TF32 GEMM over K' = 3K
+// computes A_hi.B_hi + A_hi.B_lo + A_lo.B_hi with fp32 accumulation (dropped terms are O(2^-22)).  Every
+// operand value is exactly representable in TF32, so the tensor-core products are exact.
+namespace sdetr {
+__device__ __forceinline__ float tf32_round(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict__ x, int64_t x_stride, int64_t rows, int K,
+                                                        int layout_b, int relu, float *__restrict__ out) {
+    const int64_t vec = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 of one row
+    const int kv = K / 4;
+    if (vec >= rows * kv) return;
+    const int64_t r = vec / kv;
+    const int c = (int)(vec - r * kv) * 4;
+    float4 v = ld_stream_f4(x + r * x_stride + c);
+    if (relu) v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+    float4 hi, lo;
+    hi.x = tf32_round(v.x), hi.y = tf32_round(v.y), hi.z = tf32_round(v.z), hi.w = tf32_round(v.w);
+    lo.x = tf32_round(v.x - hi.x), lo.y = tf32_round(v.y - hi.y), lo.z = tf32_round(v.z - hi.z), lo.w = tf32_round(v.w - hi.w);
+    float *o = out + r * 3 * (int64_t)K + c;
+    *reinterpret_cast<float4 *>(o) = hi;
+    *reinterpret_cast<float4 *>(o + K) = layout_b ? lo : hi;
+    *reinterpret_cast<float4 *>(o + 2 * (int64_t)K) = layout_b ? hi : lo;
+}
+}  // namespace sdetr
+
+extern "C" int sdetr_split_tf32(const float *x, int64_t x_row_stride, int64_t rows, int K, int layout_b, int relu,
+                                float *out, sdetr_stream_t stream) {
+    SDETR_REQUIRE(x && out, SDETR_ERR_INVALID_ARG, "split_tf32: null pointer");
+    SDETR_REQUIRE(rows >= 0 && K > 0 && K % 4 == 0 && x_row_stride % 4 == 0 && aligned16(x) && aligned16(out),
+                  SDETR_ERR_INVALID_ARG, "split_tf32: K %% 4 == 0 and 16-byte alignment required");
+    if (rows == 0) return SDETR_OK;
+    const int64_t vecs = rows * (K / 4);
+    split_tf32_kernel<<<(unsigned)((vecs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, x_row_stride, rows, K, layout_b,
+                                                                                       relu, out);
+    return check_launch("split_tf32");
+}

@@ -1,0 +1,59 @@
+"""Dense projections of the path (value/output/offset/class projections, FFN, MaskPredictor).
+
+These are true dense GEMMs, the only place of the path where tensor cores belong.  ``MODE``:
+
+* ``"3xtf32"`` (default): each operand is split into two TF32 pieces by ``sdetr_split_tf32`` and ONE cuBLAS TF32
+  GEMM over K' = 3K accumulates A_hi.B_hi + A_hi.B_lo + A_lo.B_hi in fp32 -- tensor-core speed with fp32-class
+  accuracy (error ~2^-21 relative per product, same order as fp32 summation-order noise; measured in
+  tests/test_gpu_parity.py::test_linear_3xtf32_accuracy).  Weight splits are cached per parameter version.
+* ``"fp32"``: cuBLAS SGEMM on the fp32 SIMT pipe (what the reference runs by default).
+* ``"tf32"``: single-pass TF32 (reduced precision; never the bench default).
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor
+from torch.nn import functional as F
+
+from . import cabi
+
+MODE = "3xtf32"
+_weight_cache: Dict[int, Tuple[tuple, Tensor]] = {}
+
+
+@contextlib.contextmanager
+def _tf32_matmul():
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        yield
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def split_weight(weight: Tensor) -> Tensor:
+    """(N,K) -> cached (N,3K) [hi|lo|hi]; rebuilt when the parameter is modified in place or replaced."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape))
+    hit = _weight_cache.get(id(weight))
+    if hit is None or hit[0] != key:
+        with torch.no_grad():
+            hit = (key, cabi.split_tf32(weight.detach().contiguous(), layout_b=True))
+        _weight_cache[id(weight)] = hit
+    return hit[1]
+
+
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, relu_input: bool = False) -> Tensor:
+    """y = (relu(x) if relu_input else x) @ weight.T + bias, inference only (no autograd through the split)."""
+    if MODE == "fp32" or weight.shape[1] % 4 != 0:
+        return F.linear(F.relu(x) if relu_input else x, weight, bias)
+    if MODE == "tf32":
+        with _tf32_matmul():
+            return F.linear(F.relu(x) if relu_input else x, weight, bias)
+    x3 = cabi.split_tf32(x, layout_b=False, relu=relu_input)
+    w3 = split_weight(weight)
+    with _tf32_matmul():
+        y = F.linear(x3, w3, bias)
+    return y.view(*x.shape[:-1], weight.shape[0])

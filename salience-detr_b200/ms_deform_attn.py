@@ -25,7 +25,7 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 from torch.nn import functional as F
 
-from . import cabi
+from . import cabi, gemm
 
 
 def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step=64):
@@ -130,9 +130,10 @@ class MultiScaleDeformableAttention(nn.Module):
     def project_value(self, value: Tensor, key_padding_mask: Optional[Tensor]) -> Tensor:
         """value_proj + zeroing of padded rows (ms_deform_attn.py:316-321) -> (b,Nv,M,D)."""
         b, nv, _ = value.shape
-        v = self.value_proj(value)
+        train = torch.is_grad_enabled() and (value.requires_grad or self.value_proj.weight.requires_grad)
+        v = self.value_proj(value) if train else gemm.linear(value, self.value_proj.weight, self.value_proj.bias)
         if key_padding_mask is not None:
-            if torch.is_grad_enabled() and v.requires_grad:
+            if train:
                 v = v.masked_fill(key_padding_mask[..., None], 0.0)
             else:
                 cabi.zero_masked_rows_(v, self.embed_dim, self.embed_dim, key_padding_mask.to(torch.uint8).contiguous(),
@@ -144,12 +145,12 @@ class MultiScaleDeformableAttention(nn.Module):
                           level_start_index: Tensor, query_order: Optional[Tensor] = None, schedule: int = 0) -> Tensor:
         """Inference path with an already projected (and masked) value buffer; 2-d reference points."""
         w, b = self.fused_projection()
-        proj = F.linear(query, w, b)
+        proj = gemm.linear(query, w, b)
         out = cabi.msda_fused_forward(value_buf, value_batch_stride, value_token_stride, value_offset, spatial_shapes,
                                       level_start_index, reference_points, proj, self.num_heads,
                                       self.embed_dim // self.num_heads, self.num_levels, self.num_points, num_value,
                                       query_order, schedule)
-        return self.output_proj(out)
+        return gemm.linear(out, self.output_proj.weight, self.output_proj.bias)
 
     def forward(self, query: Tensor, reference_points: Tensor, value: Tensor, spatial_shapes: Tensor,
                 level_start_index: Tensor, key_padding_mask: Tensor) -> Tensor:

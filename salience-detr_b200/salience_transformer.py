@@ -29,11 +29,11 @@ import torch
 from torch import Tensor, nn
 from torch.nn import functional as F
 
-from . import cabi
+from . import cabi, gemm
 from .ms_deform_attn import MultiScaleDeformableAttention
 
-TILE_CELL_PX = 128  # edge (image pixels) of the spatial cells that define the MSDA processing order
-MSDA_SCHEDULE = 0   # 0 = query-major, 1 = head-major chunks (see include/sdetr_b200.h)
+TILE_CELL_PX = 64   # edge (image pixels) of the spatial cells that define the MSDA processing order
+MSDA_SCHEDULE = 1   # 0 = query-major, 1 = head-major chunks (see include/sdetr_b200.h)
 
 
 class MaskPredictor(nn.Module):
@@ -55,6 +55,16 @@ class MaskPredictor(nn.Module):
         half = self.h_dim // 2
         z = torch.cat([z[..., :half], z[..., half:].mean(dim=1, keepdim=True).expand(-1, z.shape[1], -1)], dim=-1)
         return self.layer2(z)
+
+    def forward_fast(self, x):
+        """Inference: same math with the projections on the tensor cores (gemm.linear)."""
+        ln, fc = self.layer1[0], self.layer1[1]
+        z = F.gelu(gemm.linear(F.layer_norm(x, ln.normalized_shape, ln.weight, ln.bias, ln.eps), fc.weight, fc.bias))
+        half = self.h_dim // 2
+        z = torch.cat([z[..., :half], z[..., half:].mean(dim=1, keepdim=True).expand(-1, z.shape[1], -1)], dim=-1)
+        z = F.gelu(gemm.linear(z, self.layer2[0].weight, self.layer2[0].bias))
+        z = F.gelu(gemm.linear(z, self.layer2[2].weight, self.layer2[2].bias))
+        return gemm.linear(z, self.layer2[4].weight, self.layer2[4].bias)
 
 
 class PositionEmbeddingLearned(nn.Module):
@@ -171,7 +181,8 @@ class SalienceTransformerEncoderLayer(nn.Module):
         a = self.self_attn.forward_projected(q + qp, ref_q, vbuf, v_bstride, v_tstride, v_off, num_value, spatial_shapes,
                                              level_start_index, order, schedule)
         q = cabi.add_layernorm(q, a, self.norm1.weight, self.norm1.bias, self.norm1.eps, out=q)
-        f = self.linear2(F.relu(self.linear1(q), inplace=True))
+        h = gemm.linear(q, self.linear1.weight, self.linear1.bias)
+        f = gemm.linear(h, self.linear2.weight, self.linear2.bias, relu_input=True)  # ReLU fused into the operand split
         return cabi.add_layernorm(q, f, self.norm2.weight, self.norm2.bias, self.norm2.eps, out=q)
 
 
@@ -229,7 +240,7 @@ class SalienceTransformerEncoder(nn.Module):
         focus = focus_token_nums.to(torch.int32).contiguous()
         # one GEMM for the value projections of all layers; zero the padded rows once
         wv, bv = self._value_projection()
-        vbuf = F.linear(query, wv, bv)  # (b,Nv,layers*C)
+        vbuf = gemm.linear(query, wv, bv)  # (b,Nv,layers*C)
         wide = vbuf.shape[-1]
         cabi.zero_masked_rows_(vbuf, wide, wide, mask_u8, b * nv)
         out = query.clone()  # `value` stays the original tokens (:452); `out` is updated in place
@@ -241,7 +252,7 @@ class SalienceTransformerEncoder(nn.Module):
             inds = foreground_inds[j]
             nq = inds.shape[1]
             q, qp, fq, rq = cabi.token_gather(out, pos, fg, vr, inds, spatial_shapes, level_start_index, nq)
-            mc = cabi.class_max_times_fg(self.enhance_mcsp(q), fq)
+            mc = cabi.class_max_times_fg(gemm.linear(q, self.enhance_mcsp.weight, self.enhance_mcsp.bias), fq)
             q = layer.forward_fast(q, qp, mc, rq, vbuf, nv * wide, wide, j * c, nv, spatial_shapes, level_start_index,
                                    None if query_orders is None else query_orders[j])
             cabi.token_scatter_(out, q, inds, focus)
@@ -365,10 +376,10 @@ class SalienceTransformer(nn.Module):
         # training keeps the scores differentiable (salience supervision): plain torch ops instead of the fused kernels
         grad = torch.is_grad_enabled() and (feat.requires_grad or any(p.requires_grad for p in self.parameters()))
         x = (feat + lpos) * plan.keep
-        mem = self.enc_output(x)
         if grad:
-            mem = self.enc_output_norm(mem)
+            mem = self.enc_output_norm(self.enc_output(x))
         else:
+            mem = gemm.linear(x, self.enc_output.weight, self.enc_output.bias)
             mem = cabi.add_layernorm(mem, None, self.enc_output_norm.weight, self.enc_output_norm.bias,
                                      self.enc_output_norm.eps, out=mem)
         raw = torch.empty(b, nv, device=feat.device, dtype=torch.float32)
@@ -386,7 +397,7 @@ class SalienceTransformer(nn.Module):
                     m_l = m_l + m_l * up.view(b, 1, h * w).transpose(1, 2) * self.alpha[lvl]
                 else:
                     m_l = cabi.score_modulate(mem, s0, h, w, raw[:, s1:s1 + hc * wc], hc, wc, self.alpha, lvl)
-            prev = self.enc_mask_predictor(m_l)
+            prev = self.enc_mask_predictor(m_l) if grad else self.enc_mask_predictor.forward_fast(m_l)
             raw[:, s0:s0 + h * w] = prev.squeeze(-1)
         sel_in = raw.detach() if grad else raw
         inds, score, fg, order = cabi.salience_select(

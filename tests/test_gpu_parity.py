@@ -272,6 +272,31 @@ def test_score_modulate_zero_rows_classmax_layernorm(pkg):
         assert (xd.cpu() - torch.nn.functional.layer_norm(x, (c,), gam, bet)).abs().max() < 2e-5
 
 
+def test_linear_3xtf32_accuracy(pkg):
+    """The split-operand TF32 GEMM must be fp32-class: error vs an fp64 reference within 4x of cuBLAS fp32's."""
+    g = torch.Generator().manual_seed(0)
+    for rows, K, N in [(4097, 256, 384), (1000, 2048, 256), (333, 256, 91), (50, 64, 1)]:
+        x = torch.randn(rows, K, generator=g).to(DEV)
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+        b = torch.randn(N, generator=g).to(DEV)
+        ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+        pkg.gemm.MODE = "fp32"
+        e32 = (pkg.gemm.linear(x, w, b).double() - ref).abs().max().item()
+        pkg.gemm.MODE = "3xtf32"
+        y = pkg.gemm.linear(x, w, b)
+        e3 = (y.double() - ref).abs().max().item()
+        pkg.gemm.MODE = "tf32"
+        e1 = (pkg.gemm.linear(x, w, b).double() - ref).abs().max().item()
+        pkg.gemm.MODE = "3xtf32"
+        assert e3 < max(4 * e32, 2e-6), (rows, K, N, e3, e32, e1)
+        assert e1 > 10 * e3 or K <= 64  # single-pass TF32 is visibly worse: the split is what buys the accuracy
+        # fused ReLU on the input operand
+        yr = pkg.gemm.linear(x, w, b, relu_input=True)
+        assert (yr.double() - torch.nn.functional.linear(x.relu().double(), w.double(), b.double())).abs().max() < max(4 * e32, 2e-6)
+    s3 = pkg.cabi.split_tf32(x)
+    assert torch.equal(s3[:, :K], s3[:, K:2 * K]) and (s3[:, :K] + s3[:, 2 * K:] - x).abs().max() < 1e-6
+
+
 # ---- module level ---------------------------------------------------------------------------------------------------
 def _tiny_model(pkg, sd):
     enc = pkg.SalienceTransformerEncoder(pkg.SalienceTransformerEncoderLayer(64, 128, 0.0, 2, topk_sa=20), 3, 40)
