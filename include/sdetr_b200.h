@@ -185,13 +185,22 @@ int sdetr_class_max_times_fg(const float *logits, const float *fg, int64_t rows,
 int sdetr_add_layernorm(const float *x, const float *r, const float *gamma, const float *beta, float eps,
                         int64_t rows, int channels, float *y, sdetr_stream_t stream);
 
+/* Row gather / scatter by per-image index (the top-k tokens of the pre-attention, salience_transformer.py:368-379):
+ * out[b,j,:] = src[b,index[b,j],:]   /   dst[b,index[b,j],:] = src[b,j,:]  (indices unique per image).
+ * src/dst (b,num_rows,C), index (b,k) int64. */
+int sdetr_rows_gather(const float *src, const int64_t *index, int batch, int num_rows, int k, int channels, float *out,
+                      sdetr_stream_t stream);
+int sdetr_rows_scatter(float *dst, const int64_t *index, int batch, int num_rows, int k, int channels, const float *src,
+                       sdetr_stream_t stream);
+
 /* 3xTF32 operand split for the dense projections (tensor cores with fp32-class accuracy):
- * x (rows, K) with row stride x_row_stride -> out (rows, 3K) = [hi | hi | lo] (layout_b = 0, activations) or
- * [hi | lo | hi] (layout_b = 1, weights), hi = tf32(x), lo = tf32(x - hi); relu != 0 applies max(x, 0) first
- * (fuses the FFN activation, salience_transformer.py:348).  One TF32 GEMM over K' = 3K of the two layouts
- * yields A_hi.B_hi + A_hi.B_lo + A_lo.B_hi accumulated in fp32. */
-int sdetr_split_tf32(const float *x, int64_t x_row_stride, int64_t rows, int K, int layout_b, int relu, float *out,
-                     sdetr_stream_t stream);
+ * x (rows, K) with row stride x_row_stride -> out (rows, K/chunk, 3, chunk): per K-chunk [hi | hi | lo]
+ * (layout_b = 0, activations) or [hi | lo | hi] (layout_b = 1, weights), hi = tf32(x), lo = tf32(x - hi);
+ * relu != 0 applies max(x, 0) first (fuses the FFN activation, salience_transformer.py:348).  A TF32 GEMM over
+ * a chunk's 3*chunk columns of both operands yields A_hi.B_hi + A_hi.B_lo + A_lo.B_hi for that chunk; chunks are
+ * accumulated by the GEMM epilogue in fp32 (chunk == K: a single GEMM). */
+int sdetr_split_tf32(const float *x, int64_t x_row_stride, int64_t rows, int K, int chunk, int layout_b, int relu,
+                     float *out, sdetr_stream_t stream);
 
 #ifdef __cplusplus
 }

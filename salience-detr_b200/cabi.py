@@ -44,7 +44,9 @@ SIGNATURES = {
     "sdetr_zero_masked_rows": (_i, [_vp, _i64, _i, _vp, _i64, _vp]),
     "sdetr_class_max_times_fg": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
     "sdetr_add_layernorm": (_i, [_vp, _vp, _vp, _vp, _f, _i64, _i, _vp, _vp]),
-    "sdetr_split_tf32": (_i, [_vp, _i64, _i64, _i, _i, _i, _vp, _vp]),
+    "sdetr_split_tf32": (_i, [_vp, _i64, _i64, _i, _i, _i, _i, _vp, _vp]),
+    "sdetr_rows_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "sdetr_rows_scatter": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
 }
 
 
@@ -318,15 +320,37 @@ def add_layernorm(x, r, gamma, beta, eps: float = 1e-5, out=None):
     return out
 
 
-def split_tf32(x, layout_b: bool = False, relu: bool = False):
-    """(..., K) fp32 with contiguous rows -> (rows, 3K) 3xTF32 operand ([hi|hi|lo] or, for weights, [hi|lo|hi])."""
+def split_tf32(x, layout_b: bool = False, relu: bool = False, chunk: int = 0):
+    """(..., K) fp32 with contiguous rows -> (rows, 3K) 3xTF32 operand: per K-chunk [hi|hi|lo] (weights: [hi|lo|hi])."""
     K = x.shape[-1]
+    chunk = chunk or K
     if not (x.is_cuda and x.dtype == torch.float32 and x.stride(-1) == 1):
         raise RuntimeError("split_tf32 needs a CUDA float32 tensor with unit last stride")
     x2 = x if x.dim() == 2 else x.reshape(-1, K)  # view when rows are uniformly strided
     rows = x2.shape[0]
     out = torch.empty(rows, 3 * K, device=x.device, dtype=torch.float32)
-    rc = lib().sdetr_split_tf32(x2.data_ptr(), x2.stride(0) if rows > 1 else K, rows, K, int(layout_b), int(relu),
+    rc = lib().sdetr_split_tf32(x2.data_ptr(), x2.stride(0) if rows > 1 else K, rows, K, chunk, int(layout_b), int(relu),
                                 out.data_ptr(), _stream())
     _check(rc, "sdetr_split_tf32")
     return out
+
+
+def rows_gather(src, index):
+    """src (b,n,C), index (b,k) int64 -> (b,k,C)."""
+    b, n, c = src.shape
+    k = index.shape[1]
+    out = torch.empty(b, k, c, device=src.device, dtype=torch.float32)
+    rc = lib().sdetr_rows_gather(_req(src, "src", torch.float32), _req(index, "index", torch.int64), b, n, k, c,
+                                 out.data_ptr(), _stream())
+    _check(rc, "sdetr_rows_gather")
+    return out
+
+
+def rows_scatter_(dst, index, src):
+    """dst (b,n,C) <- src (b,k,C) at index (b,k) int64, in place."""
+    b, n, c = dst.shape
+    k = index.shape[1]
+    rc = lib().sdetr_rows_scatter(_req(dst, "dst", torch.float32), _req(index, "index", torch.int64), b, n, k, c,
+                                  _req(src, "src", torch.float32), _stream())
+    _check(rc, "sdetr_rows_scatter")
+    return dst

@@ -383,6 +383,8 @@ static int msda_forward_dispatch(MsdaFwdParams p, bool fused, int head_dim, int 
     if (special && head_dim == 32 && levels == 4 && points == 4) {
         if (g_minb == 3) launch_special<32, 4, 4, 3>(p, fused, schedule, s);
         else if (g_minb == 4) launch_special<32, 4, 4, 4>(p, fused, schedule, s);
+        else if (g_minb == 5) launch_special<32, 4, 4, 5>(p, fused, schedule, s);
+        else if (g_minb == 6) launch_special<32, 4, 4, 6>(p, fused, schedule, s);
         else launch_special<32, 4, 4, 2>(p, fused, schedule, s);
     } else if (special && head_dim == 32 && levels == 5 && points == 4)
         launch_special<32, 5, 4, 2>(p, fused, schedule, s);
@@ -404,7 +406,7 @@ extern "C" int sdetr_set_option(const char *name, int value) {
     SDETR_REQUIRE(name, SDETR_ERR_INVALID_ARG, "set_option: null name");
     const auto eq = [&](const char *k) { int i = 0; while (k[i] && k[i] == name[i]) ++i; return k[i] == 0 && name[i] == 0; };
     if (eq("msda_min_blocks")) {
-        SDETR_REQUIRE(value >= 2 && value <= 4, SDETR_ERR_INVALID_ARG, "set_option: msda_min_blocks in 2..4");
+        SDETR_REQUIRE(value >= 2 && value <= 6, SDETR_ERR_INVALID_ARG, "set_option: msda_min_blocks in 2..6");
         g_minb = value;
     } else if (eq("msda_chunk")) {
         SDETR_REQUIRE(value >= 8 && value <= 4096, SDETR_ERR_INVALID_ARG, "set_option: msda_chunk in 8..4096");

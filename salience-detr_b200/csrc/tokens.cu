@@ -371,8 +371,11 @@ __device__ __forceinline__ float tf32_round(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
 }
+// out layout: (rows, K/chunk, 3, chunk): every K-chunk carries its own [hi|hi|lo] (or [hi|lo|hi]) triple, so a
+// long reduction can be issued as several GEMMs accumulated in fp32 by the GEMM epilogue (beta = 1) -- the tensor
+// core's own accumulator truncates, and its error grows linearly with the reduction length.
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict__ x, int64_t x_stride, int64_t rows, int K,
-                                                        int layout_b, int relu, float *__restrict__ out) {
+                                                        int chunk, int layout_b, int relu, float *__restrict__ out) {
     const int64_t vec = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 of one row
     const int kv = K / 4;
     if (vec >= rows * kv) return;
@@ -383,21 +386,68 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict
     float4 hi, lo;
     hi.x = tf32_round(v.x), hi.y = tf32_round(v.y), hi.z = tf32_round(v.z), hi.w = tf32_round(v.w);
     lo.x = tf32_round(v.x - hi.x), lo.y = tf32_round(v.y - hi.y), lo.z = tf32_round(v.z - hi.z), lo.w = tf32_round(v.w - hi.w);
-    float *o = out + r * 3 * (int64_t)K + c;
+    const int ck = c / chunk, cc = c - ck * chunk;
+    float *o = out + r * 3 * (int64_t)K + (int64_t)ck * 3 * chunk + cc;
     *reinterpret_cast<float4 *>(o) = hi;
-    *reinterpret_cast<float4 *>(o + K) = layout_b ? lo : hi;
-    *reinterpret_cast<float4 *>(o + 2 * (int64_t)K) = layout_b ? hi : lo;
+    *reinterpret_cast<float4 *>(o + chunk) = layout_b ? lo : hi;
+    *reinterpret_cast<float4 *>(o + 2 * chunk) = layout_b ? hi : lo;
 }
 }  // namespace sdetr
 
-extern "C" int sdetr_split_tf32(const float *x, int64_t x_row_stride, int64_t rows, int K, int layout_b, int relu,
-                                float *out, sdetr_stream_t stream) {
+extern "C" int sdetr_split_tf32(const float *x, int64_t x_row_stride, int64_t rows, int K, int chunk, int layout_b,
+                                int relu, float *out, sdetr_stream_t stream) {
     SDETR_REQUIRE(x && out, SDETR_ERR_INVALID_ARG, "split_tf32: null pointer");
+    SDETR_REQUIRE(chunk > 0 && chunk % 4 == 0 && K % chunk == 0, SDETR_ERR_INVALID_ARG,
+                  "split_tf32: chunk %d must divide K %d and be a multiple of 4", chunk, K);
     SDETR_REQUIRE(rows >= 0 && K > 0 && K % 4 == 0 && x_row_stride % 4 == 0 && aligned16(x) && aligned16(out),
                   SDETR_ERR_INVALID_ARG, "split_tf32: K %% 4 == 0 and 16-byte alignment required");
     if (rows == 0) return SDETR_OK;
     const int64_t vecs = rows * (K / 4);
-    split_tf32_kernel<<<(unsigned)((vecs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, x_row_stride, rows, K, layout_b,
-                                                                                       relu, out);
+    split_tf32_kernel<<<(unsigned)((vecs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, x_row_stride, rows, K, chunk,
+                                                                                       layout_b, relu, out);
     return check_launch("split_tf32");
+}
+
+// ---- generic row gather / scatter by index (the 300-token pre-attention, salience_transformer.py:368-379) ----
+namespace sdetr {
+__global__ void __launch_bounds__(kRowThreads) rows_gather_kernel(const float *__restrict__ src, const int64_t *__restrict__ idx,
+                                                                  int batch, int n, int k, int C, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+    if (row >= (int64_t)batch * k) return;
+    const int b = (int)(row / k);
+    const float *s = src + ((int64_t)b * n + __ldg(idx + row)) * C;
+    for (int c = lane * 4; c < C; c += 128) st_stream_f4(out + row * C + c, ld_stream_f4(s + c));
+}
+__global__ void __launch_bounds__(kRowThreads) rows_scatter_kernel(float *__restrict__ dst, const int64_t *__restrict__ idx,
+                                                                   int batch, int n, int k, int C, const float *__restrict__ src) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+    if (row >= (int64_t)batch * k) return;
+    const int b = (int)(row / k);
+    float *d = dst + ((int64_t)b * n + __ldg(idx + row)) * C;
+    for (int c = lane * 4; c < C; c += 128) st_stream_f4(d + c, ld_stream_f4(src + row * C + c));
+}
+}  // namespace sdetr
+
+extern "C" int sdetr_rows_gather(const float *src, const int64_t *index, int batch, int num_rows, int k, int channels,
+                                 float *out, sdetr_stream_t stream) {
+    SDETR_REQUIRE(src && index && out, SDETR_ERR_INVALID_ARG, "rows_gather: null pointer");
+    SDETR_REQUIRE(batch > 0 && num_rows > 0 && k >= 0 && channels % 4 == 0 && aligned16(src) && aligned16(out),
+                  SDETR_ERR_INVALID_ARG, "rows_gather: bad sizes / alignment");
+    if (k == 0) return SDETR_OK;
+    rows_gather_kernel<<<row_blocks((int64_t)batch * k), kRowThreads, 0, (cudaStream_t)stream>>>(src, index, batch, num_rows, k,
+                                                                                                channels, out);
+    return check_launch("rows_gather");
+}
+
+extern "C" int sdetr_rows_scatter(float *dst, const int64_t *index, int batch, int num_rows, int k, int channels,
+                                  const float *src, sdetr_stream_t stream) {
+    SDETR_REQUIRE(dst && index && src, SDETR_ERR_INVALID_ARG, "rows_scatter: null pointer");
+    SDETR_REQUIRE(batch > 0 && num_rows > 0 && k >= 0 && channels % 4 == 0 && aligned16(src) && aligned16(dst),
+                  SDETR_ERR_INVALID_ARG, "rows_scatter: bad sizes / alignment");
+    if (k == 0) return SDETR_OK;
+    rows_scatter_kernel<<<row_blocks((int64_t)batch * k), kRowThreads, 0, (cudaStream_t)stream>>>(dst, index, batch, num_rows, k,
+                                                                                                 channels, src);
+    return check_launch("rows_scatter");
 }

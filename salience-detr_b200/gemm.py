@@ -21,6 +21,7 @@ from torch.nn import functional as F
 from . import cabi
 
 MODE = "3xtf32"
+K_CHUNK = 512  # longest reduction handed to one tensor-core GEMM (its accumulator truncates: error ~ length)
 _weight_cache: Dict[int, Tuple[tuple, Tensor]] = {}
 
 
@@ -34,13 +35,17 @@ def _tf32_matmul():
         torch.backends.cuda.matmul.allow_tf32 = prev
 
 
+def _chunk_of(K: int) -> int:
+    return K_CHUNK if K > K_CHUNK and K % K_CHUNK == 0 else K
+
+
 def split_weight(weight: Tensor) -> Tensor:
-    """(N,K) -> cached (N,3K) [hi|lo|hi]; rebuilt when the parameter is modified in place or replaced."""
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape))
+    """(N,K) -> cached (N,3K) per-chunk [hi|lo|hi]; rebuilt when the parameter is modified in place or replaced."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), _chunk_of(weight.shape[1]))
     hit = _weight_cache.get(id(weight))
     if hit is None or hit[0] != key:
         with torch.no_grad():
-            hit = (key, cabi.split_tf32(weight.detach().contiguous(), layout_b=True))
+            hit = (key, cabi.split_tf32(weight.detach().contiguous(), layout_b=True, chunk=_chunk_of(weight.shape[1])))
         _weight_cache[id(weight)] = hit
     return hit[1]
 
@@ -52,8 +57,15 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, relu_input:
     if MODE == "tf32":
         with _tf32_matmul():
             return F.linear(F.relu(x) if relu_input else x, weight, bias)
-    x3 = cabi.split_tf32(x, layout_b=False, relu=relu_input)
+    K = weight.shape[1]
+    kc = _chunk_of(K)
+    x3 = cabi.split_tf32(x, layout_b=False, relu=relu_input, chunk=kc)
     w3 = split_weight(weight)
     with _tf32_matmul():
-        y = F.linear(x3, w3, bias)
+        if kc == K:
+            y = F.linear(x3, w3, bias)
+        else:  # long reduction: one GEMM per K-chunk, accumulated in fp32 by the epilogue (beta = 1)
+            y = F.linear(x3[:, :3 * kc], w3[:, :3 * kc], bias)
+            for c in range(1, K // kc):
+                y.addmm_(x3[:, 3 * kc * c:3 * kc * (c + 1)], w3[:, 3 * kc * c:3 * kc * (c + 1)].t())
     return y.view(*x.shape[:-1], weight.shape[0])

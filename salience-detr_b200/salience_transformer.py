@@ -162,8 +162,7 @@ class SalienceTransformerEncoderLayer(nn.Module):
         b, nq, c = q.shape
         k = min(self.topk_sa, nq)
         top = cabi.topk_desc(mc, k)
-        ix = top.unsqueeze(-1).expand(-1, -1, c)
-        t, tp = torch.gather(q, 1, ix), torch.gather(qp, 1, ix)
+        t, tp = cabi.rows_gather(q, top), cabi.rows_gather(qp, top)
         x = t + tp
         w, bias = self.pre_attention.in_proj_weight, self.pre_attention.in_proj_bias
         h, d = self.n_heads, c // self.n_heads
@@ -172,7 +171,7 @@ class SalienceTransformerEncoderLayer(nn.Module):
         o = F.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2), v.transpose(1, 2))
         o = self.pre_attention.out_proj(o.transpose(1, 2).reshape(b, k, c))
         t = cabi.add_layernorm(t, o, self.pre_norm.weight, self.pre_norm.bias, self.pre_norm.eps)
-        q.scatter_(1, ix, t)  # q is this layer's private gather buffer
+        cabi.rows_scatter_(q, top, t)  # q is this layer's private gather buffer
         return q
 
     def forward_fast(self, q, qp, mc, ref_q, vbuf, v_bstride, v_tstride, v_off, num_value, spatial_shapes,

@@ -67,13 +67,13 @@ def alg_bytes(plan):
 ref_out = None
 print(f"workload {workload}")
 print("cell  order sched minb chunk | per-layer us | total us | GB/s")
-for cell in (64, 128, 256):
+for cell in (32, 64):
     calls, plan = capture(cell)
     byts = alg_bytes(plan)
-    for use_order, schedule, minb in itertools.product((False, True), (0, 1), (2, 3, 4)):
-        if not use_order and cell != 128:
+    for use_order, schedule, minb in itertools.product((True,), (0, 1), (4, 5, 6)):
+        if not use_order and cell != 64:
             continue
-        for chunk in ((64,) if schedule == 0 else (32, 64, 128, 256)):
+        for chunk in ((64,) if schedule == 0 else (32, 64, 96)):
             cabi.set_option("msda_min_blocks", minb)
             cabi.set_option("msda_chunk", chunk)
             t = time_calls(calls, schedule, use_order)
