@@ -135,6 +135,48 @@ struct LevelLoop {
     }
 };
 
+// Variant B of the gather: the owners publish their setups in shared memory (one STS.128 + one STS.32 per
+// point) and every lane reads a level's four packed indices with ONE LDS.128 and each point's four weights with
+// ONE LDS.128 (warp-wide broadcast reads: 4 distinct 16-byte chunks in distinct banks) -- 5 shared-memory
+// wavefronts per level instead of 20 shuffle wavefronts on the same LSU data pipe that the gathers saturate.
+constexpr int kWStride = 336;  // bytes per group for weights: 16 points x 16 B, padded so 4 groups hit distinct banks
+constexpr int kPkStride = 80;  // bytes per group for packed indices: 16 x 4 B, padded likewise
+
+template <int L, int P, int LANES, int LVL = 0>
+struct LevelLoopSmem {
+    static __device__ __forceinline__ void run(float4 &acc, const char *wsm, const char *pksm, const LevelGeom (&geo)[L],
+                                               const float *__restrict__ vbase, uint32_t ts) {
+        static_assert(P == 4, "one LDS.128 carries the four packed indices of a level");
+        const char *lvl_base = reinterpret_cast<const char *>(vbase + geo[LVL].start * (int64_t)ts);
+        const uint32_t tsb = ts * 4u;
+        const uint32_t W = (uint32_t)geo[LVL].W;
+        const uint4 pk4 = *reinterpret_cast<const uint4 *>(pksm + LVL * 16);
+        const uint32_t pks[4] = {pk4.x, pk4.y, pk4.z, pk4.w};
+        float4 v[P][4], w[P];
+#pragma unroll
+        for (int pt = 0; pt < P; ++pt) {
+            w[pt] = *reinterpret_cast<const float4 *>(wsm + (LVL * P + pt) * 16);
+            const uint32_t pk = pks[pt];
+            const uint32_t i00 = pk & 0x3fffffffu;
+            const uint32_t i01 = i00 + ((pk >> 30) & 1u);
+            const uint32_t i10 = i00 + (pk >> 31) * W;
+            const uint32_t i11 = i10 + ((pk >> 30) & 1u);
+            v[pt][0] = ldg_f4(row_ptr(lvl_base, i00, tsb));
+            v[pt][1] = ldg_f4(row_ptr(lvl_base, i01, tsb));
+            v[pt][2] = ldg_f4(row_ptr(lvl_base, i10, tsb));
+            v[pt][3] = ldg_f4(row_ptr(lvl_base, i11, tsb));
+        }
+#pragma unroll
+        for (int pt = 0; pt < P; ++pt) {
+            fma4(acc, w[pt].x, v[pt][0]);
+            fma4(acc, w[pt].y, v[pt][1]);
+            fma4(acc, w[pt].z, v[pt][2]);
+            fma4(acc, w[pt].w, v[pt][3]);
+        }
+        if constexpr (LVL + 1 < L) LevelLoopSmem<L, P, LANES, LVL + 1>::run(acc, wsm, pksm, geo, vbase, ts);
+    }
+};
+
 // level geometry of the point owned by (slot, lane): only the levels a slot can span are tested
 template <int L, int P, int LANES, int SLOT>
 __device__ __forceinline__ void slot_geom(const LevelGeom (&geo)[L], int lane, int &l, int &H, int &W, float &Hf, float &Wf) {
@@ -170,7 +212,7 @@ struct SlotLoop {
 };
 
 // ---- the specialised kernel -------------------------------------------------------------------------
-template <int D, int L, int P, bool FUSED, bool HEAD_MAJOR, int MINB>
+template <int D, int L, int P, bool FUSED, bool HEAD_MAJOR, int MINB, bool SMEM_BCAST = false>
 __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_kernel(const MsdaFwdParams p) {
     constexpr int LANES = D / 4;
     constexpr int GROUPS = kThreads / LANES;
@@ -270,7 +312,23 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_kernel(const MsdaFwdP
         // ---- phase 2: gather ------------------------------------------------------------------------------------
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         const float *vbase = p.value + (int64_t)b * p.v_bstride + (int64_t)m * D + lane * 4;
-        LevelLoop<L, P, LANES, SLOTS>::run(acc, st, geo, vbase, (uint32_t)p.v_tstride);
+        if constexpr (SMEM_BCAST) {
+            static_assert(!SMEM_BCAST || (NP == 16 && LANES == 8), "shared-memory broadcast variant: 16 points, 8 lanes");
+            __shared__ __align__(16) char bc_smem[GROUPS * (kWStride + kPkStride)];
+            char *wsm = bc_smem + grp * kWStride;
+            char *pksm = bc_smem + GROUPS * kWStride + grp * kPkStride;
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                const int e = s * LANES + lane;
+                *reinterpret_cast<float4 *>(wsm + e * 16) = make_float4(st[s].w00, st[s].w01, st[s].w10, st[s].w11);
+                *reinterpret_cast<uint32_t *>(pksm + e * 4) = st[s].packed;
+            }
+            __syncwarp();
+            LevelLoopSmem<L, P, LANES>::run(acc, wsm, pksm, geo, vbase, (uint32_t)p.v_tstride);
+            __syncwarp();  // all lanes have read this item's setups before the next item overwrites them
+        } else {
+            LevelLoop<L, P, LANES, SLOTS>::run(acc, st, geo, vbase, (uint32_t)p.v_tstride);
+        }
         if (active) st_stream_f4(p.out + qm * D + lane * 4, acc);
     }
 }
@@ -338,6 +396,7 @@ __global__ void __launch_bounds__(kThreads) msda_fwd_generic_kernel(const MsdaFw
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
+static int g_bcast = 1;   // 0 = shuffle broadcast, 1 = shared-memory broadcast (D=32, L=4, P=4 only)
 static int g_minb = 4;    // tuning knobs (sdetr_set_option)
 static int g_chunk = 64;
 
@@ -380,7 +439,18 @@ static int msda_forward_dispatch(MsdaFwdParams p, bool fused, int head_dim, int 
     bool special = true;
     if (fused) special = (p.proj_stride % 4 == 0) && aligned16(p.proj);
     else special = aligned16(p.loc) && aligned16(p.attn);
-    if (special && head_dim == 32 && levels == 4 && points == 4) {
+    if (special && head_dim == 32 && levels == 4 && points == 4 && g_bcast == 1) {
+        constexpr int GROUPS = kThreads / 8;
+        if (schedule == 1) {
+            dim3 grid((p.nq + p.chunk - 1) / p.chunk, p.heads, p.batch);
+            if (fused) msda_fwd_kernel<32, 4, 4, true, true, 4, true><<<grid, kThreads, 0, s>>>(p);
+            else msda_fwd_kernel<32, 4, 4, false, true, 4, true><<<grid, kThreads, 0, s>>>(p);
+        } else {
+            dim3 grid((unsigned)(((int64_t)p.nq * p.heads + GROUPS - 1) / GROUPS), p.batch);
+            if (fused) msda_fwd_kernel<32, 4, 4, true, false, 4, true><<<grid, kThreads, 0, s>>>(p);
+            else msda_fwd_kernel<32, 4, 4, false, false, 4, true><<<grid, kThreads, 0, s>>>(p);
+        }
+    } else if (special && head_dim == 32 && levels == 4 && points == 4) {
         if (g_minb == 3) launch_special<32, 4, 4, 3>(p, fused, schedule, s);
         else if (g_minb == 4) launch_special<32, 4, 4, 4>(p, fused, schedule, s);
         else if (g_minb == 5) launch_special<32, 4, 4, 5>(p, fused, schedule, s);
@@ -408,6 +478,9 @@ extern "C" int sdetr_set_option(const char *name, int value) {
     if (eq("msda_min_blocks")) {
         SDETR_REQUIRE(value >= 2 && value <= 6, SDETR_ERR_INVALID_ARG, "set_option: msda_min_blocks in 2..6");
         g_minb = value;
+    } else if (eq("msda_smem_broadcast")) {
+        SDETR_REQUIRE(value == 0 || value == 1, SDETR_ERR_INVALID_ARG, "set_option: msda_smem_broadcast in {0,1}");
+        g_bcast = value;
     } else if (eq("msda_chunk")) {
         SDETR_REQUIRE(value >= 8 && value <= 4096, SDETR_ERR_INVALID_ARG, "set_option: msda_chunk in 8..4096");
         g_chunk = value;

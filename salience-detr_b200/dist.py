@@ -1,0 +1,79 @@
+"""Multi-GPU plumbing of the path: batch-sharded independent replicas.
+
+The encoder forward has NO collective: each rank owns its local batch (the reference under DDP behaves the same:
+per-process local batch, train_config.py:9).  torch.distributed is used only for (a) the barrier + max-over-ranks
+timing of bench.py and (b) the gradient all-reduce of the training configuration."""
+from __future__ import annotations
+
+import os
+from typing import Iterable, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def env_rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def init_from_env(backend: Optional[str] = None, device: Optional[torch.device] = None) -> bool:
+    """Initialise the default process group from torchrun's environment (MASTER_ADDR defaults to 127.0.0.1)."""
+    rank, world, _ = env_rank_world()
+    if world <= 1:
+        return False
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+    kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
+    dist.init_process_group(backend, rank=rank, world_size=world, **kw)
+    return True
+
+
+def max_over_ranks(value: float, device="cpu") -> float:
+    """The slowest rank's time: what a multi-GPU throughput number must be computed from."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def shard_batch_seed(base_seed: int, rank: int) -> int:
+    """Every replica draws its own synthetic batch (weak scaling: per-GPU work is fixed)."""
+    return base_seed + rank
+
+
+def aggregate_throughput(units_per_rank_step: int, steps: int, world: int, total_ms_max: float) -> float:
+    """Whole-job units/s = all ranks' units / slowest rank's time."""
+    return units_per_rank_step * steps * world / (total_ms_max / 1000.0)
+
+
+def allreduce_gradients_(params: Iterable[torch.nn.Parameter], bucket_bytes: int = 32 << 20):
+    """Mean gradient all-reduce in flat buckets (the one collective of the training configuration,
+    accelerate/DDP in the reference: main.py:144, util/engine.py:58).  Over NVSwitch the cost is per-launch
+    latency, not per-link bandwidth, so buckets are sized for few launches."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    world = dist.get_world_size()
+    grads = [p.grad for p in params if p.grad is not None]
+    bucket, size = [], 0
+
+    def flush():
+        nonlocal bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([g.reshape(-1) for g in bucket])
+        dist.all_reduce(flat)
+        flat.div_(world)
+        off = 0
+        for g in bucket:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        bucket, size = [], 0
+
+    for g in grads:
+        bucket.append(g)
+        size += g.numel() * g.element_size()
+        if size >= bucket_bytes:
+            flush()
+    flush()

@@ -14,6 +14,60 @@ from . import cabi
 from .salience_transformer import SalienceTransformer
 
 
+class HostPipeline:
+    """Double-buffered host -> device -> host streaming over two EncoderRunners of the same geometry.
+
+    H2D copies (copy stream), the encoder graph (compute stream) and the D2H copy of the memory (second copy
+    stream) of consecutive batches overlap; a batch's buffers are reused only after its D2H has finished.
+    PCIe is full duplex, so the steady-state step time is max(compute, H2D, D2H) instead of their sum."""
+
+    def __init__(self, model: SalienceTransformer, feats, masks, pos, depth: int = 2, **kw):
+        self.lanes = [EncoderRunner(model, feats, masks, pos, **kw) for _ in range(depth)]
+        dev = self.lanes[0].dev
+        self.h2d = torch.cuda.Stream(device=dev)
+        self.d2h = torch.cuda.Stream(device=dev)
+        self.done = [None] * depth     # event: D2H of the lane's previous batch finished
+        self.host_out = [torch.empty(self.lanes[0].memory.shape, dtype=torch.float32, pin_memory=True)
+                         for _ in range(depth)]
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def run(self, batches, on_output=None):
+        """batches: iterable of (feats_host, pos_host) pinned-memory level lists.  Returns the number processed;
+        ``on_output(i, host_memory)`` (optional) is called once batch i's output is in host memory."""
+        pending = []
+        n = 0
+        for i, (feats_h, pos_h) in enumerate(batches):
+            k = i % len(self.lanes)
+            lane = self.lanes[k]
+            if self.done[k] is not None:
+                self.h2d.wait_event(self.done[k])          # lane buffers are free again
+                if on_output is not None:
+                    self.done[k].synchronize()
+                    on_output(i - len(self.lanes), self.host_out[k])
+            with torch.cuda.stream(self.h2d):
+                for dst, src in zip(lane.feats + lane.pos, list(feats_h) + list(pos_h)):
+                    dst.copy_(src, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(self.h2d)
+            lane.stream.wait_event(ready)
+            mem = lane.step()
+            computed = torch.cuda.Event()
+            computed.record(lane.stream)
+            self.d2h.wait_event(computed)
+            with torch.cuda.stream(self.d2h):
+                self.host_out[k].copy_(mem, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.d2h)
+            self.done[k] = ev
+            n += 1
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.lanes[0].feats + self.lanes[0].pos)
+        self.d2h_bytes = self.host_out[0].numel() * 4
+        for k, ev in enumerate(self.done):
+            if ev is not None:
+                ev.synchronize()
+        return n
+
+
 class EncoderRunner:
     def __init__(self, model: SalienceTransformer, feats: Sequence[torch.Tensor], masks: Sequence[torch.Tensor],
                  pos: Sequence[torch.Tensor], use_graph: bool = True, use_order: bool = True, warmup: int = 2):

@@ -90,6 +90,22 @@ def test_msda_backward_vs_oracle(pkg, case):
     assert (gl.cpu() - wl).abs().max() / wl.abs().max() < 1e-5
 
 
+def test_msda_smem_broadcast_variant(pkg):
+    """The shared-memory-broadcast build of the specialised kernel gives the same bits as the shuffle build."""
+    b, shapes, m, d, nq, p = CASES[0]
+    value, st, lsi, loc, attn = _msda_inputs(b, shapes, m, d, nq, p, seed=9)
+    args = [t.to(DEV) for t in (value, st, lsi, loc, attn)]
+    try:
+        outs = []
+        for bc in (0, 1):
+            pkg.cabi.set_option("msda_smem_broadcast", bc)
+            outs.append([pkg.cabi.msda_forward(*args, schedule=s) for s in (0, 1)])
+    finally:
+        pkg.cabi.set_option("msda_smem_broadcast", 0)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert (outs[1][0].cpu() - orc.c_msda_forward(value, st, lsi, loc, attn)).abs().max() < 1e-4
+
+
 def test_msda_autograd_function(pkg):
     value, st, lsi, loc, attn = _msda_inputs(1, [(6, 5), (3, 3)], 2, 32, 9, 2, seed=3)
     v, l, a = (t.to(DEV).requires_grad_(True) for t in (value, loc, attn))

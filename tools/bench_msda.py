@@ -67,14 +67,15 @@ def alg_bytes(plan):
 ref_out = None
 print(f"workload {workload}")
 print("cell  order sched minb chunk | per-layer us | total us | GB/s")
-for cell in (32, 64):
+for cell in (64,):
     calls, plan = capture(cell)
     byts = alg_bytes(plan)
-    for use_order, schedule, minb in itertools.product((True,), (0, 1), (4, 5, 6)):
+    for use_order, schedule, minb in itertools.product((True,), (0, 1), (4, 41)):
         if not use_order and cell != 64:
             continue
-        for chunk in ((64,) if schedule == 0 else (32, 64, 96)):
-            cabi.set_option("msda_min_blocks", minb)
+        for chunk in ((64,) if schedule == 0 else (32, 64)):
+            cabi.set_option("msda_smem_broadcast", 1 if minb == 41 else 0)  # 41 = minb 4 + shared-memory broadcast
+            cabi.set_option("msda_min_blocks", 4 if minb == 41 else minb)
             cabi.set_option("msda_chunk", chunk)
             t = time_calls(calls, schedule, use_order)
             # correctness of every variant against the first one
