@@ -202,6 +202,18 @@ int sdetr_rows_scatter(float *dst, const int64_t *index, int batch, int num_rows
 int sdetr_split_tf32(const float *x, int64_t x_row_stride, int64_t rows, int K, int chunk, int layout_b, int relu,
                      float *out, sdetr_stream_t stream);
 
+/* Dense projection on the tcgen05 tensor cores with fp32-class accuracy (hand-written sm_100a GEMM):
+ *   C[M,N] = act(A)[M,K] . W[N,K]^T + bias,  act = ReLU when relu_a != 0 (salience_transformer.py:348), else identity.
+ * A (M,K) row pitch lda floats; W_hi/W_lo (N,K) contiguous = sdetr_split_tf32_pair(W); bias (N) nullable;
+ * C (M,N) row pitch ldc.  K % 32 == 0; A/W 16-byte aligned, lda % 4 == 0.  The activation is split into TF32 pieces
+ * inside the kernel (no extra HBM pass); products A_hi.W_hi + A_hi.W_lo + A_lo.W_hi accumulate in TMEM (fp32).
+ * Replaces the cuBLAS path for: value_proj / sampling_offsets|attention_weights / output_proj
+ * (models/bricks/ms_deform_attn.py:316,322-328,375), FFN (salience_transformer.py:347-351), class head (:462),
+ * MaskPredictor (:16-47), enc_output (base_transformer.py:111). */
+int sdetr_split_tf32_pair(const float *w, int64_t count, float *w_hi, float *w_lo, sdetr_stream_t stream);
+int sdetr_gemm_3xtf32(const float *A, int64_t lda, const float *W_hi, const float *W_lo, const float *bias, float *C,
+                      int64_t ldc, int M, int N, int K, int relu_a, sdetr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

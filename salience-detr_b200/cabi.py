@@ -45,6 +45,8 @@ SIGNATURES = {
     "sdetr_class_max_times_fg": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
     "sdetr_add_layernorm": (_i, [_vp, _vp, _vp, _vp, _f, _i64, _i, _vp, _vp]),
     "sdetr_split_tf32": (_i, [_vp, _i64, _i64, _i, _i, _i, _i, _vp, _vp]),
+    "sdetr_split_tf32_pair": (_i, [_vp, _i64, _vp, _vp, _vp]),
+    "sdetr_gemm_3xtf32": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
     "sdetr_rows_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "sdetr_rows_scatter": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
 }
@@ -354,3 +356,29 @@ def rows_scatter_(dst, index, src):
                                   _req(src, "src", torch.float32), _stream())
     _check(rc, "sdetr_rows_scatter")
     return dst
+
+
+def split_tf32_pair(w):
+    """(N,K) fp32 -> (W_hi, W_lo), both TF32-representable fp32 tensors of the same shape."""
+    w = w.contiguous()
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    _check(lib().sdetr_split_tf32_pair(_req(w, "w", torch.float32), w.numel(), hi.data_ptr(), lo.data_ptr(), _stream()),
+           "sdetr_split_tf32_pair")
+    return hi, lo
+
+
+def gemm_3xtf32(x, w_hi, w_lo, bias=None, relu_input: bool = False):
+    """y = act(x) @ W.T + bias on the tcgen05 tensor cores; x (..., K) with unit last stride and uniform row pitch."""
+    K = x.shape[-1]
+    N = w_hi.shape[0]
+    if not (x.is_cuda and x.dtype == torch.float32 and x.stride(-1) == 1):
+        raise RuntimeError("gemm_3xtf32 needs a CUDA float32 input with unit last stride")
+    x2 = x if x.dim() == 2 else x.reshape(-1, K)
+    M = x2.shape[0]
+    y = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    rc = lib().sdetr_gemm_3xtf32(x2.data_ptr(), x2.stride(0) if M > 1 else K, _req(w_hi, "w_hi", torch.float32),
+                                 _req(w_lo, "w_lo", torch.float32),
+                                 _req(bias, "bias", torch.float32) if bias is not None else None, y.data_ptr(), N, M, N, K,
+                                 int(relu_input), _stream())
+    _check(rc, "sdetr_gemm_3xtf32")
+    return y.view(*x.shape[:-1], N)

@@ -1,0 +1,312 @@
+// Dense projection GEMM of the path on the 5th-generation tensor cores -- sdetr_gemm_3xtf32.
+//
+//   C[M,N] = act(A)[M,K] . W[N,K]^T + bias        fp32 in / fp32 out, fp32-class accuracy ("3xTF32")
+//
+// These are the only true dense GEMMs of the path (models/bricks/ms_deform_attn.py:316,322-328,375 value / offset /
+// weight / output projections; salience_transformer.py:347-351 FFN; :462 class head; :16-47 MaskPredictor;
+// base_transformer.py:111 enc_output).  Hand-written for sm_100a:
+//
+//   * operands move with TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) into a 3-stage shared-memory ring;
+//   * the weight arrives pre-split (W_hi = tf32(W), W_lo = tf32(W - W_hi), cached per parameter); the activation is
+//     split IN the kernel: four converter warps rewrite each landed A tile in place as A_hi and write A_lo next to
+//     it (element-wise, so the TMA swizzle is preserved) -- no extra HBM pass, optional ReLU fused in;
+//   * one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=128, K=8): A_hi.W_hi + A_hi.W_lo + A_lo.W_hi into
+//     ONE fp32 accumulator tile in tensor memory (128 lanes x 128 columns);
+//   * tcgen05.commit signals stage release / accumulator ready through mbarriers; the converter warps then become
+//     the epilogue: tcgen05.ld (32 lanes x 32 columns per warp and step) -> + bias -> 128-bit global stores.
+//
+// Warp roles (256 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4..7 = convert + epilogue.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace sdetr {
+
+constexpr int kBM = 128, kBN = 128, kBK = 32;       // tile (fp32 elements); kBK * 4 B = one 128-byte swizzle row
+constexpr int kStages = 3;
+constexpr int kTileBytes = kBM * kBK * 4;           // 16 KB (A and W tiles have the same footprint: kBM == kBN)
+constexpr int kStageBytes = 4 * kTileBytes;         // A (raw -> hi), A_lo, W_hi, W_lo
+constexpr int kGemmThreads = 256;
+constexpr int kTmemCols = 128;
+constexpr int kGemmSmem = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_c),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor: K-major tile, rows of 128 bytes, SWIZZLE_128B, 8-row groups 1024 bytes apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout=2 [61,64))
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, both K-major, N=128, M=128
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+struct GemmParams {
+    const float *bias;
+    float *C;
+    int64_t ldc;
+    int M, N, K, relu_a;
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_whi,
+                   const __grid_constant__ CUtensorMap map_wlo, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
+    uint64_t *tma_full = bars, *conv_full = bars + kStages, *empty = bars + 2 * kStages, *acc_full = bars + 3 * kStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * kStages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * kBN, m0 = blockIdx.y * kBM;
+    const int nk = p.K / kBK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(tma_full + s, 1);
+            mbar_init(conv_full + s, 128);
+            mbar_init(empty + s, 1);
+        }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < nk; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                mbar_wait(empty + s, ph ^ 1);
+                uint8_t *st = smem + s * kStageBytes;
+                mbar_expect_tx(tma_full + s, 3 * kTileBytes);
+                tma_load_2d(&map_a, tma_full + s, st, kb * kBK, m0);
+                tma_load_2d(&map_whi, tma_full + s, st + 2 * kTileBytes, kb * kBK, n0);
+                tma_load_2d(&map_wlo, tma_full + s, st + 3 * kTileBytes, kb * kBK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < nk; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                mbar_wait(tma_full + s, ph);
+                mbar_wait(conv_full + s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t base = smem_u32(smem + s * kStageBytes);
+#pragma unroll
+                for (int k = 0; k < kBK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes = 2 sixteen-byte units
+                    const uint64_t a_hi = umma_desc(base) + 2 * k, a_lo = umma_desc(base + kTileBytes) + 2 * k;
+                    const uint64_t w_hi = umma_desc(base + 2 * kTileBytes) + 2 * k, w_lo = umma_desc(base + 3 * kTileBytes) + 2 * k;
+                    umma_tf32(tmem_acc, a_hi, w_hi, kIdesc, (kb | k) != 0);
+                    umma_tf32(tmem_acc, a_hi, w_lo, kIdesc, 1);
+                    umma_tf32(tmem_acc, a_lo, w_hi, kIdesc, 1);
+                }
+                umma_commit(empty + s);  // stage reusable once these MMAs have read it
+            }
+            umma_commit(acc_full);       // accumulator complete
+        }
+    } else if (warp >= 4) {
+        // ===== converter: A tile -> (A_hi in place, A_lo) =====
+        const int t = threadIdx.x - 128;  // 0..127
+        for (int kb = 0; kb < nk; ++kb) {
+            const int s = kb % kStages;
+            const uint32_t ph = (kb / kStages) & 1;
+            mbar_wait(tma_full + s, ph);
+            float4 *a = reinterpret_cast<float4 *>(smem + s * kStageBytes);
+            float4 *alo = reinterpret_cast<float4 *>(smem + s * kStageBytes + kTileBytes);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int idx = it * 128 + t;  // 16-byte chunk; a quarter-warp covers one 128-byte row: conflict-free
+                float4 v = a[idx];
+                if (p.relu_a) v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+                float4 hi, lo;
+                hi.x = tf32_rn(v.x), hi.y = tf32_rn(v.y), hi.z = tf32_rn(v.z), hi.w = tf32_rn(v.w);
+                lo.x = tf32_rn(v.x - hi.x), lo.y = tf32_rn(v.y - hi.y), lo.z = tf32_rn(v.z - hi.z), lo.w = tf32_rn(v.w - hi.w);
+                a[idx] = hi;
+                alo[idx] = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
+            mbar_arrive(conv_full + s);
+        }
+        // ===== epilogue: TMEM -> registers -> (+bias) -> global =====
+        mbar_wait(acc_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;                     // TMEM lane quadrant this warp may read
+        const int row = m0 + q * 32 + lane;
+        float *crow = p.C + (int64_t)row * p.ldc;
+        const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
+#pragma unroll 1
+        for (int c = 0; c < kBN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+            if (row < p.M) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int col = n0 + c * 32 + j;
+                    float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                           __uint_as_float(r[j + 3]));
+                    if (col + 3 < p.N && vec_ok) {
+                        if (p.bias) {
+                            const float4 bv = ldg_f4(p.bias + col);
+                            o.x += bv.x, o.y += bv.y, o.z += bv.z, o.w += bv.w;
+                        }
+                        *reinterpret_cast<float4 *>(crow + col) = o;
+                    } else {
+                        const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (col + e < p.N) crow[col + e] = ov[e] + (p.bias ? __ldg(p.bias + col + e) : 0.f);
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(kTmemCols));
+    }
+}
+
+// weight split: (N,K) -> W_hi, W_lo (both (N,K), TF32-representable)
+__global__ void split_pair_kernel(const float *__restrict__ w, int64_t n, float *__restrict__ hi, float *__restrict__ lo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = w[i], h = tf32_rn(x);
+    hi[i] = h, lo[i] = tf32_rn(x - h);
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor (rows, cols) with row stride ld (floats); box = (kBK cols, box_rows rows), 128-byte swizzle
+static bool make_map(CUtensorMap *m, const float *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace sdetr
+
+using namespace sdetr;
+
+extern "C" int sdetr_split_tf32_pair(const float *w, int64_t count, float *w_hi, float *w_lo, sdetr_stream_t stream) {
+    SDETR_REQUIRE(w && w_hi && w_lo, SDETR_ERR_INVALID_ARG, "split_tf32_pair: null pointer");
+    if (count <= 0) return SDETR_OK;
+    split_pair_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, count, w_hi, w_lo);
+    return check_launch("split_tf32_pair");
+}
+
+extern "C" int sdetr_gemm_3xtf32(const float *A, int64_t lda, const float *W_hi, const float *W_lo, const float *bias,
+                                 float *C, int64_t ldc, int M, int N, int K, int relu_a, sdetr_stream_t stream) {
+    SDETR_REQUIRE(A && W_hi && W_lo && C, SDETR_ERR_INVALID_ARG, "gemm_3xtf32: null pointer");
+    SDETR_REQUIRE(M >= 0 && N > 0 && K > 0, SDETR_ERR_INVALID_ARG, "gemm_3xtf32: bad sizes");
+    SDETR_REQUIRE(K % kBK == 0, SDETR_ERR_UNSUPPORTED, "gemm_3xtf32: K=%d must be a multiple of %d", K, kBK);
+    SDETR_REQUIRE(lda % 4 == 0 && aligned16(A) && aligned16(W_hi) && aligned16(W_lo) && lda >= K && ldc >= N,
+                  SDETR_ERR_INVALID_ARG, "gemm_3xtf32: operands must be 16-byte aligned with 16-byte row pitch");
+    if (M == 0) return SDETR_OK;
+    CUtensorMap ma, mh, ml;
+    SDETR_REQUIRE(make_map(&ma, A, M, K, lda, kBM) && make_map(&mh, W_hi, N, K, K, kBN) && make_map(&ml, W_lo, N, K, K, kBN),
+                  SDETR_ERR_CUDA, "gemm_3xtf32: cuTensorMapEncodeTiled failed");
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+        SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "gemm_3xtf32: smem attribute: %s", cudaGetErrorString(e));
+        attr = true;
+    }
+    GemmParams p{bias, C, ldc, M, N, K, relu_a};
+    dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM);
+    gemm_3xtf32_kernel<<<grid, kGemmThreads, kGemmSmem, (cudaStream_t)stream>>>(ma, mh, ml, p);
+    return check_launch("gemm_3xtf32");
+}

@@ -2,7 +2,9 @@
 
 These are true dense GEMMs, the only place of the path where tensor cores belong.  ``MODE``:
 
-* ``"3xtf32"`` (default): each operand is split into two TF32 pieces by ``sdetr_split_tf32`` and ONE cuBLAS TF32
+* ``"tcgen05"``: the hand-written sm_100a GEMM (``sdetr_gemm_3xtf32``: TMA -> in-kernel TF32 split of the activation
+  -> tcgen05.mma.kind::tf32 into TMEM -> epilogue), same 3xTF32 arithmetic without the separate split pass.
+* ``"3xtf32"``: each operand is split into two TF32 pieces by ``sdetr_split_tf32`` and ONE cuBLAS TF32
   GEMM over K' = 3K accumulates A_hi.B_hi + A_hi.B_lo + A_lo.B_hi in fp32 -- tensor-core speed with fp32-class
   accuracy (error ~2^-21 relative per product, same order as fp32 summation-order noise; measured in
   tests/test_gpu_parity.py::test_linear_3xtf32_accuracy).  Weight splits are cached per parameter version.
@@ -20,7 +22,7 @@ from torch.nn import functional as F
 
 from . import cabi
 
-MODE = "3xtf32"
+MODE = "tcgen05"
 K_CHUNK = 512  # longest reduction handed to one tensor-core GEMM (its accumulator truncates: error ~ length)
 _weight_cache: Dict[int, Tuple[tuple, Tensor]] = {}
 
@@ -50,15 +52,33 @@ def split_weight(weight: Tensor) -> Tensor:
     return hit[1]
 
 
+_pair_cache: Dict[int, Tuple[tuple, Tuple[Tensor, Tensor]]] = {}
+
+
+def split_weight_pair(weight: Tensor) -> Tuple[Tensor, Tensor]:
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape))
+    hit = _pair_cache.get(id(weight))
+    if hit is None or hit[0] != key:
+        with torch.no_grad():
+            hit = (key, cabi.split_tf32_pair(weight.detach()))
+        _pair_cache[id(weight)] = hit
+    return hit[1]
+
+
 def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, relu_input: bool = False) -> Tensor:
     """y = (relu(x) if relu_input else x) @ weight.T + bias, inference only (no autograd through the split)."""
+    if MODE == "tcgen05" and weight.shape[1] % 32 == 0 and x.stride(-1) == 1 and x.shape[-1] % 4 == 0:
+        x2 = x if x.dim() == 2 else x.reshape(-1, x.shape[-1])
+        if x2.stride(0) % 4 == 0 or x2.shape[0] == 1:
+            w_hi, w_lo = split_weight_pair(weight)
+            return cabi.gemm_3xtf32(x, w_hi, w_lo, bias, relu_input)
     if MODE == "fp32" or weight.shape[1] % 4 != 0:
         return F.linear(F.relu(x) if relu_input else x, weight, bias)
     if MODE == "tf32":
         with _tf32_matmul():
             return F.linear(F.relu(x) if relu_input else x, weight, bias)
     K = weight.shape[1]
-    kc = _chunk_of(K)
+    kc = _chunk_of(K)  # (MODE "3xtf32", or "tcgen05" falling back for an unsupported shape)
     x3 = cabi.split_tf32(x, layout_b=False, relu=relu_input, chunk=kc)
     w3 = split_weight(weight)
     with _tf32_matmul():

@@ -333,8 +333,39 @@ def test_linear_3xtf32_accuracy(pkg):
     assert torch.equal(s3[:, :, 0], s3[:, :, 1]) and (s3[:, :, 0] + s3[:, :, 2] - x.view(7, 4, 16)).abs().max() < 1e-6
 
 
+def test_gemm_tcgen05_3xtf32(pkg):
+    """Hand-written tcgen05 GEMM (TMA + in-kernel TF32 split + TMEM accumulator) against an fp64 reference."""
+    g = torch.Generator().manual_seed(1)
+    for rows, K, N, relu in [(128, 32, 128, False), (300, 256, 384, False), (4097, 256, 256, False), (1000, 2048, 256, True),
+                             (333, 256, 91, False), (50, 64, 1, False), (22726, 256, 1536, False), (513, 128, 64, False)]:
+        x = torch.randn(rows, K, generator=g).to(DEV)
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+        b = torch.randn(N, generator=g).to(DEV)
+        w_hi, w_lo = pkg.cabi.split_tf32_pair(w)
+        assert (w_hi + w_lo - w).abs().max() < 1e-6
+        y = pkg.cabi.gemm_3xtf32(x, w_hi, w_lo, b, relu)
+        torch.cuda.synchronize()
+        ref = torch.nn.functional.linear((x.relu() if relu else x).double(), w.double(), b.double())
+        err = (y.double() - ref).abs().max().item()
+        assert err < 1e-4, (rows, K, N, err)
+        # no bias, strided rows (a column slice of a wider buffer)
+        wide = torch.randn(rows, K + 32, generator=g).to(DEV)
+        y2 = pkg.cabi.gemm_3xtf32(wide[:, 32:], w_hi, w_lo)
+        ref2 = wide[:, 32:].double() @ w.double().t()
+        assert (y2.double() - ref2).abs().max() < 1e-4
+    prev = pkg.gemm.MODE
+    try:
+        pkg.gemm.MODE = "tcgen05"
+        x = torch.randn(2, 77, 256, generator=g).to(DEV)
+        w = torch.randn(384, 256, generator=g).to(DEV) / 16
+        y = pkg.gemm.linear(x, w, None)
+        assert y.shape == (2, 77, 384) and (y.double() - x.double() @ w.double().t()).abs().max() < 1e-4
+    finally:
+        pkg.gemm.MODE = prev
+
+
 # ---- module level ---------------------------------------------------------------------------------------------------
-@pytest.fixture(params=["fp32", "3xtf32"])
+@pytest.fixture(params=["fp32", "3xtf32", "tcgen05"])
 def gemm_mode(pkg, request):
     prev = pkg.gemm.MODE
     pkg.gemm.MODE = request.param

@@ -19,12 +19,14 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="resnet50_800_1333_bs2")
 ap.add_argument("--no-order", action="store_true")
 ap.add_argument("--schedule", type=int, default=None)
+ap.add_argument("--gemm", default="tcgen05")
 args = ap.parse_args()
 if args.schedule is not None:
     import salience_detr_b200.salience_transformer as st
     st.MSDA_SCHEDULE = args.schedule
     st.SalienceTransformerEncoderLayer.forward_fast.__defaults__ = (None, args.schedule)
 
+pkg.gemm.MODE = args.gemm
 dev = torch.device("cuda:0")
 model = build_model().to(dev)
 feats, masks, pos = make_inputs(args.workload, seed=0, device=dev)
