@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-order", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
-    ap.add_argument("--gemm", default="tcgen05", choices=["tcgen05", "3xtf32", "fp32", "tf32"])
+    ap.add_argument("--gemm", default="auto", choices=["auto", "tcgen05", "3xtf32", "fp32", "tf32"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -299,7 +299,9 @@ def main():
             "config": {"workload": WORKLOAD, "batch_per_gpu": bsz, "global_batch": bsz * world,
                        "parallelism": f"dp{world} (independent replicas, no forward collective)",
                        "weights": "random init (seed 0) + N(0,0.02) sampling-offset weights",
-                       "gemm": {"tcgen05": "hand-written tcgen05.mma.kind::tf32 GEMM (TMA, in-kernel 3xTF32 split, TMEM accumulator; fp32-class accuracy)",
+                       "gemm": {"auto": "3xTF32 (fp32-class accuracy) everywhere: hand-written tcgen05.mma.kind::tf32 GEMM (TMA multicast, in-kernel "
+                                        "operand split, TMEM accumulator) for N<=512 or K>=1024, cuBLAS TF32 on pre-split operands for the wide K=256 GEMMs",
+                                "tcgen05": "hand-written tcgen05.mma.kind::tf32 GEMM (TMA, in-kernel 3xTF32 split, TMEM accumulator; fp32-class accuracy)",
                                 "3xtf32": "cuBLAS TF32 tensor cores on 3-way split operands (3xTF32, fp32-class accuracy)",
                                 "fp32": "cuBLAS fp32 SIMT", "tf32": "cuBLAS TF32 (reduced precision)"}[pkg.gemm.MODE], "cuda_graph": runner.graph is not None,
                        "msda_order": "spatial tiles" if runner.use_order else "score order",

@@ -210,6 +210,8 @@ int sdetr_split_tf32(const float *x, int64_t x_row_stride, int64_t rows, int K, 
  * Replaces the cuBLAS path for: value_proj / sampling_offsets|attention_weights / output_proj
  * (models/bricks/ms_deform_attn.py:316,322-328,375), FFN (salience_transformer.py:347-351), class head (:462),
  * MaskPredictor (:16-47), enc_output (base_transformer.py:111). */
+/* debugging aid: when set, CTA (0,0) of every sdetr_gemm_3xtf32 launch records clock64() per pipeline event */
+int sdetr_gemm_set_trace(long long *device_buffer);
 int sdetr_split_tf32_pair(const float *w, int64_t count, float *w_hi, float *w_lo, sdetr_stream_t stream);
 int sdetr_gemm_3xtf32(const float *A, int64_t lda, const float *W_hi, const float *W_lo, const float *bias, float *C,
                       int64_t ldc, int M, int N, int K, int relu_a, sdetr_stream_t stream);

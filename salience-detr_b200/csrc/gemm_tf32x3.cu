@@ -15,7 +15,12 @@
 //   * tcgen05.commit signals stage release / accumulator ready through mbarriers; the converter warps then become
 //     the epilogue: tcgen05.ld (32 lanes x 32 columns per warp and step) -> + bias -> 128-bit global stores.
 //
-// Warp roles (256 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4..7 = convert + epilogue.
+//   * CTAs run as clusters of two along M: both need the same W k-block, so rank 0 fetches W_hi and rank 1 fetches
+//     W_lo and each TMA load is MULTICAST into both CTAs' rings (the kernel is bound by L2->SM bandwidth: this cuts
+//     a CTA's traffic per k-block from 48 KB to 32 KB).  A ring stage is refilled only when the MMAs of BOTH CTAs
+//     have released it (tcgen05.commit multicast onto both `empty` barriers).
+//
+// Warp roles (384 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4..11 = convert + epilogue.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -23,12 +28,15 @@
 namespace sdetr {
 
 constexpr int kBM = 128, kBN = 128, kBK = 32;       // tile (fp32 elements); kBK * 4 B = one 128-byte swizzle row
-constexpr int kStages = 3;
+constexpr int kStages = 4;                          // TMA ring: covers ~2.7k cycles of L2->smem latency
+constexpr int kLoSlots = 2;                         // A_lo ring (written by the converters, read by the MMAs)
 constexpr int kTileBytes = kBM * kBK * 4;           // 16 KB (A and W tiles have the same footprint: kBM == kBN)
-constexpr int kStageBytes = 4 * kTileBytes;         // A (raw -> hi), A_lo, W_hi, W_lo
-constexpr int kGemmThreads = 256;
+constexpr int kStageBytes = 3 * kTileBytes;         // A (raw -> hi in place), W_hi, W_lo
+constexpr int kConvWarps = 8;
+constexpr int kGemmThreads = 128 + 32 * kConvWarps; // warps 0..3: producer / MMA / TMEM / idle; 4..11: convert + epilogue
 constexpr int kTmemCols = 128;
-constexpr int kGemmSmem = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int kRingBytes = kStages * kStageBytes + kLoSlots * kTileBytes;  // 224 KB
+constexpr int kGemmSmem = kRingBytes + 1024 /* alignment slack */ + 256 /* barriers */;
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -61,6 +69,36 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *ba
             smem_u32(dst)),
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+        "[%2], %5;" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -96,27 +134,32 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, both K-major, N=128, M=128
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 
-__device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
-}
+// tf32 rounding (nearest, ties away from zero) with two ALU ops -- same result as cvt.rna.tf32.f32 for finite inputs
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
 struct GemmParams {
     const float *bias;
     float *C;
     int64_t ldc;
-    int M, N, K, relu_a;
+    int M, N, K, relu_a, use_tma_store;
+    long long *dbg;  // optional per-event clock64() trace of CTA (0,0): [role][kb] (tools/gemm_trace.py)
 };
+#define SDETR_TRACE(role, kb)                                                             \
+    do {                                                                                  \
+        if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0) p.dbg[(role) * 128 + (kb)] = clock64(); \
+    } while (0)
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_whi,
-                   const __grid_constant__ CUtensorMap map_wlo, const GemmParams p) {
+                   const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_c,
+                   const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
-    uint64_t *tma_full = bars, *conv_full = bars + kStages, *empty = bars + 2 * kStages, *acc_full = bars + 3 * kStages;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * kStages + 1);
+    uint8_t *lo_ring = smem + kStages * kStageBytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kRingBytes);
+    uint64_t *tma_full = bars, *conv_full = bars + kStages, *empty = bars + 2 * kStages;
+    uint64_t *lo_empty = bars + 3 * kStages, *acc_full = lo_empty + kLoSlots;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * kBN, m0 = blockIdx.y * kBM;
@@ -125,9 +168,10 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(tma_full + s, 1);
-            mbar_init(conv_full + s, 128);
-            mbar_init(empty + s, 1);
+            mbar_init(conv_full + s, 32 * kConvWarps);
+            mbar_init(empty + s, 2);  // released by the MMA warps of BOTH CTAs of the cluster
         }
+        for (int s = 0; s < kLoSlots; ++s) mbar_init(lo_empty + s, 1);
         mbar_init(acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -137,8 +181,11 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    cluster_sync_all();  // the peer's barriers are initialised before any multicast / remote arrive can reach them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_acc = *tmem_slot;
+    const uint32_t rank = cluster_ctarank();
+    if (threadIdx.x == 0) SDETR_TRACE(5, 2);  // setup done
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -147,93 +194,120 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 const int s = kb % kStages;
                 const uint32_t ph = (kb / kStages) & 1;
                 mbar_wait(empty + s, ph ^ 1);
+                SDETR_TRACE(0, kb);  // producer: stage free, issuing TMA
                 uint8_t *st = smem + s * kStageBytes;
-                mbar_expect_tx(tma_full + s, 3 * kTileBytes);
+                mbar_expect_tx(tma_full + s, 3 * kTileBytes);  // own A + W_hi + W_lo (one of them arrives from the peer)
                 tma_load_2d(&map_a, tma_full + s, st, kb * kBK, m0);
-                tma_load_2d(&map_whi, tma_full + s, st + 2 * kTileBytes, kb * kBK, n0);
-                tma_load_2d(&map_wlo, tma_full + s, st + 3 * kTileBytes, kb * kBK, n0);
+                if (rank == 0) tma_load_2d_mc(&map_whi, tma_full + s, st + kTileBytes, kb * kBK, n0, 0b11);
+                else tma_load_2d_mc(&map_wlo, tma_full + s, st + 2 * kTileBytes, kb * kBK, n0, 0b11);
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
             for (int kb = 0; kb < nk; ++kb) {
-                const int s = kb % kStages;
+                const int s = kb % kStages, ls = kb % kLoSlots;
                 const uint32_t ph = (kb / kStages) & 1;
                 mbar_wait(tma_full + s, ph);
+                SDETR_TRACE(1, kb);  // MMA: TMA landed
                 mbar_wait(conv_full + s, ph);
+                SDETR_TRACE(2, kb);  // MMA: converted, issuing
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t base = smem_u32(smem + s * kStageBytes);
+                const uint32_t lo_base = smem_u32(lo_ring + ls * kTileBytes);
 #pragma unroll
                 for (int k = 0; k < kBK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes = 2 sixteen-byte units
-                    const uint64_t a_hi = umma_desc(base) + 2 * k, a_lo = umma_desc(base + kTileBytes) + 2 * k;
-                    const uint64_t w_hi = umma_desc(base + 2 * kTileBytes) + 2 * k, w_lo = umma_desc(base + 3 * kTileBytes) + 2 * k;
+                    const uint64_t a_hi = umma_desc(base) + 2 * k, a_lo = umma_desc(lo_base) + 2 * k;
+                    const uint64_t w_hi = umma_desc(base + kTileBytes) + 2 * k, w_lo = umma_desc(base + 2 * kTileBytes) + 2 * k;
                     umma_tf32(tmem_acc, a_hi, w_hi, kIdesc, (kb | k) != 0);
                     umma_tf32(tmem_acc, a_hi, w_lo, kIdesc, 1);
                     umma_tf32(tmem_acc, a_lo, w_hi, kIdesc, 1);
                 }
-                umma_commit(empty + s);  // stage reusable once these MMAs have read it
+                umma_commit_mc(empty + s, 0b11);  // TMA stage reusable (in both CTAs) once these MMAs have read it
+                umma_commit(lo_empty + ls);   // ... and so is the A_lo slot
             }
-            umma_commit(acc_full);       // accumulator complete
+            umma_commit(acc_full);            // accumulator complete
         }
     } else if (warp >= 4) {
-        // ===== converter: A tile -> (A_hi in place, A_lo) =====
-        const int t = threadIdx.x - 128;  // 0..127
+        // ===== converters: landed A tile -> A_hi (in place) + A_lo (ring) =====
+        const int t = threadIdx.x - 128;  // 0 .. 32*kConvWarps-1
+        constexpr int kPer = (kTileBytes / 16) / (32 * kConvWarps);  // 16-byte chunks per thread and stage
         for (int kb = 0; kb < nk; ++kb) {
-            const int s = kb % kStages;
-            const uint32_t ph = (kb / kStages) & 1;
+            const int s = kb % kStages, ls = kb % kLoSlots;
+            const uint32_t ph = (kb / kStages) & 1, lph = (kb / kLoSlots) & 1;
+            mbar_wait(lo_empty + ls, lph ^ 1);  // A_lo slot released by the MMAs of k-block kb - kLoSlots
             mbar_wait(tma_full + s, ph);
+            if (t == 0) SDETR_TRACE(3, kb);  // converter: start
             float4 *a = reinterpret_cast<float4 *>(smem + s * kStageBytes);
-            float4 *alo = reinterpret_cast<float4 *>(smem + s * kStageBytes + kTileBytes);
+            float4 *alo = reinterpret_cast<float4 *>(lo_ring + ls * kTileBytes);
+            float4 v[kPer];
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int idx = it * 128 + t;  // 16-byte chunk; a quarter-warp covers one 128-byte row: conflict-free
-                float4 v = a[idx];
-                if (p.relu_a) v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+            for (int it = 0; it < kPer; ++it) v[it] = a[it * (32 * kConvWarps) + t];  // a quarter-warp = one 128-byte row
+#pragma unroll
+            for (int it = 0; it < kPer; ++it) {
+                float4 x = v[it];
+                if (p.relu_a) x.x = fmaxf(x.x, 0.f), x.y = fmaxf(x.y, 0.f), x.z = fmaxf(x.z, 0.f), x.w = fmaxf(x.w, 0.f);
                 float4 hi, lo;
-                hi.x = tf32_rn(v.x), hi.y = tf32_rn(v.y), hi.z = tf32_rn(v.z), hi.w = tf32_rn(v.w);
-                lo.x = tf32_rn(v.x - hi.x), lo.y = tf32_rn(v.y - hi.y), lo.z = tf32_rn(v.z - hi.z), lo.w = tf32_rn(v.w - hi.w);
-                a[idx] = hi;
-                alo[idx] = lo;
+                hi.x = tf32_rn(x.x), hi.y = tf32_rn(x.y), hi.z = tf32_rn(x.z), hi.w = tf32_rn(x.w);
+                lo.x = tf32_rn(x.x - hi.x), lo.y = tf32_rn(x.y - hi.y), lo.z = tf32_rn(x.z - hi.z), lo.w = tf32_rn(x.w - hi.w);
+                a[it * (32 * kConvWarps) + t] = hi;
+                alo[it * (32 * kConvWarps) + t] = lo;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
             mbar_arrive(conv_full + s);
+            if (t == 0) SDETR_TRACE(4, kb);  // converter: done
         }
-        // ===== epilogue: TMEM -> registers -> (+bias) -> global =====
+        // ===== epilogue: TMEM -> registers -> (+bias) -> swizzled smem box -> TMA store (or direct stores) =====
         mbar_wait(acc_full, 0);
+        if (t == 0) SDETR_TRACE(5, 0);  // epilogue start
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int q = warp & 3;                     // TMEM lane quadrant this warp may read
-        const int row = m0 + q * 32 + lane;
-        float *crow = p.C + (int64_t)row * p.ldc;
-        const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+        const int half = (warp - 4) >> 2;       // warps 4..7: column blocks 0,1; warps 8..11: column blocks 2,3
+        const int r_in = q * 32 + lane, row = m0 + r_in;
 #pragma unroll 1
-        for (int c = 0; c < kBN / 32; ++c) {
+        for (int cc = 0; cc < 2; ++cc) {
+            const int c = half * 2 + cc;
             uint32_t r[32];
             tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-            if (row < p.M) {
+            const int col0 = n0 + c * 32;
+            if (p.use_tma_store) {
+                // all MMAs have completed (acc_full), so the TMA ring is free: box c lives at smem + c*16 KB,
+                // 128 rows x 128 B, 128-byte swizzle (chunk ^ (row & 7)) like the tensor map expects
+                uint8_t *box = smem + c * kTileBytes;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const int col = n0 + c * 32 + j;
                     float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                                            __uint_as_float(r[j + 3]));
-                    if (col + 3 < p.N && vec_ok) {
-                        if (p.bias) {
-                            const float4 bv = ldg_f4(p.bias + col);
-                            o.x += bv.x, o.y += bv.y, o.z += bv.z, o.w += bv.w;
-                        }
-                        *reinterpret_cast<float4 *>(crow + col) = o;
-                    } else {
-                        const float ov[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (col + e < p.N) crow[col + e] = ov[e] + (p.bias ? __ldg(p.bias + col + e) : 0.f);
+                    if (p.bias && col0 + j + 3 < p.N) {
+                        const float4 bv = ldg_f4(p.bias + col0 + j);
+                        o.x += bv.x, o.y += bv.y, o.z += bv.z, o.w += bv.w;
+                    } else if (p.bias) {
+                        if (col0 + j < p.N) o.x += __ldg(p.bias + col0 + j);
+                        if (col0 + j + 1 < p.N) o.y += __ldg(p.bias + col0 + j + 1);
+                        if (col0 + j + 2 < p.N) o.z += __ldg(p.bias + col0 + j + 2);
                     }
+                    *reinterpret_cast<float4 *>(box + r_in * 128 + (((j >> 2) ^ (r_in & 7)) << 4)) = o;
                 }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                named_bar_sync(1 + half, 128);  // the four warps that filled this box
+                if ((warp & 3) == 0 && lane == 0 && col0 < p.N) {
+                    tma_store_2d(&map_c, box, col0, m0);  // clips rows >= M and columns >= N
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else if (row < p.M) {
+                float *crow = p.C + (int64_t)row * p.ldc;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col0 + j < p.N) crow[col0 + j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
             }
         }
+        if (p.use_tma_store && (warp & 3) == 0 && lane == 0)
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the bulk stores
     }
+    if (threadIdx.x == 128) SDETR_TRACE(5, 1);  // epilogue end
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's shared memory until it is done too
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(kTmemCols));
     }
@@ -265,6 +339,7 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 tensor (rows, cols) with row stride ld (floats); box = (kBK cols, box_rows rows), 128-byte swizzle
+static long long *g_gemm_dbg = nullptr;
 static bool make_map(CUtensorMap *m, const float *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
@@ -281,6 +356,11 @@ static bool make_map(CUtensorMap *m, const float *base, int64_t rows, int64_t co
 
 using namespace sdetr;
 
+extern "C" int sdetr_gemm_set_trace(long long *device_buffer /* 6*128 int64, or NULL */) {
+    g_gemm_dbg = device_buffer;
+    return SDETR_OK;
+}
+
 extern "C" int sdetr_split_tf32_pair(const float *w, int64_t count, float *w_hi, float *w_lo, sdetr_stream_t stream) {
     SDETR_REQUIRE(w && w_hi && w_lo, SDETR_ERR_INVALID_ARG, "split_tf32_pair: null pointer");
     if (count <= 0) return SDETR_OK;
@@ -296,17 +376,30 @@ extern "C" int sdetr_gemm_3xtf32(const float *A, int64_t lda, const float *W_hi,
     SDETR_REQUIRE(lda % 4 == 0 && aligned16(A) && aligned16(W_hi) && aligned16(W_lo) && lda >= K && ldc >= N,
                   SDETR_ERR_INVALID_ARG, "gemm_3xtf32: operands must be 16-byte aligned with 16-byte row pitch");
     if (M == 0) return SDETR_OK;
-    CUtensorMap ma, mh, ml;
+    CUtensorMap ma, mh, ml, mc;
     SDETR_REQUIRE(make_map(&ma, A, M, K, lda, kBM) && make_map(&mh, W_hi, N, K, K, kBN) && make_map(&ml, W_lo, N, K, K, kBN),
                   SDETR_ERR_CUDA, "gemm_3xtf32: cuTensorMapEncodeTiled failed");
+    // the epilogue leaves through TMA bulk stores when C's rows are 16-byte aligned (else plain stores, e.g. N = 91)
+    const int use_tma_store = (ldc % 4 == 0) && aligned16(C) && make_map(&mc, C, M, N, ldc, kBM);
+    if (!use_tma_store) mc = ma;
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
         SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "gemm_3xtf32: smem attribute: %s", cudaGetErrorString(e));
         attr = true;
     }
-    GemmParams p{bias, C, ldc, M, N, K, relu_a};
-    dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM);
-    gemm_3xtf32_kernel<<<grid, kGemmThreads, kGemmSmem, (cudaStream_t)stream>>>(ma, mh, ml, p);
+    GemmParams p{bias, C, ldc, M, N, K, relu_a, use_tma_store, g_gemm_dbg};
+    const int mtiles = (M + kBM - 1) / kBM;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((N + kBN - 1) / kBN, (mtiles + 1) & ~1);  // clusters of 2 along M (an odd tail tile is all out-of-bounds)
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = kGemmSmem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1, at[0].val.clusterDim.y = 2, at[0].val.clusterDim.z = 1;
+    cfg.attrs = at, cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_3xtf32_kernel, ma, mh, ml, mc, p);
+    SDETR_REQUIRE(le == cudaSuccess, SDETR_ERR_CUDA, "gemm_3xtf32: launch: %s", cudaGetErrorString(le));
     return check_launch("gemm_3xtf32");
 }

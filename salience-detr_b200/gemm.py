@@ -2,6 +2,9 @@
 
 These are true dense GEMMs, the only place of the path where tensor cores belong.  ``MODE``:
 
+* ``"auto"`` (default): per shape, whichever of the next two measured faster on B200 (tools/bench_gemm.py,
+  profiles/r1_gemm_shapes.txt): the hand-written kernel for N <= 512 or K >= 1024 (output / offset / class / FFN-2 /
+  enc_output / MaskPredictor projections), cuBLAS 3xTF32 for the wide K = 256 GEMMs (value_proj x6, FFN-1).
 * ``"tcgen05"``: the hand-written sm_100a GEMM (``sdetr_gemm_3xtf32``: TMA -> in-kernel TF32 split of the activation
   -> tcgen05.mma.kind::tf32 into TMEM -> epilogue), same 3xTF32 arithmetic without the separate split pass.
 * ``"3xtf32"``: each operand is split into two TF32 pieces by ``sdetr_split_tf32`` and ONE cuBLAS TF32
@@ -22,7 +25,7 @@ from torch.nn import functional as F
 
 from . import cabi
 
-MODE = "tcgen05"
+MODE = "auto"
 K_CHUNK = 512  # longest reduction handed to one tensor-core GEMM (its accumulator truncates: error ~ length)
 _weight_cache: Dict[int, Tuple[tuple, Tensor]] = {}
 
@@ -67,12 +70,14 @@ def split_weight_pair(weight: Tensor) -> Tuple[Tensor, Tensor]:
 
 def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, relu_input: bool = False) -> Tensor:
     """y = (relu(x) if relu_input else x) @ weight.T + bias, inference only (no autograd through the split)."""
-    if MODE == "tcgen05" and weight.shape[1] % 32 == 0 and x.stride(-1) == 1 and x.shape[-1] % 4 == 0:
+    n, k = weight.shape
+    own = MODE == "tcgen05" or (MODE == "auto" and (n <= 512 or k >= 1024))
+    if own and k % 32 == 0 and x.stride(-1) == 1:
         x2 = x if x.dim() == 2 else x.reshape(-1, x.shape[-1])
         if x2.stride(0) % 4 == 0 or x2.shape[0] == 1:
             w_hi, w_lo = split_weight_pair(weight)
             return cabi.gemm_3xtf32(x, w_hi, w_lo, bias, relu_input)
-    if MODE == "fp32" or weight.shape[1] % 4 != 0:
+    if MODE == "fp32" or k % 4 != 0:
         return F.linear(F.relu(x) if relu_input else x, weight, bias)
     if MODE == "tf32":
         with _tf32_matmul():

@@ -365,7 +365,7 @@ def test_gemm_tcgen05_3xtf32(pkg):
 
 
 # ---- module level ---------------------------------------------------------------------------------------------------
-@pytest.fixture(params=["fp32", "3xtf32", "tcgen05"])
+@pytest.fixture(params=["fp32", "3xtf32", "tcgen05", "auto"])
 def gemm_mode(pkg, request):
     prev = pkg.gemm.MODE
     pkg.gemm.MODE = request.param

@@ -19,7 +19,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="resnet50_800_1333_bs2")
 ap.add_argument("--no-order", action="store_true")
 ap.add_argument("--schedule", type=int, default=None)
-ap.add_argument("--gemm", default="tcgen05")
+ap.add_argument("--gemm", default="auto")
 args = ap.parse_args()
 if args.schedule is not None:
     import salience_detr_b200.salience_transformer as st
