@@ -185,6 +185,14 @@ int sdetr_class_max_times_fg(const float *logits, const float *fg, int64_t rows,
 int sdetr_add_layernorm(const float *x, const float *r, const float *gamma, const float *beta, float eps,
                         int64_t rows, int channels, float *y, sdetr_stream_t stream);
 
+/* Front end: per-level NCHW maps -> token layout in one pass (base_transformer.py:21-32,
+ * salience_transformer.py:107-113):  feat_tok[b,t,:] = feat_l[b,:,y,x];  lpos_tok = pos_l + level_embeds[l];
+ * x_tok = (feat_tok + lpos_tok) * keep[b,t]  (keep = ~padding & proposal-valid, base_transformer.py:100-108).
+ * feats_host / pos_host: HOST arrays of num_levels device pointers to (b,C,H_l*W_l) fp32; level_size_host = H_l*W_l. */
+int sdetr_flatten_tokens(const float *const *feats_host, const float *const *pos_host, const float *level_embeds,
+                         const float *keep, const int32_t *level_size_host, int batch, int channels, int num_levels,
+                         float *feat_tok, float *lpos_tok, float *x_tok, sdetr_stream_t stream);
+
 /* Row gather / scatter by per-image index (the top-k tokens of the pre-attention, salience_transformer.py:368-379):
  * out[b,j,:] = src[b,index[b,j],:]   /   dst[b,index[b,j],:] = src[b,j,:]  (indices unique per image).
  * src/dst (b,num_rows,C), index (b,k) int64. */
@@ -203,7 +211,7 @@ int sdetr_split_tf32(const float *x, int64_t x_row_stride, int64_t rows, int K, 
                      float *out, sdetr_stream_t stream);
 
 /* Dense projection on the tcgen05 tensor cores with fp32-class accuracy (hand-written sm_100a GEMM):
- *   C[M,N] = act(A)[M,K] . W[N,K]^T + bias,  act = ReLU when relu_a != 0 (salience_transformer.py:348), else identity.
+ *   C[M,N] = act(A)[M,K] . W[N,K]^T + bias,  act = ReLU (relu_a = 1, salience_transformer.py:348), exact GELU (relu_a = 2, :23-29) or identity (0).
  * A (M,K) row pitch lda floats; W_hi/W_lo (N,K) contiguous = sdetr_split_tf32_pair(W); bias (N) nullable;
  * C (M,N) row pitch ldc.  K % 32 == 0; A/W 16-byte aligned, lda % 4 == 0.  The activation is split into TF32 pieces
  * inside the kernel (no extra HBM pass); products A_hi.W_hi + A_hi.W_lo + A_lo.W_hi accumulate in TMEM (fp32).

@@ -48,6 +48,7 @@ SIGNATURES = {
     "sdetr_gemm_set_trace": (_i, [_vp]),
     "sdetr_split_tf32_pair": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "sdetr_gemm_3xtf32": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "sdetr_flatten_tokens": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "sdetr_rows_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "sdetr_rows_scatter": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
 }
@@ -323,7 +324,7 @@ def add_layernorm(x, r, gamma, beta, eps: float = 1e-5, out=None):
     return out
 
 
-def split_tf32(x, layout_b: bool = False, relu: bool = False, chunk: int = 0):
+def split_tf32(x, layout_b: bool = False, relu=0, chunk: int = 0):
     """(..., K) fp32 with contiguous rows -> (rows, 3K) 3xTF32 operand: per K-chunk [hi|hi|lo] (weights: [hi|lo|hi])."""
     K = x.shape[-1]
     chunk = chunk or K
@@ -368,7 +369,7 @@ def split_tf32_pair(w):
     return hi, lo
 
 
-def gemm_3xtf32(x, w_hi, w_lo, bias=None, relu_input: bool = False):
+def gemm_3xtf32(x, w_hi, w_lo, bias=None, relu_input=0):
     """y = act(x) @ W.T + bias on the tcgen05 tensor cores; x (..., K) with unit last stride and uniform row pitch."""
     K = x.shape[-1]
     N = w_hi.shape[0]
@@ -383,3 +384,19 @@ def gemm_3xtf32(x, w_hi, w_lo, bias=None, relu_input: bool = False):
                                  int(relu_input), _stream())
     _check(rc, "sdetr_gemm_3xtf32")
     return y.view(*x.shape[:-1], N)
+
+
+def flatten_tokens(feats, pos, level_embeds, keep):
+    """Per-level (b,C,H,W) feats / pos -> (feat_tok, lpos_tok, x_tok), each (b,Nv,C); keep (b,Nv) float."""
+    L = len(feats)
+    b, c = feats[0].shape[:2]
+    sizes = [f.shape[2] * f.shape[3] for f in feats]
+    nv = sum(sizes)
+    dev = feats[0].device
+    fp = (ctypes.c_void_p * L)(*[_req(f, "feat", torch.float32) for f in feats])
+    pp = (ctypes.c_void_p * L)(*[_req(p, "pos", torch.float32) for p in pos])
+    out = [torch.empty(b, nv, c, device=dev, dtype=torch.float32) for _ in range(3)]
+    rc = lib().sdetr_flatten_tokens(fp, pp, _req(level_embeds, "level_embeds", torch.float32), _req(keep, "keep", torch.float32),
+                                    _host_i32(sizes), b, c, L, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), _stream())
+    _check(rc, "sdetr_flatten_tokens")
+    return out

@@ -134,6 +134,8 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, both K-major, N=128, M=128
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
 // tf32 rounding (nearest, ties away from zero) with two ALU ops -- same result as cvt.rna.tf32.f32 for finite inputs
 __device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
@@ -246,7 +248,11 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
             for (int it = 0; it < kPer; ++it) {
                 float4 x = v[it];
-                if (p.relu_a) x.x = fmaxf(x.x, 0.f), x.y = fmaxf(x.y, 0.f), x.z = fmaxf(x.z, 0.f), x.w = fmaxf(x.w, 0.f);
+                if (p.relu_a == 1) {
+                    x.x = fmaxf(x.x, 0.f), x.y = fmaxf(x.y, 0.f), x.z = fmaxf(x.z, 0.f), x.w = fmaxf(x.w, 0.f);
+                } else if (p.relu_a == 2) {  // exact (erf) GELU, torch.nn.GELU default
+                    x.x = gelu_erf(x.x), x.y = gelu_erf(x.y), x.z = gelu_erf(x.z), x.w = gelu_erf(x.w);
+                }
                 float4 hi, lo;
                 hi.x = tf32_rn(x.x), hi.y = tf32_rn(x.y), hi.z = tf32_rn(x.z), hi.w = tf32_rn(x.w);
                 lo.x = tf32_rn(x.x - hi.x), lo.y = tf32_rn(x.y - hi.y), lo.z = tf32_rn(x.z - hi.z), lo.w = tf32_rn(x.w - hi.w);
@@ -371,7 +377,7 @@ extern "C" int sdetr_split_tf32_pair(const float *w, int64_t count, float *w_hi,
 extern "C" int sdetr_gemm_3xtf32(const float *A, int64_t lda, const float *W_hi, const float *W_lo, const float *bias,
                                  float *C, int64_t ldc, int M, int N, int K, int relu_a, sdetr_stream_t stream) {
     SDETR_REQUIRE(A && W_hi && W_lo && C, SDETR_ERR_INVALID_ARG, "gemm_3xtf32: null pointer");
-    SDETR_REQUIRE(M >= 0 && N > 0 && K > 0, SDETR_ERR_INVALID_ARG, "gemm_3xtf32: bad sizes");
+    SDETR_REQUIRE(M >= 0 && N > 0 && K > 0 && relu_a >= 0 && relu_a <= 2, SDETR_ERR_INVALID_ARG, "gemm_3xtf32: bad sizes / activation");
     SDETR_REQUIRE(K % kBK == 0, SDETR_ERR_UNSUPPORTED, "gemm_3xtf32: K=%d must be a multiple of %d", K, kBK);
     SDETR_REQUIRE(lda % 4 == 0 && aligned16(A) && aligned16(W_hi) && aligned16(W_lo) && lda >= K && ldc >= N,
                   SDETR_ERR_INVALID_ARG, "gemm_3xtf32: operands must be 16-byte aligned with 16-byte row pitch");

@@ -382,7 +382,12 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict
     const int64_t r = vec / kv;
     const int c = (int)(vec - r * kv) * 4;
     float4 v = ld_stream_f4(x + r * x_stride + c);
-    if (relu) v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+    if (relu == 1) {
+        v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+    } else if (relu == 2) {  // exact (erf) GELU
+        v.x = 0.5f * v.x * (1.f + erff(v.x * 0.70710678118654752f)), v.y = 0.5f * v.y * (1.f + erff(v.y * 0.70710678118654752f));
+        v.z = 0.5f * v.z * (1.f + erff(v.z * 0.70710678118654752f)), v.w = 0.5f * v.w * (1.f + erff(v.w * 0.70710678118654752f));
+    }
     float4 hi, lo;
     hi.x = tf32_round(v.x), hi.y = tf32_round(v.y), hi.z = tf32_round(v.z), hi.w = tf32_round(v.w);
     lo.x = tf32_round(v.x - hi.x), lo.y = tf32_round(v.y - hi.y), lo.z = tf32_round(v.z - hi.z), lo.w = tf32_round(v.w - hi.w);
@@ -450,4 +455,72 @@ extern "C" int sdetr_rows_scatter(float *dst, const int64_t *index, int batch, i
     rows_scatter_kernel<<<row_blocks((int64_t)batch * k), kRowThreads, 0, (cudaStream_t)stream>>>(dst, index, batch, num_rows, k,
                                                                                                  channels, src);
     return check_launch("rows_scatter");
+}
+
+// ---- front end: (b,C,H_l,W_l) feature / position maps -> token layout ------------------------
+// One pass replaces flatten_multi_level x2, `pos + level_embed`, `feat + lpos` and the keep-mask multiply
+// (models/bricks/base_transformer.py:21-32,104; salience_transformer.py:107-113): 32x32 (channel x token) tiles are
+// transposed through shared memory so both the NCHW reads and the token-major writes are coalesced.
+namespace sdetr {
+struct FlattenArgs {
+    const float *feat[kMaxLevels], *pos[kMaxLevels];
+    int size[kMaxLevels], start[kMaxLevels], tile0[kMaxLevels + 1];  // tokens per level, token offset, first tile
+    int L;
+};
+__global__ void __launch_bounds__(256) flatten_tokens_kernel(FlattenArgs a, const float *__restrict__ level_embeds,
+                                                             const float *__restrict__ keep, int nv, int C,
+                                                             float *__restrict__ feat_tok, float *__restrict__ lpos_tok,
+                                                             float *__restrict__ x_tok) {
+    __shared__ float sf[32][33], sp[32][33];
+    int l = 0;
+#pragma unroll
+    for (int u = 1; u < kMaxLevels; ++u)
+        if (u < a.L && (int)blockIdx.x >= a.tile0[u]) l = u;
+    const int t0 = ((int)blockIdx.x - a.tile0[l]) * 32, c0 = blockIdx.y * 32, b = blockIdx.z;
+    const int hw = a.size[l];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const float *f = a.feat[l] + ((int64_t)b * C + c0) * hw, *p = a.pos[l] + ((int64_t)b * C + c0) * hw;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = ty + 8 * i, t = t0 + tx;
+        const bool ok = t < hw && c0 + c < C;
+        sf[c][tx] = ok ? __ldg(f + (int64_t)c * hw + t) : 0.f;
+        sp[c][tx] = ok ? __ldg(p + (int64_t)c * hw + t) + __ldg(level_embeds + l * C + c0 + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int t = t0 + ty + 8 * i, c = c0 + tx;
+        if (t < hw && c < C) {
+            const int64_t row = (int64_t)b * nv + a.start[l] + t;
+            const float fv = sf[tx][ty + 8 * i], pv = sp[tx][ty + 8 * i];
+            feat_tok[row * C + c] = fv;
+            lpos_tok[row * C + c] = pv;
+            x_tok[row * C + c] = (fv + pv) * __ldg(keep + row);
+        }
+    }
+}
+}  // namespace sdetr
+
+extern "C" int sdetr_flatten_tokens(const float *const *feats_host, const float *const *pos_host, const float *level_embeds,
+                                    const float *keep, const int32_t *level_size_host, int batch, int channels,
+                                    int num_levels, float *feat_tok, float *lpos_tok, float *x_tok, sdetr_stream_t stream) {
+    SDETR_REQUIRE(feats_host && pos_host && level_embeds && keep && level_size_host && feat_tok && lpos_tok && x_tok,
+                  SDETR_ERR_INVALID_ARG, "flatten_tokens: null pointer");
+    SDETR_REQUIRE(batch > 0 && channels > 0 && num_levels > 0 && num_levels <= kMaxLevels, SDETR_ERR_INVALID_ARG,
+                  "flatten_tokens: bad sizes");
+    FlattenArgs a{};
+    a.L = num_levels;
+    int nv = 0, tiles = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        SDETR_REQUIRE(feats_host[l] && pos_host[l] && level_size_host[l] > 0, SDETR_ERR_INVALID_ARG,
+                      "flatten_tokens: level %d", l);
+        a.feat[l] = feats_host[l], a.pos[l] = pos_host[l], a.size[l] = level_size_host[l], a.start[l] = nv, a.tile0[l] = tiles;
+        nv += level_size_host[l];
+        tiles += (level_size_host[l] + 31) / 32;
+    }
+    a.tile0[num_levels] = tiles;
+    dim3 grid(tiles, (channels + 31) / 32, batch);
+    flatten_tokens_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, level_embeds, keep, nv, channels, feat_tok, lpos_tok, x_tok);
+    return check_launch("flatten_tokens");
 }

@@ -17,6 +17,7 @@ These are true dense GEMMs, the only place of the path where tensor cores belong
 from __future__ import annotations
 
 import contextlib
+import weakref
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -27,7 +28,7 @@ from . import cabi
 
 MODE = "auto"
 K_CHUNK = 512  # longest reduction handed to one tensor-core GEMM (its accumulator truncates: error ~ length)
-_weight_cache: Dict[int, Tuple[tuple, Tensor]] = {}
+_weight_cache: Dict[int, tuple] = {}
 
 
 @contextlib.contextmanager
@@ -48,28 +49,39 @@ def split_weight(weight: Tensor) -> Tensor:
     """(N,K) -> cached (N,3K) per-chunk [hi|lo|hi]; rebuilt when the parameter is modified in place or replaced."""
     key = (weight.data_ptr(), weight._version, tuple(weight.shape), _chunk_of(weight.shape[1]))
     hit = _weight_cache.get(id(weight))
-    if hit is None or hit[0] != key:
+    # the weak reference guards against id()/data_ptr reuse by a NEW tensor after the cached one was freed
+    if hit is None or hit[0] != key or hit[2]() is not weight:
         with torch.no_grad():
-            hit = (key, cabi.split_tf32(weight.detach().contiguous(), layout_b=True, chunk=_chunk_of(weight.shape[1])))
+            hit = (key, cabi.split_tf32(weight.detach().contiguous(), layout_b=True, chunk=_chunk_of(weight.shape[1])),
+                   weakref.ref(weight))
         _weight_cache[id(weight)] = hit
     return hit[1]
 
 
-_pair_cache: Dict[int, Tuple[tuple, Tuple[Tensor, Tensor]]] = {}
+_pair_cache: Dict[int, tuple] = {}
 
 
 def split_weight_pair(weight: Tensor) -> Tuple[Tensor, Tensor]:
     key = (weight.data_ptr(), weight._version, tuple(weight.shape))
     hit = _pair_cache.get(id(weight))
-    if hit is None or hit[0] != key:
+    if hit is None or hit[0] != key or hit[2]() is not weight:
         with torch.no_grad():
-            hit = (key, cabi.split_tf32_pair(weight.detach()))
+            hit = (key, cabi.split_tf32_pair(weight.detach()), weakref.ref(weight))
         _pair_cache[id(weight)] = hit
     return hit[1]
 
 
-def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, relu_input: bool = False) -> Tensor:
-    """y = (relu(x) if relu_input else x) @ weight.T + bias, inference only (no autograd through the split)."""
+_ACT = {None: 0, "relu": 1, "gelu": 2}
+
+
+def _act_torch(x: Tensor, act) -> Tensor:
+    return F.relu(x) if act == 1 else F.gelu(x) if act == 2 else x
+
+
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, relu_input: bool = False,
+           input_act: Optional[str] = None) -> Tensor:
+    """y = act(x) @ weight.T + bias (act: None | "relu" | "gelu", fused into the operand load / split), inference only."""
+    relu_input = 1 if relu_input else _ACT[input_act]
     n, k = weight.shape
     own = MODE == "tcgen05" or (MODE == "auto" and (n <= 512 or k >= 1024))
     if own and k % 32 == 0 and x.stride(-1) == 1:
@@ -78,10 +90,10 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, relu_input:
             w_hi, w_lo = split_weight_pair(weight)
             return cabi.gemm_3xtf32(x, w_hi, w_lo, bias, relu_input)
     if MODE == "fp32" or k % 4 != 0:
-        return F.linear(F.relu(x) if relu_input else x, weight, bias)
+        return F.linear(_act_torch(x, relu_input), weight, bias)
     if MODE == "tf32":
         with _tf32_matmul():
-            return F.linear(F.relu(x) if relu_input else x, weight, bias)
+            return F.linear(_act_torch(x, relu_input), weight, bias)
     K = weight.shape[1]
     kc = _chunk_of(K)  # (MODE "3xtf32", or "tcgen05" falling back for an unsupported shape)
     x3 = cabi.split_tf32(x, layout_b=False, relu=relu_input, chunk=kc)

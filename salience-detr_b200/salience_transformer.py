@@ -57,14 +57,16 @@ class MaskPredictor(nn.Module):
         return self.layer2(z)
 
     def forward_fast(self, x):
-        """Inference: same math with the projections on the tensor cores (gemm.linear)."""
+        """Inference: same math; projections on the tensor cores, GELUs fused into the next GEMM's operand load,
+        LayerNorm by the fused kernel, global half written in place instead of split/expand/cat."""
         ln, fc = self.layer1[0], self.layer1[1]
-        z = F.gelu(gemm.linear(F.layer_norm(x, ln.normalized_shape, ln.weight, ln.bias, ln.eps), fc.weight, fc.bias))
+        x = x if x.is_contiguous() else x.contiguous()
+        z = F.gelu(gemm.linear(cabi.add_layernorm(x, None, ln.weight, ln.bias, ln.eps), fc.weight, fc.bias))
         half = self.h_dim // 2
-        z = torch.cat([z[..., :half], z[..., half:].mean(dim=1, keepdim=True).expand(-1, z.shape[1], -1)], dim=-1)
-        z = F.gelu(gemm.linear(z, self.layer2[0].weight, self.layer2[0].bias))
-        z = F.gelu(gemm.linear(z, self.layer2[2].weight, self.layer2[2].bias))
-        return gemm.linear(z, self.layer2[4].weight, self.layer2[4].bias)
+        z[..., half:] = z[..., half:].mean(dim=1, keepdim=True)  # global half = token mean, broadcast in place (:43-45)
+        z = gemm.linear(z, self.layer2[0].weight, self.layer2[0].bias)
+        z = gemm.linear(z, self.layer2[2].weight, self.layer2[2].bias, input_act="gelu")
+        return gemm.linear(z, self.layer2[4].weight, self.layer2[4].bias, input_act="gelu")
 
 
 class PositionEmbeddingLearned(nn.Module):
@@ -369,12 +371,14 @@ class SalienceTransformer(nn.Module):
             layer_num_query=layer_nq)
 
     # -- salience filter (:112-168) ------------------------------------------------------------------------------
-    def salience_filter(self, feat: Tensor, lpos: Tensor, plan: EncoderPlan, want_order: bool = True):
+    def salience_filter(self, feat: Tensor, lpos: Tensor, plan: EncoderPlan, want_order: bool = True,
+                        x: Optional[Tensor] = None):
         b, nv, c = feat.shape
         L = len(plan.shapes_list)
         # training keeps the scores differentiable (salience supervision): plain torch ops instead of the fused kernels
         grad = torch.is_grad_enabled() and (feat.requires_grad or any(p.requires_grad for p in self.parameters()))
-        x = (feat + lpos) * plan.keep
+        if x is None:
+            x = (feat + lpos) * plan.keep
         if grad:
             mem = self.enc_output_norm(self.enc_output(x))
         else:
@@ -412,10 +416,16 @@ class SalienceTransformer(nn.Module):
         Reference lines 106-183.  Pass a cached ``plan`` (``make_plan``) to run with no host sync."""
         if plan is None:
             plan = self.make_plan(multi_level_masks)
-        feat = flatten_levels(multi_level_feats)
-        lpos = flatten_levels([p + e.view(1, -1, 1, 1) for p, e in zip(multi_level_pos_embeds, self.level_embeds)])
         grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        raw, inds, score, fg, order = self.salience_filter(feat, lpos, plan, want_order=use_order and not grad)
+        x = None
+        if grad or multi_level_feats[0].dtype != torch.float32:
+            feat = flatten_levels(multi_level_feats)
+            lpos = flatten_levels([p + e.view(1, -1, 1, 1) for p, e in zip(multi_level_pos_embeds, self.level_embeds)])
+        else:  # one fused pass: token layout + level embedding + (feat + pos) * keep
+            feat, lpos, x = cabi.flatten_tokens([f.contiguous() for f in multi_level_feats],
+                                                [p.contiguous() for p in multi_level_pos_embeds],
+                                                self.level_embeds.detach().contiguous(), plan.keep.view(plan.keep.shape[0], -1))
+        raw, inds, score, fg, order = self.salience_filter(feat, lpos, plan, want_order=use_order and not grad, x=x)
         layer_inds = [inds[:, :n] for n in plan.layer_num_query]
         orders = cabi.order_prefixes(order, plan.layer_num_query) if order is not None else None
         memory = self.encoder(

@@ -253,6 +253,22 @@ def test_gather_scatter_background(pkg, C):
     assert torch.equal(tok_d.cpu(), want)
 
 
+def test_flatten_tokens(pkg):
+    g = torch.Generator().manual_seed(6)
+    b, C = 2, 64
+    shapes = [(13, 21), (7, 11), (4, 6), (2, 3)]
+    feats = [torch.randn(b, C, h, w, generator=g) for h, w in shapes]
+    pos = [torch.randn(b, C, h, w, generator=g) for h, w in shapes]
+    emb = torch.randn(4, C, generator=g)
+    nv = sum(h * w for h, w in shapes)
+    keep = (torch.rand(b, nv, generator=g) > 0.2).float()
+    want_f = orc.flatten_levels(feats)
+    want_p = orc.flatten_levels([p + e.view(1, -1, 1, 1) for p, e in zip(pos, emb)])
+    f, p_, x = pkg.cabi.flatten_tokens([t.to(DEV) for t in feats], [t.to(DEV) for t in pos], emb.to(DEV), keep.to(DEV))
+    assert torch.equal(f.cpu(), want_f) and torch.equal(p_.cpu(), want_p)
+    assert torch.equal(x.cpu(), (want_f + want_p) * keep[..., None])
+
+
 def test_rows_gather_scatter(pkg):
     g = torch.Generator().manual_seed(4)
     b, n, k, C = 2, 500, 300, 256
