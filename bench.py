@@ -127,6 +127,17 @@ def time_msda_kernels(pkg, runner, reps=20):
     return med, byts
 
 
+def use_host_cores():
+    """The CPU arm uses all physical host cores (torchrun pins OMP_NUM_THREADS=1 by default)."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(max(1, n // 2))  # SMT siblings do not help the GEMM / grid_sample kernels
+    return torch.get_num_threads()
+
+
 def cpu_port_step(state_dict, feats, masks, pos, cfg):
     from oracle import oracle as orc  # CPU baseline leg only
     with torch.no_grad():
@@ -137,6 +148,7 @@ def cpu_port_step(state_dict, feats, masks, pos, cfg):
 def cpu_baseline(pkg, model, budget_s=20.0):
     """The oracle port of the reference's PyTorch CPU path on this host's cores, bounded sample."""
     from salience_detr_b200.synthetic import make_inputs
+    use_host_cores()
     feats, masks, pos = make_inputs(WORKLOAD, seed=0)
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     m = model.encoder.layers[0]
@@ -160,6 +172,7 @@ def run_reference(args, rank, world):
         return
     import salience_detr_b200 as pkg
     from salience_detr_b200.synthetic import build_model, make_inputs
+    use_host_cores()
     model = build_model()
     feats, masks, pos = make_inputs(WORKLOAD, seed=0)
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
