@@ -176,9 +176,9 @@ int sdetr_score_modulate(const float *mem, int64_t mem_batch_stride, const float
 int sdetr_zero_masked_rows(float *rows, int64_t row_stride, int row_floats, const uint8_t *mask,
                            int64_t num_rows, sdetr_stream_t stream);
 
-/* mc_score = max_c(class_logits) * fg (:366).  logits (rows, num_classes) -> out (rows). */
-int sdetr_class_max_times_fg(const float *logits, const float *fg, int64_t rows, int num_classes, float *out,
-                             sdetr_stream_t stream);
+/* mc_score = max_c(class_logits) * fg (:366).  logits (rows, num_classes) with row pitch row_pitch -> out (rows). */
+int sdetr_class_max_times_fg(const float *logits, int64_t row_pitch, const float *fg, int64_t rows, int num_classes,
+                             float *out, sdetr_stream_t stream);
 
 /* y = LayerNorm(x + r) * gamma + beta (:390-391, :349-350); rows of `channels` (<= 1024, multiple of 4).
  * May run in place (y == x). */
@@ -218,6 +218,13 @@ int sdetr_split_tf32(const float *x, int64_t x_row_stride, int64_t rows, int K, 
  * Replaces the cuBLAS path for: value_proj / sampling_offsets|attention_weights / output_proj
  * (models/bricks/ms_deform_attn.py:316,322-328,375), FFN (salience_transformer.py:347-351), class head (:462),
  * MaskPredictor (:16-47), enc_output (base_transformer.py:111). */
+/* Same contract with the RAW weight W (N,K): the kernel splits both operands itself (32 KB instead of 48 KB of TMA
+ * traffic per k-block), keeps the split activation in tensor memory, and runs two CTAs per SM. */
+int sdetr_gemm_3xtf32_raw(const float *A, int64_t lda, const float *W, const float *bias, float *C, int64_t ldc, int M,
+                          int N, int K, int act, sdetr_stream_t stream);
+/* kernel variant of sdetr_gemm_3xtf32: 0 = "SS" (both operands from shared memory), 1 = "TS" (the split activation
+ * is written to tensor memory by the converter warps and the MMAs read A from TMEM) */
+int sdetr_gemm_set_variant(int variant);
 /* debugging aid: when set, CTA (0,0) of every sdetr_gemm_3xtf32 launch records clock64() per pipeline event */
 int sdetr_gemm_set_trace(long long *device_buffer);
 int sdetr_split_tf32_pair(const float *w, int64_t count, float *w_hi, float *w_lo, sdetr_stream_t stream);

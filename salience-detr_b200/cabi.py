@@ -42,10 +42,12 @@ SIGNATURES = {
     "sdetr_background_embed": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp] + [_i] * 4 + [_vp, _vp]),
     "sdetr_score_modulate": (_i, [_vp, _i64, _vp, _i64, _vp] + [_i] * 7 + [_vp, _vp]),
     "sdetr_zero_masked_rows": (_i, [_vp, _i64, _i, _vp, _i64, _vp]),
-    "sdetr_class_max_times_fg": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
+    "sdetr_class_max_times_fg": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp]),
     "sdetr_add_layernorm": (_i, [_vp, _vp, _vp, _vp, _f, _i64, _i, _vp, _vp]),
     "sdetr_split_tf32": (_i, [_vp, _i64, _i64, _i, _i, _i, _i, _vp, _vp]),
+    "sdetr_gemm_3xtf32_raw": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
     "sdetr_gemm_set_trace": (_i, [_vp]),
+    "sdetr_gemm_set_variant": (_i, [_i]),
     "sdetr_split_tf32_pair": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "sdetr_gemm_3xtf32": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
     "sdetr_flatten_tokens": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
@@ -303,9 +305,15 @@ def zero_masked_rows_(buf, row_stride: int, row_floats: int, mask_u8, num_rows: 
 
 
 def class_max_times_fg(logits, fg):
+    """logits (..., num_classes) with unit last stride and a uniform row pitch (a padded GEMM output is fine)."""
     rows = fg.numel()
     out = torch.empty_like(fg)
-    rc = lib().sdetr_class_max_times_fg(_req(logits, "logits", torch.float32), _req(fg, "fg", torch.float32), rows,
+    if not (logits.is_cuda and logits.dtype == torch.float32 and logits.stride(-1) == 1):
+        raise RuntimeError("logits must be CUDA float32 with unit last stride")
+    pitch = logits.stride(-2)
+    if logits.dim() == 3 and logits.stride(0) != logits.shape[1] * pitch:
+        logits, pitch = logits.contiguous(), logits.shape[-1]
+    rc = lib().sdetr_class_max_times_fg(logits.data_ptr(), pitch, _req(fg, "fg", torch.float32), rows,
                                         logits.shape[-1], out.data_ptr(), _stream())
     _check(rc, "sdetr_class_max_times_fg")
     return out
@@ -400,3 +408,21 @@ def flatten_tokens(feats, pos, level_embeds, keep):
                                     _host_i32(sizes), b, c, L, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), _stream())
     _check(rc, "sdetr_flatten_tokens")
     return out
+
+
+def gemm_3xtf32_raw(x, w, bias=None, act=0):
+    """y = act(x) @ w.T + bias, both operands split inside the kernel (w: raw fp32 (N,K) contiguous)."""
+    K = x.shape[-1]
+    N = w.shape[0]
+    if not (x.is_cuda and x.dtype == torch.float32 and x.stride(-1) == 1):
+        raise RuntimeError("gemm_3xtf32_raw needs a CUDA float32 input with unit last stride")
+    x2 = x if x.dim() == 2 else x.reshape(-1, K)
+    M = x2.shape[0]
+    ldc = (N + 3) // 4 * 4  # 16-byte row pitch lets the epilogue leave through TMA bulk stores (e.g. N = 91 -> 92)
+    y = torch.empty(M, ldc, device=x.device, dtype=torch.float32)
+    rc = lib().sdetr_gemm_3xtf32_raw(x2.data_ptr(), x2.stride(0) if M > 1 else K, _req(w, "w", torch.float32),
+                                     _req(bias, "bias", torch.float32) if bias is not None else None, y.data_ptr(), ldc, M, N, K,
+                                     int(act), _stream())
+    _check(rc, "sdetr_gemm_3xtf32_raw")
+    y = y if ldc == N else y[:, :N]
+    return y.reshape(*x.shape[:-1], N) if ldc == N else y.unflatten(0, x.shape[:-1])

@@ -110,6 +110,26 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand from tensor memory (TS form): no shared-memory read for A
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_c),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -319,6 +339,352 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
 }
 
+
+// ---- variant "TS": the split activation lives in TENSOR MEMORY ---------------------------------------------------------
+// The SS kernel above is bound by shared-memory bandwidth: per k-block the MMAs re-read 96 KB of operands, TMA
+// writes 48 KB and the converters move another 48 KB through the same 128 B/clk port.  Here the converters read the
+// landed A tile once (16 KB, swizzle-aware so a quarter-warp stays conflict-free) and write A_hi / A_lo with
+// tcgen05.st into TMEM slots (lane = row, column = k); the MMAs take A from TMEM ([a] operand) and only W from
+// shared memory: 112 KB instead of 192 KB of shared-memory traffic per k-block.  TMEM map (512 columns): accumulator
+// [0,128), A slot i in [128 + 64 i, 128 + 64 (i+1)): 32 columns A_hi then 32 columns A_lo, one slot per TMA stage.
+constexpr int kTsStages = 4;
+constexpr int kTsStageBytes = 3 * kTileBytes;  // A raw, W_hi, W_lo
+constexpr int kTsRingBytes = kTsStages * kTsStageBytes;
+constexpr int kTsSmem = kTsRingBytes + 1024 + 256;
+constexpr int kTsTmemCols = 512;
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_3xtf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_whi,
+                      const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_c,
+                      const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kTsRingBytes);
+    uint64_t *tma_full = bars, *conv_full = bars + kTsStages, *empty = bars + 2 * kTsStages, *acc_full = bars + 3 * kTsStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * kBN, m0 = blockIdx.y * kBM;
+    const int nk = p.K / kBK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTsStages; ++s) {
+            mbar_init(tma_full + s, 1);
+            mbar_init(conv_full + s, 32 * kConvWarps);
+            mbar_init(empty + s, 2);
+        }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTsTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t rank = cluster_ctarank();
+    if (threadIdx.x == 0) SDETR_TRACE(5, 2);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nk; ++kb) {
+                const int s = kb % kTsStages;
+                const uint32_t ph = (kb / kTsStages) & 1;
+                mbar_wait(empty + s, ph ^ 1);  // both CTAs' MMAs have released ring stage s (and TMEM slot s)
+                SDETR_TRACE(0, kb);
+                uint8_t *st = smem + s * kTsStageBytes;
+                mbar_expect_tx(tma_full + s, 3 * kTileBytes);
+                tma_load_2d(&map_a, tma_full + s, st, kb * kBK, m0);
+                if (rank == 0) tma_load_2d_mc(&map_whi, tma_full + s, st + kTileBytes, kb * kBK, n0, 0b11);
+                else tma_load_2d_mc(&map_wlo, tma_full + s, st + 2 * kTileBytes, kb * kBK, n0, 0b11);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nk; ++kb) {
+                const int s = kb % kTsStages;
+                const uint32_t ph = (kb / kTsStages) & 1;
+                mbar_wait(tma_full + s, ph);
+                SDETR_TRACE(1, kb);
+                mbar_wait(conv_full + s, ph);
+                SDETR_TRACE(2, kb);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t base = smem_u32(smem + s * kTsStageBytes);
+                const uint32_t a_hi = tmem_base + 128u + 64u * (uint32_t)s, a_lo = a_hi + 32u;
+#pragma unroll
+                for (int k = 0; k < kBK / 8; ++k) {
+                    const uint64_t w_hi = umma_desc(base + kTileBytes) + 2 * k, w_lo = umma_desc(base + 2 * kTileBytes) + 2 * k;
+                    umma_tf32_ts(tmem_base, a_hi + 8u * k, w_hi, kIdesc, (kb | k) != 0);
+                    umma_tf32_ts(tmem_base, a_hi + 8u * k, w_lo, kIdesc, 1);
+                    umma_tf32_ts(tmem_base, a_lo + 8u * k, w_hi, kIdesc, 1);
+                }
+                umma_commit_mc(empty + s, 0b11);
+            }
+            umma_commit(acc_full);
+        }
+    } else if (warp >= 4) {
+        const int t = threadIdx.x - 128;
+        const int q = warp & 3;             // TMEM lane quadrant of this warp
+        const int half = (warp - 4) >> 2;   // which 16 of the 32 k-columns (converter) / which column blocks (epilogue)
+        const int r_in = q * 32 + lane;     // tile row handled by this thread
+        for (int kb = 0; kb < nk; ++kb) {
+            const int s = kb % kTsStages;
+            const uint32_t ph = (kb / kTsStages) & 1;
+            mbar_wait(tma_full + s, ph);    // implies TMEM slot s is free: the refill waited for the MMAs of kb - stages
+            if (t == 0) SDETR_TRACE(3, kb);
+            const uint8_t *arow = smem + s * kTsStageBytes + r_in * 128;
+            float hi[16], lo[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {   // logical 16-byte chunk 4*half + c sits at physical chunk ^ (row & 7)
+                float4 x = *reinterpret_cast<const float4 *>(arow + ((((half << 2) + c) ^ (r_in & 7)) << 4));
+                if (p.relu_a == 1) {
+                    x.x = fmaxf(x.x, 0.f), x.y = fmaxf(x.y, 0.f), x.z = fmaxf(x.z, 0.f), x.w = fmaxf(x.w, 0.f);
+                } else if (p.relu_a == 2) {
+                    x.x = gelu_erf(x.x), x.y = gelu_erf(x.y), x.z = gelu_erf(x.z), x.w = gelu_erf(x.w);
+                }
+                hi[4 * c] = tf32_rn(x.x), hi[4 * c + 1] = tf32_rn(x.y), hi[4 * c + 2] = tf32_rn(x.z), hi[4 * c + 3] = tf32_rn(x.w);
+                lo[4 * c] = tf32_rn(x.x - hi[4 * c]), lo[4 * c + 1] = tf32_rn(x.y - hi[4 * c + 1]);
+                lo[4 * c + 2] = tf32_rn(x.z - hi[4 * c + 2]), lo[4 * c + 3] = tf32_rn(x.w - hi[4 * c + 3]);
+            }
+            const uint32_t slot = tmem_base + ((uint32_t)(q * 32) << 16) + 128u + 64u * (uint32_t)s + 16u * (uint32_t)half;
+            tmem_st16(slot, hi);
+            tmem_st16(slot + 32u, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(conv_full + s);
+            if (t == 0) SDETR_TRACE(4, kb);
+        }
+        mbar_wait(acc_full, 0);
+        if (t == 0) SDETR_TRACE(5, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = m0 + r_in;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+            const int c = half * 2 + cc;
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+            const int col0 = n0 + c * 32;
+            if (p.use_tma_store) {
+                uint8_t *box = smem + c * kTileBytes;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                           __uint_as_float(r[j + 3]));
+                    if (p.bias && col0 + j + 3 < p.N) {
+                        const float4 bv = ldg_f4(p.bias + col0 + j);
+                        o.x += bv.x, o.y += bv.y, o.z += bv.z, o.w += bv.w;
+                    } else if (p.bias) {
+                        if (col0 + j < p.N) o.x += __ldg(p.bias + col0 + j);
+                        if (col0 + j + 1 < p.N) o.y += __ldg(p.bias + col0 + j + 1);
+                        if (col0 + j + 2 < p.N) o.z += __ldg(p.bias + col0 + j + 2);
+                    }
+                    *reinterpret_cast<float4 *>(box + r_in * 128 + (((j >> 2) ^ (r_in & 7)) << 4)) = o;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                named_bar_sync(1 + half, 128);
+                if ((warp & 3) == 0 && lane == 0 && col0 < p.N) {
+                    tma_store_2d(&map_c, box, col0, m0);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else if (row < p.M) {
+                float *crow = p.C + (int64_t)row * p.ldc;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col0 + j < p.N) crow[col0 + j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
+            }
+        }
+        if (p.use_tma_store && (warp & 3) == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    if (threadIdx.x == 128) SDETR_TRACE(5, 1);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTsTmemCols));
+    }
+}
+
+
+// ---- variant "TS2": TS + weight split in the kernel + two CTAs per SM -----------------------------------------------------
+// Traces of the variants above show ~44 B/clk of TMA traffic INTO each SM as the wall (48 KB per k-block: A + W_hi +
+// W_lo), and at K = 256 the un-overlapped prologue/epilogue costs as much as the 8-k-block main loop.  This variant
+// loads the weight tile RAW (16 KB) and lets the converter warps split it as well (W_hi in place, W_lo next to it),
+// so a k-block is 32 KB of TMA traffic; and it runs with a 2-stage ring / 256 TMEM columns so that TWO CTAs share an
+// SM: one CTA's epilogue and pipeline fill overlap the other's main loop.
+constexpr int kT2Stages = 2;
+constexpr int kT2StageBytes = 3 * kTileBytes;  // A raw, W raw -> W_hi, W_lo
+constexpr int kT2RingBytes = kT2Stages * kT2StageBytes;
+constexpr int kT2Smem = kT2RingBytes + 1024 + 256;
+constexpr int kT2TmemCols = 256;               // accumulator [0,128) + 2 A slots of 64 columns
+
+__global__ void __launch_bounds__(kGemmThreads, 2)
+gemm_3xtf32_ts2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                       const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kT2RingBytes);
+    uint64_t *tma_full = bars, *conv_full = bars + kT2Stages, *empty = bars + 2 * kT2Stages, *acc_full = bars + 3 * kT2Stages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * kBN, m0 = blockIdx.y * kBM;
+    const int nk = p.K / kBK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kT2Stages; ++s) {
+            mbar_init(tma_full + s, 1);
+            mbar_init(conv_full + s, 32 * kConvWarps);
+            mbar_init(empty + s, 1);
+        }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kT2TmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) SDETR_TRACE(5, 2);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nk; ++kb) {
+                const int s = kb % kT2Stages;
+                const uint32_t ph = (kb / kT2Stages) & 1;
+                mbar_wait(empty + s, ph ^ 1);
+                SDETR_TRACE(0, kb);
+                uint8_t *st = smem + s * kT2StageBytes;
+                mbar_expect_tx(tma_full + s, 2 * kTileBytes);
+                tma_load_2d(&map_a, tma_full + s, st, kb * kBK, m0);
+                tma_load_2d(&map_w, tma_full + s, st + kTileBytes, kb * kBK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nk; ++kb) {
+                const int s = kb % kT2Stages;
+                const uint32_t ph = (kb / kT2Stages) & 1;
+                mbar_wait(conv_full + s, ph);  // converters waited for the TMA themselves
+                SDETR_TRACE(2, kb);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t base = smem_u32(smem + s * kT2StageBytes);
+                const uint32_t a_hi = tmem_base + 128u + 64u * (uint32_t)s, a_lo = a_hi + 32u;
+#pragma unroll
+                for (int k = 0; k < kBK / 8; ++k) {
+                    const uint64_t w_hi = umma_desc(base + kTileBytes) + 2 * k, w_lo = umma_desc(base + 2 * kTileBytes) + 2 * k;
+                    umma_tf32_ts(tmem_base, a_hi + 8u * k, w_hi, kIdesc, (kb | k) != 0);
+                    umma_tf32_ts(tmem_base, a_hi + 8u * k, w_lo, kIdesc, 1);
+                    umma_tf32_ts(tmem_base, a_lo + 8u * k, w_hi, kIdesc, 1);
+                }
+                umma_commit(empty + s);
+            }
+            umma_commit(acc_full);
+        }
+    } else if (warp >= 4) {
+        const int t = threadIdx.x - 128;
+        const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const int r_in = q * 32 + lane;
+        for (int kb = 0; kb < nk; ++kb) {
+            const int s = kb % kT2Stages;
+            const uint32_t ph = (kb / kT2Stages) & 1;
+            mbar_wait(tma_full + s, ph);
+            if (t == 0) SDETR_TRACE(3, kb);
+            uint8_t *stage = smem + s * kT2StageBytes;
+            // weight tile: element-wise split, W_hi in place, W_lo into the third buffer of the stage
+            float4 *w = reinterpret_cast<float4 *>(stage + kTileBytes), *wlo = reinterpret_cast<float4 *>(stage + 2 * kTileBytes);
+            float4 wv[4];
+#pragma unroll
+            for (int it = 0; it < 4; ++it) wv[it] = w[it * (32 * kConvWarps) + t];
+            // activation tile: this thread's row, 16 of the 32 k-columns
+            const uint8_t *arow = stage + r_in * 128;
+            float hi[16], lo[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float4 x = *reinterpret_cast<const float4 *>(arow + ((((half << 2) + c) ^ (r_in & 7)) << 4));
+                if (p.relu_a == 1) {
+                    x.x = fmaxf(x.x, 0.f), x.y = fmaxf(x.y, 0.f), x.z = fmaxf(x.z, 0.f), x.w = fmaxf(x.w, 0.f);
+                } else if (p.relu_a == 2) {
+                    x.x = gelu_erf(x.x), x.y = gelu_erf(x.y), x.z = gelu_erf(x.z), x.w = gelu_erf(x.w);
+                }
+                hi[4 * c] = tf32_rn(x.x), hi[4 * c + 1] = tf32_rn(x.y), hi[4 * c + 2] = tf32_rn(x.z), hi[4 * c + 3] = tf32_rn(x.w);
+                lo[4 * c] = tf32_rn(x.x - hi[4 * c]), lo[4 * c + 1] = tf32_rn(x.y - hi[4 * c + 1]);
+                lo[4 * c + 2] = tf32_rn(x.z - hi[4 * c + 2]), lo[4 * c + 3] = tf32_rn(x.w - hi[4 * c + 3]);
+            }
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const float4 x = wv[it];
+                float4 h, l;
+                h.x = tf32_rn(x.x), h.y = tf32_rn(x.y), h.z = tf32_rn(x.z), h.w = tf32_rn(x.w);
+                l.x = tf32_rn(x.x - h.x), l.y = tf32_rn(x.y - h.y), l.z = tf32_rn(x.z - h.z), l.w = tf32_rn(x.w - h.w);
+                w[it * (32 * kConvWarps) + t] = h;
+                wlo[it * (32 * kConvWarps) + t] = l;
+            }
+            const uint32_t slot = tmem_base + ((uint32_t)(q * 32) << 16) + 128u + 64u * (uint32_t)s + 16u * (uint32_t)half;
+            tmem_st16(slot, hi);
+            tmem_st16(slot + 32u, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(conv_full + s);
+            if (t == 0) SDETR_TRACE(4, kb);
+        }
+        mbar_wait(acc_full, 0);
+        if (t == 0) SDETR_TRACE(5, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = m0 + r_in;
+        // the ring (2 x 48 KB) is free now: boxes 0..3 (16 KB each) live in its first 64 KB
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+            const int c = half * 2 + cc;
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+            const int col0 = n0 + c * 32;
+            if (p.use_tma_store) {
+                uint8_t *box = smem + c * kTileBytes;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                           __uint_as_float(r[j + 3]));
+                    if (p.bias && col0 + j + 3 < p.N) {
+                        const float4 bv = ldg_f4(p.bias + col0 + j);
+                        o.x += bv.x, o.y += bv.y, o.z += bv.z, o.w += bv.w;
+                    } else if (p.bias) {
+                        if (col0 + j < p.N) o.x += __ldg(p.bias + col0 + j);
+                        if (col0 + j + 1 < p.N) o.y += __ldg(p.bias + col0 + j + 1);
+                        if (col0 + j + 2 < p.N) o.z += __ldg(p.bias + col0 + j + 2);
+                    }
+                    *reinterpret_cast<float4 *>(box + r_in * 128 + (((j >> 2) ^ (r_in & 7)) << 4)) = o;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                named_bar_sync(1 + half, 128);
+                if ((warp & 3) == 0 && lane == 0 && col0 < p.N) {
+                    tma_store_2d(&map_c, box, col0, m0);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else if (row < p.M) {
+                float *crow = p.C + (int64_t)row * p.ldc;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col0 + j < p.N) crow[col0 + j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
+            }
+        }
+        if (p.use_tma_store && (warp & 3) == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    if (threadIdx.x == 128) SDETR_TRACE(5, 1);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kT2TmemCols));
+    }
+}
+
 // weight split: (N,K) -> W_hi, W_lo (both (N,K), TF32-representable)
 __global__ void split_pair_kernel(const float *__restrict__ w, int64_t n, float *__restrict__ hi, float *__restrict__ lo) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -346,6 +712,7 @@ static EncodeTiledFn get_encode() {
 
 // 2-D fp32 tensor (rows, cols) with row stride ld (floats); box = (kBK cols, box_rows rows), 128-byte swizzle
 static long long *g_gemm_dbg = nullptr;
+static int g_gemm_variant = 0;  // 0 = SS (operands from shared memory), 1 = TS (split activation in tensor memory)
 static bool make_map(CUtensorMap *m, const float *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
@@ -361,6 +728,37 @@ static bool make_map(CUtensorMap *m, const float *base, int64_t rows, int64_t co
 }  // namespace sdetr
 
 using namespace sdetr;
+
+extern "C" int sdetr_gemm_3xtf32_raw(const float *A, int64_t lda, const float *W, const float *bias, float *C, int64_t ldc,
+                                     int M, int N, int K, int act, sdetr_stream_t stream) {
+    SDETR_REQUIRE(A && W && C, SDETR_ERR_INVALID_ARG, "gemm_3xtf32_raw: null pointer");
+    SDETR_REQUIRE(M >= 0 && N > 0 && K > 0 && act >= 0 && act <= 2, SDETR_ERR_INVALID_ARG, "gemm_3xtf32_raw: bad sizes / activation");
+    SDETR_REQUIRE(K % kBK == 0, SDETR_ERR_UNSUPPORTED, "gemm_3xtf32_raw: K=%d must be a multiple of %d", K, kBK);
+    SDETR_REQUIRE(lda % 4 == 0 && aligned16(A) && aligned16(W) && lda >= K && ldc >= N, SDETR_ERR_INVALID_ARG,
+                  "gemm_3xtf32_raw: operands must be 16-byte aligned with 16-byte row pitch");
+    if (M == 0) return SDETR_OK;
+    CUtensorMap ma, mw, mc;
+    SDETR_REQUIRE(make_map(&ma, A, M, K, lda, kBM) && make_map(&mw, W, N, K, K, kBN), SDETR_ERR_CUDA,
+                  "gemm_3xtf32_raw: cuTensorMapEncodeTiled failed");
+    const int use_tma_store = (ldc % 4 == 0) && aligned16(C) && make_map(&mc, C, M, N, ldc, kBM);
+    if (!use_tma_store) mc = ma;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_ts2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2Smem);
+        SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "gemm_3xtf32_raw: smem attribute: %s", cudaGetErrorString(e));
+        attr = true;
+    }
+    GemmParams p{bias, C, ldc, M, N, K, act, use_tma_store, g_gemm_dbg};
+    dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM);
+    gemm_3xtf32_ts2_kernel<<<grid, kGemmThreads, kT2Smem, (cudaStream_t)stream>>>(ma, mw, mc, p);
+    return check_launch("gemm_3xtf32_raw");
+}
+
+extern "C" int sdetr_gemm_set_variant(int variant) {
+    SDETR_REQUIRE(variant == 0 || variant == 1, SDETR_ERR_INVALID_ARG, "gemm_set_variant: 0 (SS) or 1 (TS)");
+    g_gemm_variant = variant;
+    return SDETR_OK;
+}
 
 extern "C" int sdetr_gemm_set_trace(long long *device_buffer /* 6*128 int64, or NULL */) {
     g_gemm_dbg = device_buffer;
@@ -392,6 +790,8 @@ extern "C" int sdetr_gemm_3xtf32(const float *A, int64_t lda, const float *W_hi,
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
         SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "gemm_3xtf32: smem attribute: %s", cudaGetErrorString(e));
+        e = cudaFuncSetAttribute(gemm_3xtf32_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmem);
+        SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "gemm_3xtf32: smem attribute: %s", cudaGetErrorString(e));
         attr = true;
     }
     GemmParams p{bias, C, ldc, M, N, K, relu_a, use_tma_store, g_gemm_dbg};
@@ -399,13 +799,14 @@ extern "C" int sdetr_gemm_3xtf32(const float *A, int64_t lda, const float *W_hi,
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((N + kBN - 1) / kBN, (mtiles + 1) & ~1);  // clusters of 2 along M (an odd tail tile is all out-of-bounds)
     cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = kGemmSmem;
+    cfg.dynamicSmemBytes = g_gemm_variant ? kTsSmem : kGemmSmem;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 1, at[0].val.clusterDim.y = 2, at[0].val.clusterDim.z = 1;
     cfg.attrs = at, cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_3xtf32_kernel, ma, mh, ml, mc, p);
+    cudaError_t le = g_gemm_variant ? cudaLaunchKernelEx(&cfg, gemm_3xtf32_ts_kernel, ma, mh, ml, mc, p)
+                                    : cudaLaunchKernelEx(&cfg, gemm_3xtf32_kernel, ma, mh, ml, mc, p);
     SDETR_REQUIRE(le == cudaSuccess, SDETR_ERR_CUDA, "gemm_3xtf32: launch: %s", cudaGetErrorString(le));
     return check_launch("gemm_3xtf32");
 }

@@ -187,14 +187,14 @@ __global__ void __launch_bounds__(kRowThreads) zero_masked_rows_kernel(float *__
 }
 
 // ---- mc_score = max_c(logits) * fg (:366) ---------------------------------------------------------------
-__global__ void __launch_bounds__(kRowThreads) class_max_kernel(const float *__restrict__ logits,
+__global__ void __launch_bounds__(kRowThreads) class_max_kernel(const float *__restrict__ logits, int64_t pitch,
                                                                 const float *__restrict__ fg, int64_t rows, int nc,
                                                                 float *__restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
     if (row >= rows) return;
     float m = -INFINITY;
-    for (int c = lane; c < nc; c += 32) m = fmaxf(m, __ldg(logits + row * nc + c));
+    for (int c = lane; c < nc; c += 32) m = fmaxf(m, __ldg(logits + row * pitch + c));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) out[row] = m * __ldg(fg + row);
@@ -338,12 +338,13 @@ extern "C" int sdetr_zero_masked_rows(float *rows, int64_t row_stride, int row_f
     return check_launch("zero_masked_rows");
 }
 
-extern "C" int sdetr_class_max_times_fg(const float *logits, const float *fg, int64_t rows, int num_classes, float *out,
-                                        sdetr_stream_t stream) {
+extern "C" int sdetr_class_max_times_fg(const float *logits, int64_t row_pitch, const float *fg, int64_t rows,
+                                        int num_classes, float *out, sdetr_stream_t stream) {
     SDETR_REQUIRE(logits && fg && out, SDETR_ERR_INVALID_ARG, "class_max_times_fg: null pointer");
-    SDETR_REQUIRE(rows >= 0 && num_classes > 0, SDETR_ERR_INVALID_ARG, "class_max_times_fg: bad sizes");
+    SDETR_REQUIRE(rows >= 0 && num_classes > 0 && row_pitch >= num_classes, SDETR_ERR_INVALID_ARG,
+                  "class_max_times_fg: bad sizes");
     if (rows == 0) return SDETR_OK;
-    class_max_kernel<<<row_blocks(rows), kRowThreads, 0, (cudaStream_t)stream>>>(logits, fg, rows, num_classes, out);
+    class_max_kernel<<<row_blocks(rows), kRowThreads, 0, (cudaStream_t)stream>>>(logits, row_pitch, fg, rows, num_classes, out);
     return check_launch("class_max_times_fg");
 }
 

@@ -87,8 +87,11 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, relu_input:
     if own and k % 32 == 0 and x.stride(-1) == 1:
         x2 = x if x.dim() == 2 else x.reshape(-1, x.shape[-1])
         if x2.stride(0) % 4 == 0 or x2.shape[0] == 1:
-            w_hi, w_lo = split_weight_pair(weight)
-            return cabi.gemm_3xtf32(x, w_hi, w_lo, bias, relu_input)
+            if k >= 1024:   # long reductions: 4-stage ring, weight pre-split once (variant "SS")
+                w_hi, w_lo = split_weight_pair(weight)
+                return cabi.gemm_3xtf32(x, w_hi, w_lo, bias, relu_input)
+            # short reductions: both operands split in the kernel, A in TMEM, two CTAs per SM (variant "TS2")
+            return cabi.gemm_3xtf32_raw(x, weight if weight.is_contiguous() else weight.contiguous(), bias, relu_input)
     if MODE == "fp32" or k % 4 != 0:
         return F.linear(_act_torch(x, relu_input), weight, bias)
     if MODE == "tf32":

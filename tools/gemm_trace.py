@@ -6,6 +6,10 @@ import salience_detr_b200 as pkg
 dev = "cuda:0"
 lib = pkg.cabi.lib()
 M, K, N = (int(a) for a in (sys.argv[1:4] if len(sys.argv) > 3 else (16896, 256, 256)))
+variant = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+lib.sdetr_gemm_set_variant(min(variant, 1))
+if variant == 2:  # raw-weight kernel (TS2)
+    pkg.cabi.gemm_3xtf32 = lambda x, hi, lo: pkg.cabi.gemm_3xtf32_raw(x, w)
 x = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) / 16
 hi, lo = pkg.cabi.split_tf32_pair(w)
 for _ in range(3): pkg.cabi.gemm_3xtf32(x, hi, lo)
@@ -24,4 +28,6 @@ s.record()
 for _ in range(20): pkg.cabi.gemm_3xtf32(x, hi, lo)
 e.record(); torch.cuda.synchronize()
 ms = s.elapsed_time(e) / 20
+ref = (x.double() @ w.double().t())
+print("max abs err vs fp64", (pkg.cabi.gemm_3xtf32(x, hi, lo).double() - ref).abs().max().item())
 print(f"{ms*1000:.1f} us/launch, {2*3*M*N*K/ms/1e9:.1f} TF32-TFLOP/s ({2*M*N*K/ms/1e9:.1f} fp32-equivalent)")
