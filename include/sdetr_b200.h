@@ -193,11 +193,20 @@ int sdetr_flatten_tokens(const float *const *feats_host, const float *const *pos
                          const float *keep, const int32_t *level_size_host, int batch, int channels, int num_levels,
                          float *feat_tok, float *lpos_tok, float *x_tok, sdetr_stream_t stream);
 
+/* Dense self-attention core of the 300-token pre-attention (salience_transformer.py:372-376; the attention inside
+ * nn.MultiheadAttention): out = softmax(Q K^T / sqrt(d)) V per (image, head).  qk (b,n,2,heads,d): projected queries
+ * then keys; v (b,n,heads,d); out (b,n,heads*d).  head_dim must be 32; n limited by shared memory (~750). */
+int sdetr_attention_small(const float *qk, const float *v, float *out, int batch, int n, int heads, int head_dim,
+                          sdetr_stream_t stream);
+
 /* Row gather / scatter by per-image index (the top-k tokens of the pre-attention, salience_transformer.py:368-379):
  * out[b,j,:] = src[b,index[b,j],:]   /   dst[b,index[b,j],:] = src[b,j,:]  (indices unique per image).
  * src/dst (b,num_rows,C), index (b,k) int64. */
 int sdetr_rows_gather(const float *src, const int64_t *index, int batch, int num_rows, int k, int channels, float *out,
                       sdetr_stream_t stream);
+/* t[b,j,:] = src[b,index[b,j],:],  x[b,j,:] = t[b,j,:] + pos[b,index[b,j],:]  (:368-371 in one pass) */
+int sdetr_rows_gather_add(const float *src, const float *pos, const int64_t *index, int batch, int num_rows, int k,
+                          int channels, float *t, float *x, sdetr_stream_t stream);
 int sdetr_rows_scatter(float *dst, const int64_t *index, int batch, int num_rows, int k, int channels, const float *src,
                        sdetr_stream_t stream);
 

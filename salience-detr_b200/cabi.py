@@ -51,7 +51,9 @@ SIGNATURES = {
     "sdetr_split_tf32_pair": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "sdetr_gemm_3xtf32": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
     "sdetr_flatten_tokens": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "sdetr_attention_small": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sdetr_rows_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "sdetr_rows_gather_add": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "sdetr_rows_scatter": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
 }
 
@@ -426,3 +428,25 @@ def gemm_3xtf32_raw(x, w, bias=None, act=0):
     _check(rc, "sdetr_gemm_3xtf32_raw")
     y = y if ldc == N else y[:, :N]
     return y.reshape(*x.shape[:-1], N) if ldc == N else y.unflatten(0, x.shape[:-1])
+
+
+def rows_gather_add(src, pos, index):
+    """t = src[b, index], x = t + pos[b, index]  (the pre-attention's two gathers and the `with_pos_embed` add)."""
+    b, n, c = src.shape
+    k = index.shape[1]
+    t = torch.empty(b, k, c, device=src.device, dtype=torch.float32)
+    x = torch.empty_like(t)
+    rc = lib().sdetr_rows_gather_add(_req(src, "src", torch.float32), _req(pos, "pos", torch.float32),
+                                     _req(index, "index", torch.int64), b, n, k, c, t.data_ptr(), x.data_ptr(), _stream())
+    _check(rc, "sdetr_rows_gather_add")
+    return t, x
+
+
+def attention_small(qk, v):
+    """qk (b,n,2,h,d) [queries | keys], v (b,n,h,d) -> (b,n,h*d) = softmax(QK^T/sqrt(d)) V per head."""
+    b, n, _, h, d = qk.shape
+    out = torch.empty(b, n, h * d, device=qk.device, dtype=torch.float32)
+    rc = lib().sdetr_attention_small(_req(qk, "qk", torch.float32), _req(v, "v", torch.float32), out.data_ptr(), b, n, h, d,
+                                     _stream())
+    _check(rc, "sdetr_attention_small")
+    return out

@@ -525,3 +525,119 @@ extern "C" int sdetr_flatten_tokens(const float *const *feats_host, const float 
     flatten_tokens_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, level_embeds, keep, nv, channels, feat_tok, lpos_tok, x_tok);
     return check_launch("flatten_tokens");
 }
+
+// ---- pre-attention gather: t = q[top], x = t + pos[top] (salience_transformer.py:368-371) -----------------------------
+namespace sdetr {
+__global__ void __launch_bounds__(kRowThreads) rows_gather_add_kernel(const float *__restrict__ src, const float *__restrict__ pos,
+                                                                      const int64_t *__restrict__ idx, int batch, int n, int k,
+                                                                      int C, float *__restrict__ t, float *__restrict__ x) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+    if (row >= (int64_t)batch * k) return;
+    const int b = (int)(row / k);
+    const int64_t srow = ((int64_t)b * n + __ldg(idx + row)) * C;
+    for (int c = lane * 4; c < C; c += 128) {
+        const float4 a = ld_stream_f4(src + srow + c), p = ld_stream_f4(pos + srow + c);
+        st_stream_f4(t + row * C + c, a);
+        st_stream_f4(x + row * C + c, make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w));
+    }
+}
+}  // namespace sdetr
+
+extern "C" int sdetr_rows_gather_add(const float *src, const float *pos, const int64_t *index, int batch, int num_rows, int k,
+                                     int channels, float *t, float *x, sdetr_stream_t stream) {
+    SDETR_REQUIRE(src && pos && index && t && x, SDETR_ERR_INVALID_ARG, "rows_gather_add: null pointer");
+    SDETR_REQUIRE(batch > 0 && num_rows > 0 && k >= 0 && channels % 4 == 0 && aligned16(src) && aligned16(pos) && aligned16(t) &&
+                      aligned16(x),
+                  SDETR_ERR_INVALID_ARG, "rows_gather_add: bad sizes / alignment");
+    if (k == 0) return SDETR_OK;
+    rows_gather_add_kernel<<<row_blocks((int64_t)batch * k), kRowThreads, 0, (cudaStream_t)stream>>>(src, pos, index, batch,
+                                                                                                    num_rows, k, channels, t, x);
+    return check_launch("rows_gather_add");
+}
+
+// ---- small dense attention of the pre-attention (salience_transformer.py:372-376, nn.MultiheadAttention core) --------
+// softmax(Q K^T / sqrt(d)) V for a few hundred tokens, head_dim 32.  One CTA = one (image, head) and a tile of queries;
+// K and V of the head live in shared memory (K rows padded to 33 floats: lanes read different rows conflict-free).
+// A warp owns one query at a time: lanes split the keys for the scores, warp-shuffle max/sum for the softmax, the
+// probabilities go through shared memory, then lanes = output channels accumulate p_j * V[j][lane] (coalesced rows).
+namespace sdetr {
+constexpr int kAttnWarps = 8;
+__global__ void __launch_bounds__(kAttnWarps * 32) attn_small_kernel(const float *__restrict__ qk, const float *__restrict__ v,
+                                                                     float *__restrict__ out, int n, int heads, float scale,
+                                                                     int q_per_cta) {
+    extern __shared__ float sm_attn[];
+    float *ks = sm_attn;                 // n x 33
+    float *vs = ks + (size_t)n * 33;     // n x 32
+    float *ps = vs + (size_t)n * 32;     // kAttnWarps x n
+    const int h = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t qk_row = 2LL * heads * 32, v_row = (int64_t)heads * 32;
+    const float *qbase = qk + (int64_t)b * n * qk_row + (int64_t)h * 32;
+    const float *kbase = qbase + (int64_t)heads * 32;
+    const float *vbase = v + (int64_t)b * n * v_row + (int64_t)h * 32;
+    for (int i = threadIdx.x; i < n * 8; i += blockDim.x) {  // 128-bit loads of the head's K / V rows
+        const int j = i >> 3, c = (i & 7) * 4;
+        const float4 kv = ldg_f4(kbase + j * qk_row + c), vv = ldg_f4(vbase + j * v_row + c);
+        ks[j * 33 + c] = kv.x, ks[j * 33 + c + 1] = kv.y, ks[j * 33 + c + 2] = kv.z, ks[j * 33 + c + 3] = kv.w;
+        *reinterpret_cast<float4 *>(vs + j * 32 + c) = vv;
+    }
+    __syncthreads();
+    float *p = ps + (size_t)warp * n;
+    const int q0 = blockIdx.z * q_per_cta, q1 = min(n, q0 + q_per_cta);
+    for (int qi = q0 + warp; qi < q1; qi += kAttnWarps) {
+        float q[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) q[c] = __ldg(qbase + qi * qk_row + c) * scale;  // same address across the warp: broadcast
+        float mx = -INFINITY;
+        for (int j = lane; j < n; j += 32) {
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) s = fmaf(q[c], ks[j * 33 + c], s);
+            p[j] = s;
+            mx = fmaxf(mx, s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+        for (int j = lane; j < n; j += 32) {
+            const float e = __expf(p[j] - mx);
+            p[j] = e;
+            sum += e;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        __syncwarp();
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four independent chains hide the LDS -> FMA latency
+        int j = 0;
+        for (; j + 3 < n; j += 4) {
+            a0 = fmaf(p[j], vs[j * 32 + lane], a0);
+            a1 = fmaf(p[j + 1], vs[(j + 1) * 32 + lane], a1);
+            a2 = fmaf(p[j + 2], vs[(j + 2) * 32 + lane], a2);
+            a3 = fmaf(p[j + 3], vs[(j + 3) * 32 + lane], a3);
+        }
+        for (; j < n; ++j) a0 = fmaf(p[j], vs[j * 32 + lane], a0);
+        out[((int64_t)b * n + qi) * v_row + h * 32 + lane] = ((a0 + a1) + (a2 + a3)) / sum;
+        __syncwarp();
+    }
+}
+}  // namespace sdetr
+
+extern "C" int sdetr_attention_small(const float *qk, const float *v, float *out, int batch, int n, int heads, int head_dim,
+                                     sdetr_stream_t stream) {
+    SDETR_REQUIRE(qk && v && out, SDETR_ERR_INVALID_ARG, "attention_small: null pointer");
+    SDETR_REQUIRE(batch > 0 && n > 0 && heads > 0, SDETR_ERR_INVALID_ARG, "attention_small: bad sizes");
+    SDETR_REQUIRE(head_dim == 32, SDETR_ERR_UNSUPPORTED, "attention_small: head_dim %d (only 32)", head_dim);
+    const size_t smem = ((size_t)n * 65 + (size_t)kAttnWarps * n) * sizeof(float);
+    SDETR_REQUIRE(smem <= 200 * 1024, SDETR_ERR_UNSUPPORTED, "attention_small: %d tokens do not fit in shared memory", n);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "attention_small: smem attribute: %s", cudaGetErrorString(e));
+        attr = true;
+    }
+    const int q_per_cta = 16;  // two queries per warp: 300 tokens -> 19 query tiles x heads x batch = 304 CTAs at (h=8, b=2)
+    dim3 grid(heads, batch, (n + q_per_cta - 1) / q_per_cta);
+    attn_small_kernel<<<grid, kAttnWarps * 32, smem, (cudaStream_t)stream>>>(qk, v, out, n, heads, 1.f / sqrtf((float)head_dim),
+                                                                             q_per_cta);
+    return check_launch("attention_small");
+}

@@ -269,6 +269,17 @@ def test_flatten_tokens(pkg):
     assert torch.equal(x.cpu(), (want_f + want_p) * keep[..., None])
 
 
+def test_attention_small(pkg):
+    g = torch.Generator().manual_seed(8)
+    for b, n, h in [(2, 300, 8), (1, 37, 2), (3, 700, 4)]:
+        qk = torch.randn(b, n, 2, h, 32, generator=g)
+        v = torch.randn(b, n, h, 32, generator=g)
+        want = torch.nn.functional.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2),
+                                                                v.transpose(1, 2)).transpose(1, 2).reshape(b, n, h * 32)
+        got = pkg.cabi.attention_small(qk.to(DEV), v.to(DEV))
+        assert (got.cpu() - want).abs().max() < 2e-5
+
+
 def test_rows_gather_scatter(pkg):
     g = torch.Generator().manual_seed(4)
     b, n, k, C = 2, 500, 300, 256
@@ -276,6 +287,10 @@ def test_rows_gather_scatter(pkg):
     idx = torch.stack([torch.randperm(n, generator=g)[:k] for _ in range(b)])
     got = pkg.cabi.rows_gather(src.to(DEV), idx.to(DEV))
     assert torch.equal(got.cpu(), src.gather(1, idx[..., None].expand(-1, -1, C)))
+    pos = torch.randn(b, n, C, generator=g)
+    t, x = pkg.cabi.rows_gather_add(src.to(DEV), pos.to(DEV), idx.to(DEV))
+    want_t = src.gather(1, idx[..., None].expand(-1, -1, C))
+    assert torch.equal(t.cpu(), want_t) and torch.equal(x.cpu(), want_t + pos.gather(1, idx[..., None].expand(-1, -1, C)))
     new = torch.randn(b, k, C, generator=g)
     dst = src.to(DEV)
     pkg.cabi.rows_scatter_(dst, idx.to(DEV), new.to(DEV))
