@@ -231,8 +231,10 @@ int sdetr_split_tf32(const float *x, int64_t x_row_stride, int64_t rows, int K, 
  * traffic per k-block), keeps the split activation in tensor memory, and runs two CTAs per SM. */
 int sdetr_gemm_3xtf32_raw(const float *A, int64_t lda, const float *W, const float *bias, float *C, int64_t ldc, int M,
                           int N, int K, int act, sdetr_stream_t stream);
-/* kernel variant of sdetr_gemm_3xtf32: 0 = "SS" (both operands from shared memory), 1 = "TS" (the split activation
- * is written to tensor memory by the converter warps and the MMAs read A from TMEM) */
+/* kernel variants: sdetr_gemm_3xtf32: 0 = "SS" (both operands from shared memory), 1 = "TS" (the split activation is
+ * written to tensor memory by the converter warps and the MMAs read A from TMEM); sdetr_gemm_3xtf32_raw: 2 = "TS2"
+ * (one tile per CTA, two CTAs per SM), 3 = "P" (default: persistent tile loop, double-buffered TMEM accumulator,
+ * dedicated epilogue warps) */
 int sdetr_gemm_set_variant(int variant);
 /* debugging aid: when set, CTA (0,0) of every sdetr_gemm_3xtf32 launch records clock64() per pipeline event */
 int sdetr_gemm_set_trace(long long *device_buffer);

@@ -685,6 +685,209 @@ gemm_3xtf32_ts2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     }
 }
 
+
+// ---- variant "P": persistent tiles, double-buffered accumulator, dedicated epilogue warps ------------------------------
+// One CTA per SM walks a strided list of 128x128 output tiles.  Roles (512 threads): warp 0 TMA producer, warp 1 MMA
+// issuer, warp 2 TMEM allocator, warps 4..11 converters (A -> TMEM slot, raw W -> W_hi/W_lo in place), warps 12..15
+// epilogue.  The accumulator is double-buffered in tensor memory (2 x 128 columns) so the epilogue of tile i
+// (tcgen05.ld -> +bias -> swizzled box -> TMA store) overlaps the main loop of tile i+1, and the 4-stage ring keeps
+// streaming across tile boundaries -- no per-tile pipeline fill, TMEM allocation or barrier initialisation.
+// TMEM map (512 columns): accumulators [0,128) and [128,256); A slot s at [256 + 64 s, 256 + 64 (s+1)).
+constexpr int kPStages = 4;
+constexpr int kPStageBytes = 3 * kTileBytes;
+constexpr int kPRingBytes = kPStages * kPStageBytes;            // 192 KB
+constexpr int kPBoxBytes = 2 * kTileBytes;                      // two 128x32 fp32 staging boxes for the TMA stores
+constexpr int kPSmem = kPRingBytes + kPBoxBytes + 1024 + 256;
+constexpr int kPThreads = 512;
+
+__global__ void __launch_bounds__(kPThreads, 1)
+gemm_3xtf32_p_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                     const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *boxes = smem + kPRingBytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kPRingBytes + kPBoxBytes);
+    uint64_t *tma_full = bars, *conv_full = bars + kPStages, *empty = bars + 2 * kPStages;
+    uint64_t *acc_full = bars + 3 * kPStages, *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nk = p.K / kBK;
+    const int n_tiles = (p.N + kBN - 1) / kBN, m_tiles = (p.M + kBM - 1) / kBM;
+    const int tiles = n_tiles * m_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kPStages; ++s) {
+            mbar_init(tma_full + s, 1);
+            mbar_init(conv_full + s, 32 * kConvWarps);
+            mbar_init(empty + s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(acc_full + b, 1);
+            mbar_init(acc_empty + b, 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * kBN;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int s = it % kPStages;
+                    mbar_wait(empty + s, ((it / kPStages) & 1) ^ 1);
+                    uint8_t *st = smem + s * kPStageBytes;
+                    mbar_expect_tx(tma_full + s, 2 * kTileBytes);
+                    tma_load_2d(&map_a, tma_full + s, st, kb * kBK, m0);
+                    tma_load_2d(&map_w, tma_full + s, st + kTileBytes, kb * kBK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t it = 0, tc = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tc) {
+                const uint32_t buf = tc & 1;
+                mbar_wait(acc_empty + buf, ((tc >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc = tmem_base + buf * 128u;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int s = it % kPStages;
+                    mbar_wait(conv_full + s, (it / kPStages) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t base = smem_u32(smem + s * kPStageBytes);
+                    const uint32_t a_hi = tmem_base + 256u + 64u * (uint32_t)s, a_lo = a_hi + 32u;
+#pragma unroll
+                    for (int k = 0; k < kBK / 8; ++k) {
+                        const uint64_t w_hi = umma_desc(base + kTileBytes) + 2 * k, w_lo = umma_desc(base + 2 * kTileBytes) + 2 * k;
+                        umma_tf32_ts(acc, a_hi + 8u * k, w_hi, kIdesc, (kb | k) != 0);
+                        umma_tf32_ts(acc, a_hi + 8u * k, w_lo, kIdesc, 1);
+                        umma_tf32_ts(acc, a_lo + 8u * k, w_hi, kIdesc, 1);
+                    }
+                    umma_commit(empty + s);
+                }
+                umma_commit(acc_full + buf);
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ===== converters =====
+        const int t = threadIdx.x - 128;
+        const int q = warp & 3, half = (warp - 4) >> 2, r_in = q * 32 + lane;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < nk; ++kb, ++it) {
+                const int s = it % kPStages;
+                mbar_wait(tma_full + s, (it / kPStages) & 1);
+                uint8_t *stage = smem + s * kPStageBytes;
+                float4 *w = reinterpret_cast<float4 *>(stage + kTileBytes), *wlo = reinterpret_cast<float4 *>(stage + 2 * kTileBytes);
+                float4 wv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) wv[i] = w[i * (32 * kConvWarps) + t];
+                const uint8_t *arow = stage + r_in * 128;
+                float hi[16], lo[16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float4 x = *reinterpret_cast<const float4 *>(arow + ((((half << 2) + c) ^ (r_in & 7)) << 4));
+                    if (p.relu_a == 1) {
+                        x.x = fmaxf(x.x, 0.f), x.y = fmaxf(x.y, 0.f), x.z = fmaxf(x.z, 0.f), x.w = fmaxf(x.w, 0.f);
+                    } else if (p.relu_a == 2) {
+                        x.x = gelu_erf(x.x), x.y = gelu_erf(x.y), x.z = gelu_erf(x.z), x.w = gelu_erf(x.w);
+                    }
+                    hi[4 * c] = tf32_rn(x.x), hi[4 * c + 1] = tf32_rn(x.y), hi[4 * c + 2] = tf32_rn(x.z), hi[4 * c + 3] = tf32_rn(x.w);
+                    lo[4 * c] = tf32_rn(x.x - hi[4 * c]), lo[4 * c + 1] = tf32_rn(x.y - hi[4 * c + 1]);
+                    lo[4 * c + 2] = tf32_rn(x.z - hi[4 * c + 2]), lo[4 * c + 3] = tf32_rn(x.w - hi[4 * c + 3]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 x = wv[i];
+                    float4 h, l;
+                    h.x = tf32_rn(x.x), h.y = tf32_rn(x.y), h.z = tf32_rn(x.z), h.w = tf32_rn(x.w);
+                    l.x = tf32_rn(x.x - h.x), l.y = tf32_rn(x.y - h.y), l.z = tf32_rn(x.z - h.z), l.w = tf32_rn(x.w - h.w);
+                    w[i * (32 * kConvWarps) + t] = h;
+                    wlo[i * (32 * kConvWarps) + t] = l;
+                }
+                const uint32_t slot = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + 64u * (uint32_t)s + 16u * (uint32_t)half;
+                tmem_st16(slot, hi);
+                tmem_st16(slot + 32u, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(conv_full + s);
+            }
+        }
+    } else if (warp >= 12) {
+        // ===== epilogue =====
+        const int q = warp & 3, r_in = q * 32 + lane;
+        const bool elected = threadIdx.x == 12 * 32;
+        uint32_t tc = 0, box_it = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tc) {
+            const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * kBN;
+            const uint32_t buf = tc & 1;
+            mbar_wait(acc_full + buf, (tc >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = m0 + r_in;
+#pragma unroll 1
+            for (int c = 0; c < kBN / 32; ++c, ++box_it) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128u + (uint32_t)(c * 32), r);
+                if (c == kBN / 32 - 1) {  // last read of this accumulator: hand it back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(acc_empty + buf);
+                }
+                const int col0 = n0 + c * 32;
+                if (col0 >= p.N) continue;  // uniform across the CTA
+                if (p.use_tma_store) {
+                    uint8_t *box = boxes + (box_it & 1) * kTileBytes;
+                    if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // box free again
+                    named_bar_sync(1, 128);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                               __uint_as_float(r[j + 3]));
+                        if (p.bias && col0 + j + 3 < p.N) {
+                            const float4 bv = ldg_f4(p.bias + col0 + j);
+                            o.x += bv.x, o.y += bv.y, o.z += bv.z, o.w += bv.w;
+                        } else if (p.bias) {
+                            if (col0 + j < p.N) o.x += __ldg(p.bias + col0 + j);
+                            if (col0 + j + 1 < p.N) o.y += __ldg(p.bias + col0 + j + 1);
+                            if (col0 + j + 2 < p.N) o.z += __ldg(p.bias + col0 + j + 2);
+                        }
+                        *reinterpret_cast<float4 *>(box + r_in * 128 + (((j >> 2) ^ (r_in & 7)) << 4)) = o;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    named_bar_sync(1, 128);
+                    if (elected) {
+                        tma_store_2d(&map_c, box, col0, m0);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                } else if (row < p.M) {
+                    float *crow = p.C + (int64_t)row * p.ldc;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < p.N) crow[col0 + j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
+                }
+            }
+        }
+        if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
+
 // weight split: (N,K) -> W_hi, W_lo (both (N,K), TF32-representable)
 __global__ void split_pair_kernel(const float *__restrict__ w, int64_t n, float *__restrict__ hi, float *__restrict__ lo) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -712,6 +915,7 @@ static EncodeTiledFn get_encode() {
 
 // 2-D fp32 tensor (rows, cols) with row stride ld (floats); box = (kBK cols, box_rows rows), 128-byte swizzle
 static long long *g_gemm_dbg = nullptr;
+static int g_raw_persistent = 1;  // sdetr_gemm_3xtf32_raw: 1 = persistent kernel "P", 0 = "TS2"
 static int g_gemm_variant = 0;  // 0 = SS (operands from shared memory), 1 = TS (split activation in tensor memory)
 static bool make_map(CUtensorMap *m, const float *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
     EncodeTiledFn enc = get_encode();
@@ -743,20 +947,32 @@ extern "C" int sdetr_gemm_3xtf32_raw(const float *A, int64_t lda, const float *W
     const int use_tma_store = (ldc % 4 == 0) && aligned16(C) && make_map(&mc, C, M, N, ldc, kBM);
     if (!use_tma_store) mc = ma;
     static bool attr = false;
+    static int sms = 148;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_ts2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2Smem);
         SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "gemm_3xtf32_raw: smem attribute: %s", cudaGetErrorString(e));
+        e = cudaFuncSetAttribute(gemm_3xtf32_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem);
+        SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "gemm_3xtf32_raw: smem attribute: %s", cudaGetErrorString(e));
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         attr = true;
     }
     GemmParams p{bias, C, ldc, M, N, K, act, use_tma_store, g_gemm_dbg};
+    if (g_raw_persistent) {
+        const int tiles = ((N + kBN - 1) / kBN) * ((M + kBM - 1) / kBM);
+        gemm_3xtf32_p_kernel<<<tiles < sms ? tiles : sms, kPThreads, kPSmem, (cudaStream_t)stream>>>(ma, mw, mc, p);
+        return check_launch("gemm_3xtf32_raw");
+    }
     dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM);
     gemm_3xtf32_ts2_kernel<<<grid, kGemmThreads, kT2Smem, (cudaStream_t)stream>>>(ma, mw, mc, p);
     return check_launch("gemm_3xtf32_raw");
 }
 
 extern "C" int sdetr_gemm_set_variant(int variant) {
-    SDETR_REQUIRE(variant == 0 || variant == 1, SDETR_ERR_INVALID_ARG, "gemm_set_variant: 0 (SS) or 1 (TS)");
-    g_gemm_variant = variant;
+    // 0 / 1: sdetr_gemm_3xtf32 uses "SS" / "TS";   2 / 3: sdetr_gemm_3xtf32_raw uses "TS2" / persistent "P"
+    SDETR_REQUIRE(variant >= 0 && variant <= 3, SDETR_ERR_INVALID_ARG, "gemm_set_variant: 0..3");
+    if (variant <= 1) g_gemm_variant = variant;
+    else g_raw_persistent = variant - 2;
     return SDETR_OK;
 }
 

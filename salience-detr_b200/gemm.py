@@ -27,6 +27,7 @@ from torch.nn import functional as F
 from . import cabi
 
 MODE = "auto"
+LONG_K_PRESPLIT = False  # K >= 1024: True = "SS" kernel with the pre-split weight, False = persistent raw-weight kernel "P" (measured equal or faster)
 K_CHUNK = 512  # longest reduction handed to one tensor-core GEMM (its accumulator truncates: error ~ length)
 _weight_cache: Dict[int, tuple] = {}
 
@@ -87,7 +88,7 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, relu_input:
     if own and k % 32 == 0 and x.stride(-1) == 1:
         x2 = x if x.dim() == 2 else x.reshape(-1, x.shape[-1])
         if x2.stride(0) % 4 == 0 or x2.shape[0] == 1:
-            if k >= 1024:   # long reductions: 4-stage ring, weight pre-split once (variant "SS")
+            if k >= 1024 and LONG_K_PRESPLIT:   # long reductions: 4-stage ring, weight pre-split once (variant "SS")
                 w_hi, w_lo = split_weight_pair(weight)
                 return cabi.gemm_3xtf32(x, w_hi, w_lo, bias, relu_input)
             # short reductions: both operands split in the kernel, A in TMEM, two CTAs per SM (variant "TS2")

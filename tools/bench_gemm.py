@@ -20,14 +20,15 @@ def timeit(fn, reps=10):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b) * 1000)
     return statistics.median(ts)
-print(f"{'gemm':14s} {'M':>6s} {'K':>5s} {'N':>5s} | tcgen05 us | cublas3x us | fp32 us | tcgen05 TF32-TF/s")
+print(f"{'gemm':14s} {'M':>6s} {'K':>5s} {'N':>5s} | tcgen05 us (K>=1024: SS presplit) | tcgen05 us (persistent raw for all) | cublas3x us | fp32 us | best tcgen05 TF32-TF/s")
 tot = {"tcgen05": 0, "3xtf32": 0, "fp32": 0}
 for name, M, K, N, relu in shapes:
     x = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) / K ** 0.5; b = torch.randn(N, device=dev)
     r = {}
-    for mode in ("tcgen05", "3xtf32", "fp32"):
-        pkg.gemm.MODE = mode
+    for mode in ("tcgen05", "tcgen05-P", "3xtf32", "fp32"):
+        pkg.gemm.MODE = mode.split("-")[0]
+        pkg.gemm.LONG_K_PRESPLIT = mode != "tcgen05-P"
         r[mode] = timeit(lambda: pkg.gemm.linear(x, w, b, relu_input=bool(relu)))
-        tot[mode] += r[mode]
-    print(f"{name:14s} {M:6d} {K:5d} {N:5d} | {r['tcgen05']:9.1f} | {r['3xtf32']:10.1f} | {r['fp32']:7.1f} | {6*M*N*K/r['tcgen05']/1e6:7.1f}")
+        tot[mode] = tot.get(mode, 0) + r[mode]
+    print(f"{name:14s} {M:6d} {K:5d} {N:5d} | {r['tcgen05']:9.1f} | {r['tcgen05-P']:9.1f} | {r['3xtf32']:10.1f} | {r['fp32']:7.1f} | {6*M*N*K/min(r['tcgen05'], r['tcgen05-P'])/1e6:7.1f}")
 print("sum", {k: round(v, 1) for k, v in tot.items()})

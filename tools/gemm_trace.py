@@ -7,8 +7,8 @@ dev = "cuda:0"
 lib = pkg.cabi.lib()
 M, K, N = (int(a) for a in (sys.argv[1:4] if len(sys.argv) > 3 else (16896, 256, 256)))
 variant = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-lib.sdetr_gemm_set_variant(min(variant, 1))
-if variant == 2:  # raw-weight kernel (TS2)
+lib.sdetr_gemm_set_variant(variant)
+if variant >= 2:  # raw-weight kernels (TS2 / persistent)
     pkg.cabi.gemm_3xtf32 = lambda x, hi, lo: pkg.cabi.gemm_3xtf32_raw(x, w)
 x = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) / 16
 hi, lo = pkg.cabi.split_tf32_pair(w)
