@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attn_small_kernel(const float
                                                                      int q_per_cta) {
     extern __shared__ float sm_attn[];
     float *ks = sm_attn;                 // n x 33
-    float *vs = ks + (size_t)n * 33;     // n x 32
+    float *vs = ks + (((size_t)n * 33 + 3) & ~(size_t)3);  // n x 32, 16-byte aligned
     float *ps = vs + (size_t)n * 32;     // kAttnWarps x n
     const int h = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t qk_row = 2LL * heads * 32, v_row = (int64_t)heads * 32;
@@ -627,7 +627,7 @@ extern "C" int sdetr_attention_small(const float *qk, const float *v, float *out
     SDETR_REQUIRE(qk && v && out, SDETR_ERR_INVALID_ARG, "attention_small: null pointer");
     SDETR_REQUIRE(batch > 0 && n > 0 && heads > 0, SDETR_ERR_INVALID_ARG, "attention_small: bad sizes");
     SDETR_REQUIRE(head_dim == 32, SDETR_ERR_UNSUPPORTED, "attention_small: head_dim %d (only 32)", head_dim);
-    const size_t smem = ((size_t)n * 65 + (size_t)kAttnWarps * n) * sizeof(float);
+    const size_t smem = ((((size_t)n * 33 + 3) & ~(size_t)3) + (size_t)n * 32 + (size_t)kAttnWarps * n) * sizeof(float);
     SDETR_REQUIRE(smem <= 200 * 1024, SDETR_ERR_UNSUPPORTED, "attention_small: %d tokens do not fit in shared memory", n);
     static bool attr = false;
     if (!attr) {

@@ -26,7 +26,8 @@ class HostPipeline:
         dev = self.lanes[0].dev
         self.h2d = torch.cuda.Stream(device=dev)
         self.d2h = torch.cuda.Stream(device=dev)
-        self.done = [None] * depth     # event: D2H of the lane's previous batch finished
+        self.done = [None] * depth       # event: D2H of the lane's previous batch finished (its output buffers are free)
+        self.computed = [None] * depth   # event: forward of the lane's previous batch finished (its input buffers are free)
         self.host_out = [torch.empty(self.lanes[0].memory.shape, dtype=torch.float32, pin_memory=True)
                          for _ in range(depth)]
         self.h2d_bytes = self.d2h_bytes = 0
@@ -34,25 +35,27 @@ class HostPipeline:
     def run(self, batches, on_output=None):
         """batches: iterable of (feats_host, pos_host) pinned-memory level lists.  Returns the number processed;
         ``on_output(i, host_memory)`` (optional) is called once batch i's output is in host memory."""
-        pending = []
         n = 0
         for i, (feats_h, pos_h) in enumerate(batches):
             k = i % len(self.lanes)
             lane = self.lanes[k]
-            if self.done[k] is not None:
-                self.h2d.wait_event(self.done[k])          # lane buffers are free again
-                if on_output is not None:
-                    self.done[k].synchronize()
-                    on_output(i - len(self.lanes), self.host_out[k])
+            if self.computed[k] is not None:
+                self.h2d.wait_event(self.computed[k])      # the lane's INPUT buffers are free once its forward is done
+            if self.done[k] is not None and on_output is not None:
+                self.done[k].synchronize()
+                on_output(i - len(self.lanes), self.host_out[k])
             with torch.cuda.stream(self.h2d):
                 for dst, src in zip(lane.feats + lane.pos, list(feats_h) + list(pos_h)):
                     dst.copy_(src, non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(self.h2d)
             lane.stream.wait_event(ready)
+            if self.done[k] is not None:
+                lane.stream.wait_event(self.done[k])       # the lane's OUTPUT buffer was copied out
             mem = lane.step()
             computed = torch.cuda.Event()
             computed.record(lane.stream)
+            self.computed[k] = computed
             self.d2h.wait_event(computed)
             with torch.cuda.stream(self.d2h):
                 self.host_out[k].copy_(mem, non_blocking=True)

@@ -32,6 +32,7 @@ from torch.nn import functional as F
 from . import cabi, gemm
 from .ms_deform_attn import MultiScaleDeformableAttention
 
+OVERLAP_VALUE_PROJ = True  # run the all-layer value projection on a side stream, concurrently with the salience filter
 SMALL_ATTENTION = False   # hand-written 300-token attention kernel instead of SDPA (measured slower: 35 vs 30 us)
 MHA_GEMM_TENSOR_CORE = False  # pre-attention projections (M = 600 rows): cuBLAS SGEMM measured faster than the tensor-core kernels
 TILE_CELL_PX = 64   # edge (image pixels) of the spatial cells that define the MSDA processing order
@@ -241,9 +242,19 @@ class SalienceTransformerEncoder(nn.Module):
             self._vproj_key = key
         return self._vproj
 
+    def project_values(self, tokens: Tensor, mask_u8: Tensor) -> Tensor:
+        """(b,Nv,C) value tokens -> (b,Nv,layers*C): every layer's value_proj in ONE GEMM (the value tokens never
+        change across layers, reference :452), padded rows zeroed (ms_deform_attn.py:318-319)."""
+        b, nv, _ = tokens.shape
+        wv, bv = self._value_projection()
+        vbuf = gemm.linear(tokens, wv, bv)
+        wide = vbuf.shape[-1]
+        cabi.zero_masked_rows_(vbuf, wide, wide, mask_u8, b * nv)
+        return vbuf
+
     def forward(self, query, spatial_shapes, level_start_index, valid_ratios, query_pos=None,
                 query_key_padding_mask=None, foreground_score=None, focus_token_nums=None, foreground_inds=None,
-                multi_level_masks=None, query_orders=None):
+                multi_level_masks=None, query_orders=None, value_buffer=None):
         """Reference signature (:434-447) + optional ``query_orders`` (per-layer int32 processing orders).
 
         query/query_pos (b,Nv,C); foreground_inds: list of (b,Nq_j) int64 (prefix views of one selected_inds);
@@ -258,10 +269,8 @@ class SalienceTransformerEncoder(nn.Module):
         mask_u8 = query_key_padding_mask.to(torch.uint8).contiguous()
         focus = focus_token_nums.to(torch.int32).contiguous()
         # one GEMM for the value projections of all layers; zero the padded rows once
-        wv, bv = self._value_projection()
-        vbuf = gemm.linear(query, wv, bv)  # (b,Nv,layers*C)
+        vbuf = value_buffer if value_buffer is not None else self.project_values(query, mask_u8)
         wide = vbuf.shape[-1]
-        cabi.zero_masked_rows_(vbuf, wide, wide, mask_u8, b * nv)
         out = query.clone()  # `value` stays the original tokens (:452); `out` is updated in place
         pos = query_pos.contiguous()
         fg = foreground_score.contiguous()
@@ -348,6 +357,13 @@ class SalienceTransformer(nn.Module):
         nn.init.constant_(self.enc_output.bias, 0.0)
         nn.init.constant_(self.encoder_class_head.bias, -math.log((1 - 0.01) / 0.01))
         self.alpha.data.uniform_(-0.3, 0.3)
+
+    def _side_stream(self, device):
+        streams = self.__dict__.setdefault("_side_streams", {})
+        key = str(device)
+        if key not in streams:
+            streams[key] = torch.cuda.Stream(device=device)
+        return streams[key]
 
     # -- plan ------------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -443,14 +459,26 @@ class SalienceTransformer(nn.Module):
             feat, lpos, x = cabi.flatten_tokens([f.contiguous() for f in multi_level_feats],
                                                 [p.contiguous() for p in multi_level_pos_embeds],
                                                 self.level_embeds.detach().contiguous(), plan.keep.view(plan.keep.shape[0], -1))
+        vbuf = None
+        if OVERLAP_VALUE_PROJ and not grad and feat.is_cuda:
+            # fork: the (large) value projection only needs the tokens, so it runs beside the salience filter's
+            # many small kernels; works eagerly and as a parallel branch of a captured CUDA graph
+            cur = torch.cuda.current_stream(feat.device)
+            side = self._side_stream(feat.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                vbuf = self.encoder.project_values(feat, plan.mask_u8)
         raw, inds, score, fg, order = self.salience_filter(feat, lpos, plan, want_order=use_order and not grad, x=x)
+        if vbuf is not None:
+            cur.wait_stream(side)  # join
+            vbuf.record_stream(cur)
         layer_inds = [inds[:, :n] for n in plan.layer_num_query]
         orders = cabi.order_prefixes(order, plan.layer_num_query) if order is not None else None
         memory = self.encoder(
             query=feat, query_pos=lpos, query_key_padding_mask=plan.mask_flat, spatial_shapes=plan.spatial_shapes,
             level_start_index=plan.level_start_index, valid_ratios=plan.valid_ratios, foreground_score=fg,
             focus_token_nums=plan.focus_token_nums, foreground_inds=layer_inds, multi_level_masks=multi_level_masks,
-            query_orders=orders)
+            query_orders=orders, value_buffer=vbuf)
         aux = dict(raw_score=raw, selected_inds=inds, selected_score=score, foreground_score=fg, plan=plan)
         return memory, aux
 

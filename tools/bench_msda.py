@@ -70,12 +70,12 @@ print("cell  order sched minb chunk | per-layer us | total us | GB/s")
 for cell in (64,):
     calls, plan = capture(cell)
     byts = alg_bytes(plan)
-    for use_order, schedule, minb in itertools.product((True,), (0, 1), (4, 41)):
+    for use_order, schedule, minb in itertools.product((True,), (1,), (41, 31)):
         if not use_order and cell != 64:
             continue
-        for chunk in ((64,) if schedule == 0 else (32, 64)):
-            cabi.set_option("msda_smem_broadcast", 1 if minb == 41 else 0)  # 41 = minb 4 + shared-memory broadcast
-            cabi.set_option("msda_min_blocks", 4 if minb == 41 else minb)
+        for chunk in ((64,) if schedule == 0 else (64, 128, 256)):
+            cabi.set_option("msda_smem_broadcast", 1 if minb in (41, 31) else 0)  # 41 / 31 = minb 4 / 3 + shared-memory broadcast
+            cabi.set_option("msda_min_blocks", 4 if minb in (41, 31) else minb)
             cabi.set_option("msda_chunk", chunk)
             t = time_calls(calls, schedule, use_order)
             # correctness of every variant against the first one
