@@ -15,7 +15,7 @@ feats, masks, pos = make_inputs("resnet50_800_1333_bs2", seed=0, device=dev)
 res = {}
 with torch.no_grad():
     plan = model.make_plan(masks)
-    for mode in ("fp32", "3xtf32", "tf32"):
+    for mode in ("fp32", "auto", "tcgen05", "3xtf32", "tf32"):
         pkg.gemm.MODE = mode
         mem, aux = model.forward_encoder(feats, masks, pos, plan=plan)
         res[mode] = (mem.clone(), aux["raw_score"].clone(), aux["selected_inds"].clone())
@@ -31,7 +31,7 @@ with torch.no_grad():
         res[mode] += (mem_inj.clone(),)
 ref = res["fp32"]
 print("mode     | score max-abs | same index at same rank | same selected set | memory max-abs | memory max-abs (same indices)")
-for mode in ("fp32", "3xtf32", "tf32"):
+for mode in ("fp32", "auto", "tcgen05", "3xtf32", "tf32"):
     mem, raw, inds, mem_inj = res[mode]
     same_rank = (inds == ref[2]).float().mean().item()
     same_set = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(inds, ref[2])) / inds.numel()
