@@ -157,12 +157,15 @@ int sdetr_token_scatter(float *tokens, const float *query, const int64_t *inds, 
 
 /* Background embedding (:488-495, position_encoding.py:81-95), in place:
  * tokens[b,t,:] += [col_embed[x] | row_embed[y]] unless mask[b,t] or t in last_inds[b,:num_last].
- * flags: (b,Nv) uint8 scratch. */
+ * row_embed / col_embed: (num_embeddings, channels/2) tables (max_num_embedding, :400-407).  A feature map taller or
+ * wider than the table is an index error in the reference (nn.Embedding): pass the HOST copy of the level shapes in
+ * spatial_shapes_host ((L,2) int64 [H,W], may be NULL) to get SDETR_ERR_INVALID_ARG for it; the kernel itself never
+ * reads outside the tables (indices are clamped).  flags: (b,Nv) uint8 scratch. */
 int sdetr_background_embed(float *tokens, const uint8_t *mask, const int64_t *last_inds, int64_t inds_stride,
-                           int num_last, const float *row_embed, const float *col_embed,
-                           const int64_t *spatial_shapes, const int64_t *level_start_index, int batch,
-                           int num_value, int channels, int num_levels, uint8_t *flags,
-                           sdetr_stream_t stream);
+                           int num_last, const float *row_embed, const float *col_embed, int num_embeddings,
+                           const int64_t *spatial_shapes, const int64_t *spatial_shapes_host,
+                           const int64_t *level_start_index, int batch, int num_value, int channels,
+                           int num_levels, uint8_t *flags, sdetr_stream_t stream);
 
 /* Coarse-to-fine score modulation (:134-143): out = mem + mem * up * alpha[alpha_index], up = bilinear resize
  * (align_corners=True) of the coarser level's score map (b,Hc*Wc) to (H,W).  mem/out (b,H*W,C) with row

@@ -39,7 +39,7 @@ SIGNATURES = {
     "sdetr_topk_desc": (_i, [_vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "sdetr_token_gather": (_i, [_vp] * 5 + [_i64, _vp, _vp] + [_i] * 5 + [_vp] * 5),
     "sdetr_token_scatter": (_i, [_vp, _vp, _vp, _i64, _vp] + [_i] * 4 + [_vp]),
-    "sdetr_background_embed": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp] + [_i] * 4 + [_vp, _vp]),
+    "sdetr_background_embed": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp] + [_i] * 4 + [_vp, _vp]),
     "sdetr_score_modulate": (_i, [_vp, _i64, _vp, _i64, _vp] + [_i] * 7 + [_vp, _vp]),
     "sdetr_zero_masked_rows": (_i, [_vp, _i64, _i, _vp, _i64, _vp]),
     "sdetr_class_max_times_fg": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp]),
@@ -269,17 +269,26 @@ def token_scatter_(tokens, query, inds, focus_token_nums):
     return tokens
 
 
-def background_embed_(tokens, mask_u8, last_inds, row_embed, col_embed, spatial_shapes, level_start_index, flags=None):
+def background_embed_(tokens, mask_u8, last_inds, row_embed, col_embed, spatial_shapes, level_start_index, flags=None,
+                      shapes_host: Optional[Sequence[Sequence[int]]] = None):
+    """``shapes_host``: the [(H, W), ...] of the levels as host ints; a map larger than the embedding tables then raises
+    like the reference's ``nn.Embedding`` lookup.  Without it the shapes are fetched from the device (one sync)."""
     b, nv, c = tokens.shape
     num_last = last_inds.shape[1]
     ip, istride = _inds_view(last_inds, num_last)
     if flags is None:
         flags = torch.empty(b, nv, device=tokens.device, dtype=torch.uint8)
+    L = spatial_shapes.shape[0]
+    if shapes_host is None:
+        shapes_host = spatial_shapes.tolist()
+    host = (ctypes.c_int64 * (2 * L))(*[int(v) for hw in shapes_host for v in hw])
     rc = lib().sdetr_background_embed(
         _req(tokens, "tokens", torch.float32), _req(mask_u8, "mask", torch.uint8), ip, istride, num_last,
         _req(row_embed, "row_embed", torch.float32), _req(col_embed, "col_embed", torch.float32),
-        _req(spatial_shapes, "spatial_shapes", torch.int64), _req(level_start_index, "level_start_index", torch.int64),
-        b, nv, c, spatial_shapes.shape[0], _req(flags, "flags", torch.uint8), _stream())
+        min(row_embed.shape[0], col_embed.shape[0]),
+        _req(spatial_shapes, "spatial_shapes", torch.int64), ctypes.cast(host, ctypes.c_void_p),
+        _req(level_start_index, "level_start_index", torch.int64),
+        b, nv, c, L, _req(flags, "flags", torch.uint8), _stream())
     _check(rc, "sdetr_background_embed")
     return tokens
 

@@ -838,7 +838,7 @@ gemm_3xtf32_p_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = m0 + r_in;
 #pragma unroll 1
-            for (int c = 0; c < kBN / 32; ++c, ++box_it) {
+            for (int c = 0; c < kBN / 32; ++c) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128u + (uint32_t)(c * 32), r);
                 if (c == kBN / 32 - 1) {  // last read of this accumulator: hand it back to the MMA warp
@@ -848,7 +848,9 @@ gemm_3xtf32_p_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 const int col0 = n0 + c * 32;
                 if (col0 >= p.N) continue;  // uniform across the CTA
                 if (p.use_tma_store) {
-                    uint8_t *box = boxes + (box_it & 1) * kTileBytes;
+                    // the two staging boxes alternate per ISSUED store (skipped column blocks must not advance the
+                    // counter, or one box would be refilled while its previous store is still reading it)
+                    uint8_t *box = boxes + (box_it++ & 1) * kTileBytes;
                     if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // box free again
                     named_bar_sync(1, 128);
 #pragma unroll

@@ -120,7 +120,7 @@ __global__ void mark_flags_kernel(const int64_t *__restrict__ inds, int64_t inds
 __global__ void __launch_bounds__(kRowThreads) background_embed_kernel(
     float *__restrict__ tokens, const uint8_t *__restrict__ mask, const uint8_t *__restrict__ flags,
     const float *__restrict__ row_embed, const float *__restrict__ col_embed, const int64_t *__restrict__ shapes,
-    const int64_t *__restrict__ lsi, int batch, int nv, int C, int L) {
+    const int64_t *__restrict__ lsi, int batch, int nv, int C, int L, int num_embeddings) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
     if (row >= (int64_t)batch * nv) return;
@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(kRowThreads) background_embed_kernel(
     load_levels(lv, shapes, lsi, L);
     int l, y, x;
     token_to_lyx(lv, t, l, y, x);
+    y = min(y, num_embeddings - 1), x = min(x, num_embeddings - 1);  // never read outside the tables (host validates)
     const int half = C / 2;
     float *dst = tokens + row * C;
     for (int c = lane * 4; c < C; c += 128) {
@@ -289,13 +290,23 @@ extern "C" int sdetr_token_scatter(float *tokens, const float *query, const int6
 
 extern "C" int sdetr_background_embed(float *tokens, const uint8_t *mask, const int64_t *last_inds,
                                       int64_t inds_stride, int num_last, const float *row_embed,
-                                      const float *col_embed, const int64_t *spatial_shapes,
-                                      const int64_t *level_start_index, int batch, int num_value, int channels,
-                                      int num_levels, uint8_t *flags, sdetr_stream_t stream) {
+                                      const float *col_embed, int num_embeddings, const int64_t *spatial_shapes,
+                                      const int64_t *spatial_shapes_host, const int64_t *level_start_index, int batch,
+                                      int num_value, int channels, int num_levels, uint8_t *flags,
+                                      sdetr_stream_t stream) {
     SDETR_REQUIRE(tokens && mask && last_inds && row_embed && col_embed && spatial_shapes && level_start_index && flags,
                   SDETR_ERR_INVALID_ARG, "background_embed: null pointer");
-    SDETR_REQUIRE(batch > 0 && num_value > 0 && num_last >= 0 && num_levels > 0 && num_levels <= kMaxLevels,
+    SDETR_REQUIRE(batch > 0 && num_value > 0 && num_last >= 0 && num_levels > 0 && num_levels <= kMaxLevels &&
+                      num_embeddings > 0,
                   SDETR_ERR_INVALID_ARG, "background_embed: bad sizes");
+    if (spatial_shapes_host) {  // the reference's nn.Embedding lookup fails for an index >= num_embeddings
+        for (int l = 0; l < num_levels; ++l)
+            SDETR_REQUIRE(spatial_shapes_host[2 * l] <= num_embeddings && spatial_shapes_host[2 * l + 1] <= num_embeddings,
+                          SDETR_ERR_INVALID_ARG,
+                          "background_embed: level %d is %lld x %lld but the embedding tables hold %d rows/columns "
+                          "(max_num_embedding)",
+                          l, (long long)spatial_shapes_host[2 * l], (long long)spatial_shapes_host[2 * l + 1], num_embeddings);
+    }
     SDETR_REQUIRE(channels % 8 == 0 && aligned16(tokens) && aligned16(row_embed) && aligned16(col_embed),
                   SDETR_ERR_INVALID_ARG, "background_embed: channels %% 8 == 0 and 16-byte alignment required");
     cudaStream_t s = (cudaStream_t)stream;
@@ -310,7 +321,7 @@ extern "C" int sdetr_background_embed(float *tokens, const uint8_t *mask, const 
     }
     background_embed_kernel<<<row_blocks((int64_t)batch * num_value), kRowThreads, 0, s>>>(
         tokens, mask, flags, row_embed, col_embed, spatial_shapes, level_start_index, batch, num_value, channels,
-        num_levels);
+        num_levels, num_embeddings);
     return check_launch("background_embed");
 }
 

@@ -125,7 +125,8 @@ class EncoderRunner:
 
     def run_host(self) -> torch.Tensor:
         """host (pinned) -> device copies, forward, device -> host copy of the encoder memory; all on one stream.
-        Masks (and hence the plan) are fixed for the runner's geometry."""
+        Masks (and hence the plan) are fixed for the runner's geometry.  Asynchronous: synchronise ``self.stream``
+        before reading the returned pinned buffer."""
         n = len(self.feats)
         with torch.cuda.stream(self.stream):
             for dst, src in zip(self.feats + self.pos, self._host_in):

@@ -286,7 +286,8 @@ class SalienceTransformerEncoder(nn.Module):
             cabi.token_scatter_(out, q, inds, focus)
         if multi_level_masks is not None:
             cabi.background_embed_(out, mask_u8, inds, self.background_embedding.row_embed.weight,
-                                   self.background_embedding.col_embed.weight, spatial_shapes, level_start_index)
+                                   self.background_embedding.col_embed.weight, spatial_shapes, level_start_index,
+                                   shapes_host=[tuple(m.shape[-2:]) for m in multi_level_masks])
         return out
 
     def _forward_autograd(self, query, spatial_shapes, level_start_index, valid_ratios, query_pos,
@@ -460,9 +461,9 @@ class SalienceTransformer(nn.Module):
                                                 [p.contiguous() for p in multi_level_pos_embeds],
                                                 self.level_embeds.detach().contiguous(), plan.keep.view(plan.keep.shape[0], -1))
         vbuf = None
-        if OVERLAP_VALUE_PROJ and not grad and feat.is_cuda:
-            # fork: the (large) value projection only needs the tokens, so it runs beside the salience filter's
-            # many small kernels; works eagerly and as a parallel branch of a captured CUDA graph
+        if OVERLAP_VALUE_PROJ and not grad and feat.is_cuda and torch.cuda.is_current_stream_capturing():
+            # fork: the (large) value projection only needs the tokens, so it becomes a parallel branch of the captured
+            # CUDA graph, running beside the salience filter's many small kernels (eager calls stay on one stream)
             cur = torch.cuda.current_stream(feat.device)
             side = self._side_stream(feat.device)
             side.wait_stream(cur)

@@ -66,12 +66,14 @@ def make_inputs(config: str = "resnet50_800_1333_bs2", embed_dim: int = 256, see
 
 def build_model(embed_dim=256, d_ffn=2048, heads=8, levels=4, points=4, layers=6, num_classes=91,
                 level_filter_ratio=(0.4, 0.8, 1.0, 1.0), layer_filter_ratio=(1.0, 0.8, 0.6, 0.6, 0.4, 0.2),
-                topk_sa=300, max_num_embedding=200, strides=(8, 16, 32, 64), seed=0, learned_offsets=True):
+                topk_sa=300, max_num_embedding=None, strides=(8, 16, 32, 64), seed=0, learned_offsets=True):
     """Random-init encoder half with the geometry shared by all reference configs
     (configs/salience_detr/salience_detr_resnet50_800_1333.py:22-29,44-62,80-81).  ``learned_offsets`` perturbs
     the (zero-initialised) sampling-offset / attention-weight matrices so sampling is not just the init ring."""
     from .salience_transformer import SalienceTransformer, SalienceTransformerEncoder, SalienceTransformerEncoderLayer
 
+    if max_num_embedding is None:  # 200 (salience_transformer.py:400); the 5-scale config raises it to 500 for its stride-4
+        max_num_embedding = 500 if min(strides) < 8 else 200  # map (salience_detr_resnet50_5scale_800_1333.py:56)
     torch.manual_seed(seed)
     layer = SalienceTransformerEncoderLayer(embed_dim, d_ffn, 0.0, heads, torch.nn.ReLU(inplace=True), levels, points,
                                             topk_sa=topk_sa)

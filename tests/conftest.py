@@ -42,3 +42,21 @@ def load_golden(name):
 
 TINY_CFG = dict(heads=2, points=4, topk_sa=20, num_layers=3, level_filter_ratio=(0.4, 0.8, 1.0, 1.0),
                 layer_filter_ratio=(1.0, 0.6, 0.3))
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _poison_device_memory():
+    """SDETR_POISON=<hex byte>: fill the caching allocator's memory with a byte pattern before the GPU tests, so a
+    kernel that reads memory the path never wrote sees NaNs / wild indices instead of stale-but-plausible data."""
+    pat = os.environ.get("SDETR_POISON")
+    if pat and torch.cuda.is_available():
+        free, _ = torch.cuda.mem_get_info()
+        big = [torch.empty(int(free * 0.3), dtype=torch.uint8, device="cuda:0").fill_(int(pat, 16)) for _ in range(3)]
+        small = [torch.empty(s, dtype=torch.uint8, device="cuda:0").fill_(int(pat, 16))
+                 for s in (512, 4096, 65536, 524288, 1 << 20) for _ in range(400)]
+        torch.cuda.synchronize()
+        del big, small
+    if os.environ.get("SDETR_TRACE_NAN"):
+        from tools import nan_trace
+        nan_trace.install()
+    yield

@@ -4,6 +4,8 @@ BASELINE.json's full sizes -- through size-independent properties.
 
 Tolerances (north_star): top-k / sort indices bit-exact; sampled features <= 1e-3 abs in fp32 (observed ~1e-6,
 asserted at 1e-4 or tighter)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -22,6 +24,18 @@ def pkg():
 
 
 DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _restore_global_state(pkg):
+    """Every test starts from (and leaves) the shipped defaults: gemm.MODE "auto", library options at their defaults --
+    so each parity test exercises the configuration a user gets, not whatever an earlier test left behind."""
+    mode = pkg.gemm.MODE
+    yield
+    pkg.gemm.MODE = mode
+    pkg.cabi.set_option("msda_smem_broadcast", 1)
+    pkg.cabi.lib().sdetr_gemm_set_variant(0)
+    pkg.cabi.lib().sdetr_gemm_set_variant(3)
 
 
 def _msda_inputs(b, shapes, m, d, nq, p, seed):
@@ -101,7 +115,7 @@ def test_msda_smem_broadcast_variant(pkg):
             pkg.cabi.set_option("msda_smem_broadcast", bc)
             outs.append([pkg.cabi.msda_forward(*args, schedule=s) for s in (0, 1)])
     finally:
-        pkg.cabi.set_option("msda_smem_broadcast", 0)
+        pkg.cabi.set_option("msda_smem_broadcast", 1)  # the library default
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert (outs[1][0].cpu() - orc.c_msda_forward(value, st, lsi, loc, attn)).abs().max() < 1e-4
 
@@ -253,6 +267,33 @@ def test_gather_scatter_background(pkg, C):
     assert torch.equal(tok_d.cpu(), want)
 
 
+def test_background_embed_table_bounds(pkg):
+    """A feature map wider / taller than the learned embedding tables (max_num_embedding, salience_transformer.py:400-407)
+    is an index error in the reference (nn.Embedding); here it is a RuntimeError from the host-side check, and the
+    kernel clamps, so nothing outside the tables is ever read."""
+    b, c, n_emb = 1, 64, 8
+    shapes = [(4, 12), (2, 6)]
+    st = torch.tensor(shapes, dtype=torch.int64)
+    lsi = torch.tensor([0, 48], dtype=torch.int64)
+    nv = 60
+    tok = torch.zeros(b, nv, c, device=DEV)
+    mask = torch.zeros(b, nv, dtype=torch.uint8, device=DEV)
+    inds = torch.zeros(b, 1, dtype=torch.int64, device=DEV)
+    row = torch.rand(n_emb, c // 2, device=DEV)
+    col = torch.rand(n_emb, c // 2, device=DEV)
+    with pytest.raises(RuntimeError, match="embedding tables hold 8"):
+        pkg.cabi.background_embed_(tok, mask, inds, row, col, st.to(DEV), lsi.to(DEV), shapes_host=shapes)
+    with pytest.raises(RuntimeError, match="embedding tables hold 8"):  # shapes fetched from the device when not given
+        pkg.cabi.background_embed_(tok, mask, inds, row, col, st.to(DEV), lsi.to(DEV))
+    # the module path raises the same way (the reference config raises max_num_embedding to 500 for its stride-4 map)
+    from salience_detr_b200.synthetic import build_model, make_inputs
+    model = build_model(strides=(4, 8, 16, 32), max_num_embedding=200).to(DEV)
+    feats, masks, pos = make_inputs("resnet50_5scale_bs2", seed=1, device=DEV)
+    with pytest.raises(RuntimeError, match="embedding tables hold 200"), torch.no_grad():
+        model.forward_encoder(feats, masks, pos)
+    torch.cuda.synchronize()
+
+
 def test_flatten_tokens(pkg):
     g = torch.Generator().manual_seed(6)
     b, C = 2, 64
@@ -368,6 +409,24 @@ def test_linear_3xtf32_accuracy(pkg):
     assert torch.equal(s3[:, :, 0], s3[:, :, 1]) and (s3[:, :, 0] + s3[:, :, 2] - x.view(7, 4, 16)).abs().max() < 1e-6
 
 
+def test_gemm_persistent_many_tiles_ragged_n(pkg):
+    """Persistent kernel with several tiles per CTA and N not a multiple of the 32-column store box (the class head's
+    N = 91): the staging boxes of the TMA-store epilogue alternate per issued store.  Repeated, because a box re-used
+    too early is a race, not a deterministic error."""
+    g = torch.Generator().manual_seed(5)
+    for rows, K, N in [(36264, 256, 91), (54396, 256, 96), (40000, 64, 33), (30000, 128, 161)]:
+        x = torch.randn(rows, K, generator=g).to(DEV)
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+        b = torch.randn(N, generator=g).to(DEV)
+        ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+        first = None
+        for _ in range(12):
+            y = pkg.cabi.gemm_3xtf32_raw(x, w, b)
+            assert (y.double() - ref).abs().max().item() < 1e-4, (rows, K, N)
+            first = y.clone() if first is None else first
+            assert torch.equal(y, first)
+
+
 def test_gemm_tcgen05_3xtf32(pkg):
     """Hand-written tcgen05 GEMM (TMA + in-kernel TF32 split + TMEM accumulator) against an fp64 reference."""
     g = torch.Generator().manual_seed(1)
@@ -444,6 +503,65 @@ def test_msda_module_vs_reference_golden(pkg, gemm_mode):
     assert mod.sampling_offsets.weight.grad is not None and torch.isfinite(mod.value_proj.weight.grad).all()
 
 
+def test_msda_module_reference_boxes(pkg):
+    """4-d reference points (the decoder's reference-box branch, ms_deform_attn.py:345-349) through the module."""
+    g = torch.Generator().manual_seed(12)
+    mod = pkg.MultiScaleDeformableAttention(64, 4, 2, 4).to(DEV).eval()
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.05, generator=None)
+        mod.attention_weights.weight.normal_(0, 0.5)
+    shapes = [(9, 12), (5, 6), (3, 3), (2, 2)]
+    st, lsi, nv = _levels(shapes)
+    b, nq = 2, 21
+    query, value = torch.randn(b, nq, 64, generator=g), torch.randn(b, nv, 64, generator=g)
+    boxes = torch.rand(b, nq, 4, 4, generator=g) * 0.5 + 0.25
+    mask = torch.rand(b, nv, generator=g) < 0.1
+    sd = {k: v.detach().cpu() for k, v in mod.state_dict().items()}
+    v = torch.nn.functional.linear(value, sd["value_proj.weight"], sd["value_proj.bias"]).masked_fill(mask[..., None], 0).view(b, nv, 2, 32)
+    off = torch.nn.functional.linear(query, sd["sampling_offsets.weight"], sd["sampling_offsets.bias"]).view(b, nq, 2, 4, 4, 2)
+    att = torch.nn.functional.linear(query, sd["attention_weights.weight"], sd["attention_weights.bias"]).view(b, nq, 2, 16).softmax(-1).view(b, nq, 2, 4, 4)
+    loc = boxes[:, :, None, :, None, :2] + off / 4 * boxes[:, :, None, :, None, 2:] * 0.5
+    want = torch.nn.functional.linear(orc.c_msda_forward(v.contiguous(), st, lsi, loc.contiguous(), att.contiguous()),
+                                      sd["output_proj.weight"], sd["output_proj.bias"])
+    with torch.no_grad():
+        got = mod(query.to(DEV), boxes.to(DEV), value.to(DEV), st.to(DEV), lsi.to(DEV), mask.to(DEV))
+    assert (got.cpu() - want).abs().max() < 1e-4
+
+
+def test_five_scale_stress_geometry(pkg):
+    """salience_detr_resnet50_5scale geometry (strides 4/8/16/32, Nv = 89 250, K = 45 330 with the 800x1333-in-800x1344
+    padding mask; 45 570 for an all-valid mask): the large-K selection path
+    (global-memory radix sorts) stays bit-exact with the oracle and the encoder half runs end to end."""
+    from salience_detr_b200.synthetic import build_model, make_inputs
+    torch.cuda.synchronize()  # surface any earlier asynchronous error here, not inside this test
+    model = build_model(strides=(4, 8, 16, 32)).to(DEV)
+    feats, masks, pos = make_inputs("resnet50_5scale_bs2", seed=1, device=DEV)
+    assert sum(f.shape[2] * f.shape[3] for f in feats) == 89250
+    with torch.no_grad():
+        mem, aux = model.forward_encoder(feats, masks, pos)
+    plan = aux["plan"]
+    assert plan.num_selected == 45330 and mem.shape == (2, 89250, 256) and torch.isfinite(mem).all()
+    wi, ws, wf = orc.c_salience_select(aux["raw_score"].cpu(), plan.mask_flat.cpu(), plan.level_start_index.cpu(),
+                                       torch.tensor(plan.level_size), plan.level_token_nums)
+    assert torch.equal(aux["selected_inds"].cpu(), wi) and torch.equal(aux["foreground_score"].cpu(), wf)
+    # same selection re-used in strict fp32-GEMM mode: the layers agree within the 3xTF32 tolerance
+    prev = pkg.gemm.MODE
+    try:
+        pkg.gemm.MODE = "fp32"
+        feat = pkg.flatten_levels(feats)
+        lpos = pkg.flatten_levels([p + e.view(1, -1, 1, 1) for p, e in zip(pos, model.level_embeds)])
+        with torch.no_grad():
+            mem32 = model.encoder(query=feat, query_pos=lpos, query_key_padding_mask=plan.mask_flat,
+                                  spatial_shapes=plan.spatial_shapes, level_start_index=plan.level_start_index,
+                                  valid_ratios=plan.valid_ratios, foreground_score=aux["foreground_score"],
+                                  focus_token_nums=plan.focus_token_nums,
+                                  foreground_inds=[aux["selected_inds"][:, :n] for n in plan.layer_num_query],
+                                  multi_level_masks=masks)
+    finally:
+        pkg.gemm.MODE = prev
+    assert (mem - mem32).abs().max() < 5e-3
+
+
 @pytest.mark.parametrize("use_order", [False, True])
 def test_encoder_half_vs_reference_golden_even(pkg, use_order, gemm_mode):
     """Tie-free batch: bit-exact selected indices, memory within fp32 round-off of the reference.
@@ -497,6 +615,34 @@ def test_encoder_half_ragged_and_injected_indices(pkg, gemm_mode):
                              focus_token_nums=plan.focus_token_nums,
                              foreground_inds=[ref_inds[:, :n] for n in plan.layer_num_query], multi_level_masks=masks)
     assert (mem_inj.cpu() - g["memory"]).abs().max() < (2e-4 if gemm_mode == "fp32" else 2e-3)
+
+
+def test_encoder_runner_graph_matches_eager(pkg):
+    """EncoderRunner (one CUDA graph, value projection on a parallel branch) and HostPipeline (double-buffered host I/O)
+    reproduce the eager forward bit for bit."""
+    from salience_detr_b200.runner import EncoderRunner, HostPipeline
+    g, sd = load_golden("encoder_tiny_ragged")
+    tr = _tiny_model(pkg, sd)
+    feats, masks, pos = _golden_inputs(g)
+    with torch.no_grad():
+        want, _ = tr.forward_encoder(feats, masks, pos)
+    runner = EncoderRunner(tr, feats, masks, pos)
+    assert runner.graph is not None and runner.launches_per_step > 0
+    for _ in range(3):
+        got = runner.step()
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    runner.bind_host([f.cpu() for f in feats], [p.cpu() for p in pos])
+    host = runner.run_host()  # asynchronous on the runner's stream: synchronise before reading the pinned buffer
+    runner.stream.synchronize()
+    assert torch.equal(host.to(DEV), want)
+    pipe = HostPipeline(tr, feats, masks, pos, depth=2)
+    outs = {}
+    batch = ([f.cpu().pin_memory() for f in feats], [p.cpu().pin_memory() for p in pos])
+    n = pipe.run([batch] * 5, on_output=lambda i, h: outs.__setitem__(i, h.clone()))
+    assert n == 5 and len(outs) == 3  # outputs of batches 0..2 were handed out while 3..4 were still in flight
+    for h in list(outs.values()) + pipe.host_out:
+        assert torch.equal(h.to(DEV), want)
 
 
 def test_encoder_training_path_gradients(pkg):
