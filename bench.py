@@ -127,6 +127,40 @@ def time_msda_kernels(pkg, runner, reps=20):
     return med, byts
 
 
+def time_gemm_kernels(pkg, runner, reps=10):
+    """Secondary (tensor-bound) leg: every dense projection of one step replayed alone with CUDA events.
+    -> (total ms per step, logical flops per step, number of GEMM calls)."""
+    gemm = pkg.gemm
+    calls = []
+    orig = gemm.linear
+
+    def spy(x, w, b=None, *a, **k):
+        calls.append((x, w, b, a, k))
+        return orig(x, w, b, *a, **k)
+
+    gemm.linear = spy
+    try:
+        with torch.no_grad():
+            runner.model.forward_encoder(runner.feats, runner.masks, runner.pos, plan=runner.plan,
+                                         use_order=runner.use_order)
+    finally:
+        gemm.linear = orig
+    torch.cuda.synchronize()
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=runner.dev)
+    totals = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for x, w, b, a, k in calls:
+            orig(x, w, b, *a, **k)
+        e1.record()
+        torch.cuda.synchronize()
+        totals.append(e0.elapsed_time(e1))
+    flops = sum(2 * (x.numel() // x.shape[-1]) * w.shape[0] * w.shape[1] for x, w, _, _, _ in calls)
+    return statistics.median(totals), flops, len(calls)
+
+
 def use_host_cores():
     """The CPU arm uses all physical host cores (torchrun pins OMP_NUM_THREADS=1 by default)."""
     n = os.cpu_count() or 1
@@ -305,6 +339,14 @@ def main():
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch_mean")
             except Exception:
                 traffic = None
+        gemm_ms, gemm_flops, gemm_calls = time_gemm_kernels(pkg, runner)
+        tf32_peak = None
+        try:
+            tf32_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"] / 2.0
+        except Exception:
+            tf32_peak = 2250.0 / 2.0  # nominal dense bf16 / 2 (B200_PROFILING.md fallback)
+        passes = 1 if pkg.gemm.MODE in ("fp32", "tf32") else 3
+        gemm_exec = passes * gemm_flops / (gemm_ms / 1000.0) / 1e12
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
@@ -333,6 +375,14 @@ def main():
                          "frac": round(achieved / peak, 4), "traffic": traffic,
                          "algorithmic_bytes_per_step": int(sum(byts)), "kernel_ms_per_step": round(sum(med), 4),
                          "per_layer_us": [round(1000 * x, 1) for x in med]},
+            # secondary leg: the dense projections (tensor-bound; 3xTF32 issues 3 TF32 MMA passes per logical product)
+            "roofline_gemm": {"bound": "tensor", "kernels": "sdetr::gemm_3xtf32_p_kernel + cuBLAS TF32 (wide K=256 GEMMs)",
+                              "achieved": round(gemm_exec, 1), "peak": round(tf32_peak, 1),
+                              "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 dense = half the bf16 rate)",
+                              "unit": "TFLOP/s", "frac": round(gemm_exec / tf32_peak, 4),
+                              "logical_tflops": round(gemm_flops / (gemm_ms / 1000.0) / 1e12, 1),
+                              "mma_passes": passes, "gemm_calls_per_step": gemm_calls,
+                              "kernel_ms_per_step": round(gemm_ms, 4)},
         }
         if world == 1 and not args.skip_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(pkg, model)

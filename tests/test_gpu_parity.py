@@ -617,6 +617,42 @@ def test_encoder_half_ragged_and_injected_indices(pkg, gemm_mode):
     assert (mem_inj.cpu() - g["memory"]).abs().max() < (2e-4 if gemm_mode == "fp32" else 2e-3)
 
 
+def test_config1_encoder_half_vs_oracle(pkg):
+    """BASELINE.json configs[0] (512x512, bs=1, Nv=5440, K=2777) at the real model dimensions (C=256, 8 heads, 6 layers,
+    topk_sa=300): filter scores against the CPU oracle, then -- with the oracle's own indices injected, so both sides
+    process the same tokens -- the encoder memory within the north-star tolerance (1e-3 abs), in strict fp32 and in the
+    default 3xTF32 GEMM mode."""
+    from salience_detr_b200.synthetic import build_model, make_inputs
+    model = build_model().to(DEV)
+    feats, masks, pos = make_inputs("cpu_512", seed=3, device=DEV)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    cfg = dict(heads=8, points=4, topk_sa=300, num_layers=6, level_filter_ratio=(0.4, 0.8, 1.0, 1.0),
+               layer_filter_ratio=(1.0, 0.8, 0.6, 0.6, 0.4, 0.2))
+    omem, ofilt = orc.encoder_half_forward(sd, [f.cpu() for f in feats], [m.cpu() for m in masks], [p.cpu() for p in pos],
+                                           cfg, core="c", use_c_helpers=True)
+    assert ofilt["selected_inds"].shape == (1, 2777) and ofilt["layer_num_query"] == [2777, 2221, 1666, 1666, 1110, 555]
+    oinds, ofg = ofilt["selected_inds"].to(DEV), ofilt["foreground_score"].to(DEV)
+    for mode, tol_score, tol_mem in (("fp32", 2e-5, 1e-3), ("auto", 2e-4, 1e-3)):
+        pkg.gemm.MODE = mode
+        with torch.no_grad():
+            mem, aux = model.forward_encoder(feats, masks, pos)
+        plan = aux["plan"]
+        assert plan.num_selected == 2777 and plan.layer_num_query == ofilt["layer_num_query"]
+        assert (aux["raw_score"].cpu() - ofilt["raw_score"]).abs().max() < tol_score
+        got, want = set(aux["selected_inds"][0].tolist()), set(ofilt["selected_inds"][0].tolist())
+        assert len(got & want) >= 2777 - 8  # near-ties at the budget boundary may swap (scores differ by round-off)
+        feat = pkg.flatten_levels(feats)
+        lpos = pkg.flatten_levels([p + e.view(1, -1, 1, 1) for p, e in zip(pos, model.level_embeds)])
+        with torch.no_grad():
+            mem_inj = model.encoder(query=feat, query_pos=lpos, query_key_padding_mask=plan.mask_flat,
+                                    spatial_shapes=plan.spatial_shapes, level_start_index=plan.level_start_index,
+                                    valid_ratios=plan.valid_ratios, foreground_score=ofg,
+                                    focus_token_nums=plan.focus_token_nums,
+                                    foreground_inds=[oinds[:, :n] for n in plan.layer_num_query], multi_level_masks=masks)
+        err = (mem_inj.cpu() - omem).abs().max().item()
+        assert err < tol_mem, (mode, err)
+
+
 def test_encoder_runner_graph_matches_eager(pkg):
     """EncoderRunner (one CUDA graph, value projection on a parallel branch) and HostPipeline (double-buffered host I/O)
     reproduce the eager forward bit for bit."""
