@@ -179,6 +179,13 @@ int sdetr_score_modulate(const float *mem, int64_t mem_batch_stride, const float
 int sdetr_zero_masked_rows(float *rows, int64_t row_stride, int row_floats, const uint8_t *mask,
                            int64_t num_rows, sdetr_stream_t stream);
 
+/* MaskPredictor middle (salience_transformer.py:40-45), in place on z (b,num_rows,channels):
+ * z = GELU(z) (exact erf form); then z[b,:,half:] = mean over the num_rows tokens of image b (padded tokens included,
+ * like the reference).  Deterministic two-pass reduction; workspace from sdetr_gelu_colmean_workspace. */
+size_t sdetr_gelu_colmean_workspace(int batch, int num_rows, int channels, int half);
+int sdetr_gelu_colmean(float *z, int batch, int num_rows, int channels, int half, void *workspace,
+                       size_t workspace_bytes, sdetr_stream_t stream);
+
 /* mc_score = max_c(class_logits) * fg (:366).  logits (rows, num_classes) with row pitch row_pitch -> out (rows). */
 int sdetr_class_max_times_fg(const float *logits, int64_t row_pitch, const float *fg, int64_t rows, int num_classes,
                              float *out, sdetr_stream_t stream);
@@ -201,6 +208,24 @@ int sdetr_flatten_tokens(const float *const *feats_host, const float *const *pos
  * then keys; v (b,n,heads,d); out (b,n,heads*d).  head_dim must be 32; n limited by shared memory (~750). */
 int sdetr_attention_small(const float *qk, const float *v, float *out, int batch, int n, int heads, int head_dim,
                           sdetr_stream_t stream);
+/* Same core on a packed projection buffer qkv (b,n,3,heads,d) (what sdetr_mha_in_proj writes). */
+int sdetr_attention_qkv(const float *qkv, float *out, int batch, int n, int heads, int head_dim, sdetr_stream_t stream);
+
+/* Pre-attention front (salience_transformer.py:368-372 + the packed in-projection of nn.MultiheadAttention):
+ * t_out[b,j,:] = tokens[b,index[b,j],:];  x = t + pos[b,index[b,j],:];
+ * qkv[b,j,:] = [x Wq^T + bq | x Wk^T + bk | t Wv^T + bv].
+ * tokens/pos (b,num_rows,C); index (b,k) int64; w_in_t = in_proj_weight TRANSPOSED, (C,3C) row-major; b_in (3C);
+ * t_out (b,k,C); qkv (b,k,3C).  channels must be 256.  fp32 FMA arithmetic. */
+int sdetr_mha_in_proj(const float *tokens, const float *pos, const int64_t *index, int batch, int num_rows, int k,
+                      int channels, const float *w_in_t, const float *b_in, float *t_out, float *qkv,
+                      sdetr_stream_t stream);
+
+/* Pre-attention back (salience_transformer.py:373-379): y = LayerNorm(t + attn Wo^T + bo) with (gamma, beta, eps);
+ * dst[b,index[b,j],:] = y[b,j,:] (indices unique per image).  attn, t (b,k,C); w_out_t = out_proj.weight TRANSPOSED
+ * (C,C); dst (b,num_rows,C), updated in place.  channels must be 256. */
+int sdetr_mha_out_proj_ln_scatter(const float *attn, const float *t, const float *w_out_t, const float *b_out,
+                                  const float *gamma, const float *beta, float eps, const int64_t *index, float *dst,
+                                  int batch, int num_rows, int k, int channels, sdetr_stream_t stream);
 
 /* Row gather / scatter by per-image index (the top-k tokens of the pre-attention, salience_transformer.py:368-379):
  * out[b,j,:] = src[b,index[b,j],:]   /   dst[b,index[b,j],:] = src[b,j,:]  (indices unique per image).

@@ -42,6 +42,8 @@ SIGNATURES = {
     "sdetr_background_embed": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp] + [_i] * 4 + [_vp, _vp]),
     "sdetr_score_modulate": (_i, [_vp, _i64, _vp, _i64, _vp] + [_i] * 7 + [_vp, _vp]),
     "sdetr_zero_masked_rows": (_i, [_vp, _i64, _i, _vp, _i64, _vp]),
+    "sdetr_gelu_colmean_workspace": (_sz, [_i, _i, _i, _i]),
+    "sdetr_gelu_colmean": (_i, [_vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "sdetr_class_max_times_fg": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp]),
     "sdetr_add_layernorm": (_i, [_vp, _vp, _vp, _vp, _f, _i64, _i, _vp, _vp]),
     "sdetr_split_tf32": (_i, [_vp, _i64, _i64, _i, _i, _i, _i, _vp, _vp]),
@@ -52,6 +54,9 @@ SIGNATURES = {
     "sdetr_gemm_3xtf32": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
     "sdetr_flatten_tokens": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "sdetr_attention_small": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "sdetr_attention_qkv": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "sdetr_mha_in_proj": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "sdetr_mha_out_proj_ln_scatter": (_i, [_vp] * 6 + [_f, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sdetr_rows_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "sdetr_rows_gather_add": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "sdetr_rows_scatter": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
@@ -459,3 +464,52 @@ def attention_small(qk, v):
                                      _stream())
     _check(rc, "sdetr_attention_small")
     return out
+
+
+def attention_qkv(qkv, heads: int):
+    """qkv (b,n,3C) packed [q | k | v] projections -> (b,n,C) = softmax(QK^T/sqrt(d)) V per head (d = C/heads = 32)."""
+    b, n, c3 = qkv.shape
+    c = c3 // 3
+    out = torch.empty(b, n, c, device=qkv.device, dtype=torch.float32)
+    rc = lib().sdetr_attention_qkv(_req(qkv, "qkv", torch.float32), out.data_ptr(), b, n, heads, c // heads, _stream())
+    _check(rc, "sdetr_attention_qkv")
+    return out
+
+
+def mha_in_proj(tokens, pos, index, w_in_t, b_in):
+    """tokens/pos (b,nq,C), index (b,k) int64, w_in_t (C,3C) = in_proj_weight.T -> (t (b,k,C), qkv (b,k,3C))."""
+    b, nq, c = tokens.shape
+    k = index.shape[1]
+    t = torch.empty(b, k, c, device=tokens.device, dtype=torch.float32)
+    qkv = torch.empty(b, k, 3 * c, device=tokens.device, dtype=torch.float32)
+    if tuple(w_in_t.shape) != (c, 3 * c) or b_in.numel() != 3 * c:
+        raise RuntimeError("w_in_t must be (C, 3C) and b_in (3C)")
+    rc = lib().sdetr_mha_in_proj(_req(tokens, "tokens", torch.float32), _req(pos, "pos", torch.float32),
+                                 _req(index, "index", torch.int64), b, nq, k, c, _req(w_in_t, "w_in_t", torch.float32),
+                                 _req(b_in, "b_in", torch.float32), t.data_ptr(), qkv.data_ptr(), _stream())
+    _check(rc, "sdetr_mha_in_proj")
+    return t, qkv
+
+
+def mha_out_proj_ln_scatter_(dst, attn, t, w_out_t, b_out, gamma, beta, eps: float, index):
+    """dst (b,nq,C) <- LayerNorm(t + attn @ w_out_t + b_out) at index (b,k), in place."""
+    b, nq, c = dst.shape
+    k = index.shape[1]
+    if tuple(w_out_t.shape) != (c, c):
+        raise RuntimeError("w_out_t must be (C, C)")
+    rc = lib().sdetr_mha_out_proj_ln_scatter(
+        _req(attn, "attn", torch.float32), _req(t, "t", torch.float32), _req(w_out_t, "w_out_t", torch.float32),
+        _req(b_out, "b_out", torch.float32), _req(gamma, "gamma", torch.float32), _req(beta, "beta", torch.float32),
+        float(eps), _req(index, "index", torch.int64), _req(dst, "dst", torch.float32), b, nq, k, c, _stream())
+    _check(rc, "sdetr_mha_out_proj_ln_scatter")
+    return dst
+
+
+def gelu_colmean_(z, half: int):
+    """z (b,n,C) in place: GELU everywhere, then columns [half, C) replaced by their per-image token mean."""
+    b, n, c = z.shape
+    need = lib().sdetr_gelu_colmean_workspace(b, n, c, half)
+    ws = torch.empty(need, device=z.device, dtype=torch.uint8)
+    rc = lib().sdetr_gelu_colmean(_req(z, "z", torch.float32), b, n, c, half, ws.data_ptr(), ws.numel(), _stream())
+    _check(rc, "sdetr_gelu_colmean")
+    return z

@@ -425,6 +425,90 @@ extern "C" int sdetr_split_tf32(const float *x, int64_t x_row_stride, int64_t ro
     return check_launch("split_tf32");
 }
 
+// ---- MaskPredictor middle (salience_transformer.py:40-45): z = GELU(z); z[:, :, half:] = mean over the image's tokens ----
+// Two launches: (1) GELU in place on the local half + per-CTA partial column sums of GELU(global half), (2) every CTA
+// adds the partials in a fixed order (bit-reproducible, no atomics) and writes the mean over its rows' global half.
+namespace sdetr {
+constexpr int kMeanThreads = 256;
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+__global__ void __launch_bounds__(kMeanThreads) gelu_colsum_kernel(float *__restrict__ z, int n, int C, int half, int chunks,
+                                                                   float *__restrict__ partial /* (b, chunks, C - half) */) {
+    __shared__ float4 red[kMeanThreads];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int vec = C / 4, lanes = kMeanThreads / vec;          // threads per row, rows in flight
+    const int cv = threadIdx.x % vec, rl = threadIdx.x / vec;
+    const int rows_per = (n + chunks - 1) / chunks, r0 = chunk * rows_per, r1 = min(n, r0 + rows_per);
+    const bool global_half = cv * 4 >= half;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rl < lanes) {
+        for (int r = r0 + rl; r < r1; r += lanes) {
+            float *p = z + ((int64_t)b * n + r) * C + cv * 4;
+            float4 x = *reinterpret_cast<const float4 *>(p);
+            x.x = gelu_exact(x.x), x.y = gelu_exact(x.y), x.z = gelu_exact(x.z), x.w = gelu_exact(x.w);
+            if (global_half) acc.x += x.x, acc.y += x.y, acc.z += x.z, acc.w += x.w;
+            else *reinterpret_cast<float4 *>(p) = x;
+        }
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (rl == 0 && global_half) {
+        float4 t = red[cv];
+        for (int l = 1; l < lanes; ++l) {
+            const float4 y = red[l * vec + cv];
+            t.x += y.x, t.y += y.y, t.z += y.z, t.w += y.w;
+        }
+        *reinterpret_cast<float4 *>(partial + ((int64_t)b * chunks + chunk) * (C - half) + (cv * 4 - half)) = t;
+    }
+}
+
+__global__ void __launch_bounds__(kMeanThreads) colmean_broadcast_kernel(float *__restrict__ z, int n, int C, int half,
+                                                                         int chunks, const float *__restrict__ partial) {
+    __shared__ __align__(16) float mean[1024];
+    const int b = blockIdx.y, chunk = blockIdx.x, g = C - half;
+    for (int c = threadIdx.x; c < g; c += kMeanThreads) {
+        float t = 0.f;
+        for (int k = 0; k < chunks; ++k) t += __ldg(partial + ((int64_t)b * chunks + k) * g + c);
+        mean[c] = t / (float)n;
+    }
+    __syncthreads();
+    const int gv = g / 4, lanes = kMeanThreads / gv;
+    const int cv = threadIdx.x % gv, rl = threadIdx.x / gv;
+    const int rows_per = (n + chunks - 1) / chunks, r0 = chunk * rows_per, r1 = min(n, r0 + rows_per);
+    if (rl >= lanes) return;
+    const float4 m = *reinterpret_cast<const float4 *>(mean + cv * 4);
+    for (int r = r0 + rl; r < r1; r += lanes)
+        *reinterpret_cast<float4 *>(z + ((int64_t)b * n + r) * C + half + cv * 4) = m;
+}
+}  // namespace sdetr
+
+extern "C" size_t sdetr_gelu_colmean_workspace(int batch, int num_rows, int channels, int half) {
+    (void)num_rows;
+    return (size_t)batch * 148 * (size_t)(channels - half) * sizeof(float);
+}
+
+extern "C" int sdetr_gelu_colmean(float *z, int batch, int num_rows, int channels, int half, void *workspace,
+                                  size_t workspace_bytes, sdetr_stream_t stream) {
+    SDETR_REQUIRE(z && workspace, SDETR_ERR_INVALID_ARG, "gelu_colmean: null pointer");
+    SDETR_REQUIRE(batch > 0 && num_rows > 0 && channels > 0 && channels % 4 == 0 && channels <= 1024 && half >= 0 &&
+                      half < channels && half % 4 == 0 && (channels - half) % 4 == 0 && aligned16(z) && aligned16(workspace),
+                  SDETR_ERR_INVALID_ARG, "gelu_colmean: bad sizes / alignment");
+    SDETR_REQUIRE(channels / 4 <= kMeanThreads, SDETR_ERR_UNSUPPORTED, "gelu_colmean: channels %d > %d", channels, 4 * kMeanThreads);
+    SDETR_REQUIRE(workspace_bytes >= sdetr_gelu_colmean_workspace(batch, num_rows, channels, half), SDETR_ERR_WORKSPACE,
+                  "gelu_colmean: workspace too small");
+    int chunks = (num_rows + 63) / 64;  // >= 64 rows per CTA, at most one wave
+    const int cap = 148 / batch > 0 ? 148 / batch : 1;
+    if (chunks > cap) chunks = cap;
+    if (chunks < 1) chunks = 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    gelu_colsum_kernel<<<dim3(chunks, batch), kMeanThreads, 0, s>>>(z, num_rows, channels, half, chunks, (float *)workspace);
+    int rc = check_launch("gelu_colmean/colsum");
+    if (rc) return rc;
+    colmean_broadcast_kernel<<<dim3(chunks, batch), kMeanThreads, 0, s>>>(z, num_rows, channels, half, chunks,
+                                                                          (const float *)workspace);
+    return check_launch("gelu_colmean/broadcast");
+}
+
 // ---- generic row gather / scatter by index (the 300-token pre-attention, salience_transformer.py:368-379) ----
 namespace sdetr {
 __global__ void __launch_bounds__(kRowThreads) rows_gather_kernel(const float *__restrict__ src, const int64_t *__restrict__ idx,
@@ -567,88 +651,3 @@ extern "C" int sdetr_rows_gather_add(const float *src, const float *pos, const i
     return check_launch("rows_gather_add");
 }
 
-// ---- small dense attention of the pre-attention (salience_transformer.py:372-376, nn.MultiheadAttention core) --------
-// softmax(Q K^T / sqrt(d)) V for a few hundred tokens, head_dim 32.  One CTA = one (image, head) and a tile of queries;
-// K and V of the head live in shared memory (K rows padded to 33 floats: lanes read different rows conflict-free).
-// A warp owns one query at a time: lanes split the keys for the scores, warp-shuffle max/sum for the softmax, the
-// probabilities go through shared memory, then lanes = output channels accumulate p_j * V[j][lane] (coalesced rows).
-namespace sdetr {
-constexpr int kAttnWarps = 8;
-__global__ void __launch_bounds__(kAttnWarps * 32) attn_small_kernel(const float *__restrict__ qk, const float *__restrict__ v,
-                                                                     float *__restrict__ out, int n, int heads, float scale,
-                                                                     int q_per_cta) {
-    extern __shared__ float sm_attn[];
-    float *ks = sm_attn;                 // n x 33
-    float *vs = ks + (((size_t)n * 33 + 3) & ~(size_t)3);  // n x 32, 16-byte aligned
-    float *ps = vs + (size_t)n * 32;     // kAttnWarps x n
-    const int h = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t qk_row = 2LL * heads * 32, v_row = (int64_t)heads * 32;
-    const float *qbase = qk + (int64_t)b * n * qk_row + (int64_t)h * 32;
-    const float *kbase = qbase + (int64_t)heads * 32;
-    const float *vbase = v + (int64_t)b * n * v_row + (int64_t)h * 32;
-    for (int i = threadIdx.x; i < n * 8; i += blockDim.x) {  // 128-bit loads of the head's K / V rows
-        const int j = i >> 3, c = (i & 7) * 4;
-        const float4 kv = ldg_f4(kbase + j * qk_row + c), vv = ldg_f4(vbase + j * v_row + c);
-        ks[j * 33 + c] = kv.x, ks[j * 33 + c + 1] = kv.y, ks[j * 33 + c + 2] = kv.z, ks[j * 33 + c + 3] = kv.w;
-        *reinterpret_cast<float4 *>(vs + j * 32 + c) = vv;
-    }
-    __syncthreads();
-    float *p = ps + (size_t)warp * n;
-    const int q0 = blockIdx.z * q_per_cta, q1 = min(n, q0 + q_per_cta);
-    for (int qi = q0 + warp; qi < q1; qi += kAttnWarps) {
-        float q[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) q[c] = __ldg(qbase + qi * qk_row + c) * scale;  // same address across the warp: broadcast
-        float mx = -INFINITY;
-        for (int j = lane; j < n; j += 32) {
-            float s = 0.f;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) s = fmaf(q[c], ks[j * 33 + c], s);
-            p[j] = s;
-            mx = fmaxf(mx, s);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        float sum = 0.f;
-        for (int j = lane; j < n; j += 32) {
-            const float e = __expf(p[j] - mx);
-            p[j] = e;
-            sum += e;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        __syncwarp();
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four independent chains hide the LDS -> FMA latency
-        int j = 0;
-        for (; j + 3 < n; j += 4) {
-            a0 = fmaf(p[j], vs[j * 32 + lane], a0);
-            a1 = fmaf(p[j + 1], vs[(j + 1) * 32 + lane], a1);
-            a2 = fmaf(p[j + 2], vs[(j + 2) * 32 + lane], a2);
-            a3 = fmaf(p[j + 3], vs[(j + 3) * 32 + lane], a3);
-        }
-        for (; j < n; ++j) a0 = fmaf(p[j], vs[j * 32 + lane], a0);
-        out[((int64_t)b * n + qi) * v_row + h * 32 + lane] = ((a0 + a1) + (a2 + a3)) / sum;
-        __syncwarp();
-    }
-}
-}  // namespace sdetr
-
-extern "C" int sdetr_attention_small(const float *qk, const float *v, float *out, int batch, int n, int heads, int head_dim,
-                                     sdetr_stream_t stream) {
-    SDETR_REQUIRE(qk && v && out, SDETR_ERR_INVALID_ARG, "attention_small: null pointer");
-    SDETR_REQUIRE(batch > 0 && n > 0 && heads > 0, SDETR_ERR_INVALID_ARG, "attention_small: bad sizes");
-    SDETR_REQUIRE(head_dim == 32, SDETR_ERR_UNSUPPORTED, "attention_small: head_dim %d (only 32)", head_dim);
-    const size_t smem = ((((size_t)n * 33 + 3) & ~(size_t)3) + (size_t)n * 32 + (size_t)kAttnWarps * n) * sizeof(float);
-    SDETR_REQUIRE(smem <= 200 * 1024, SDETR_ERR_UNSUPPORTED, "attention_small: %d tokens do not fit in shared memory", n);
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "attention_small: smem attribute: %s", cudaGetErrorString(e));
-        attr = true;
-    }
-    const int q_per_cta = 16;  // two queries per warp: 300 tokens -> 19 query tiles x heads x batch = 304 CTAs at (h=8, b=2)
-    dim3 grid(heads, batch, (n + q_per_cta - 1) / q_per_cta);
-    attn_small_kernel<<<grid, kAttnWarps * 32, smem, (cudaStream_t)stream>>>(qk, v, out, n, heads, 1.f / sqrtf((float)head_dim),
-                                                                             q_per_cta);
-    return check_launch("attention_small");
-}

@@ -33,6 +33,7 @@ from . import cabi, gemm
 from .ms_deform_attn import MultiScaleDeformableAttention
 
 OVERLAP_VALUE_PROJ = True  # run the all-layer value projection on a side stream, concurrently with the salience filter
+FUSED_PRE_ATTENTION = True  # C = 256 / head_dim 32: gather+in-proj, attention, out-proj+LN+scatter as three kernels
 SMALL_ATTENTION = False   # hand-written 300-token attention kernel instead of SDPA (measured slower: 35 vs 30 us)
 MHA_GEMM_TENSOR_CORE = False  # pre-attention projections (M = 600 rows): cuBLAS SGEMM measured faster than the tensor-core kernels
 TILE_CELL_PX = 64   # edge (image pixels) of the spatial cells that define the MSDA processing order
@@ -64,9 +65,13 @@ class MaskPredictor(nn.Module):
         LayerNorm by the fused kernel, global half written in place instead of split/expand/cat."""
         ln, fc = self.layer1[0], self.layer1[1]
         x = x if x.is_contiguous() else x.contiguous()
-        z = F.gelu(gemm.linear(cabi.add_layernorm(x, None, ln.weight, ln.bias, ln.eps), fc.weight, fc.bias))
+        z = gemm.linear(cabi.add_layernorm(x, None, ln.weight, ln.bias, ln.eps), fc.weight, fc.bias)
         half = self.h_dim // 2
-        z[..., half:] = z[..., half:].mean(dim=1, keepdim=True)  # global half = token mean, broadcast in place (:43-45)
+        if z.dim() == 3 and z.is_contiguous() and self.h_dim % 8 == 0 and self.h_dim <= 1024:
+            cabi.gelu_colmean_(z, half)  # GELU + global half = token mean, broadcast in place (:40-45), two launches
+        else:
+            z = F.gelu(z)
+            z[..., half:] = z[..., half:].mean(dim=1, keepdim=True)
         z = gemm.linear(z, self.layer2[0].weight, self.layer2[0].bias)
         z = gemm.linear(z, self.layer2[2].weight, self.layer2[2].bias, input_act="gelu")
         return gemm.linear(z, self.layer2[4].weight, self.layer2[4].bias, input_act="gelu")
@@ -173,12 +178,31 @@ class SalienceTransformerEncoderLayer(nn.Module):
             self._mha = (w.detach()[:2 * c], bias.detach()[:2 * c], w.detach()[2 * c:], bias.detach()[2 * c:])
         return self._mha
 
+    def _mha_transposed(self):
+        """in_proj_weight^T (C,3C) and out_proj.weight^T (C,C), cached per parameter version (the fused pre-attention
+        kernels stream weight rows of the (in, out) layout)."""
+        w, wo = self.pre_attention.in_proj_weight, self.pre_attention.out_proj.weight
+        key = (w.data_ptr(), w._version, wo.data_ptr(), wo._version)
+        if getattr(self, "_mha_t_key", None) != key:
+            with torch.no_grad():
+                self._mha_t = (w.detach().t().contiguous(), wo.detach().t().contiguous())
+            self._mha_t_key = key
+        return self._mha_t
+
     def _pre_attention_fast(self, q, qp, mc):
-        """Top-k salient tokens -> MHA -> LN -> scatter (reference :366-379) with the small projections on the
-        tensor-core GEMM (bias fused) and fused gather / residual+LN / scatter kernels."""
+        """Top-k salient tokens -> MHA -> LN -> scatter (reference :366-379).  C = 256, head_dim = 32 (every reference
+        config): three fused fp32 kernels (csrc/mha_small.cu); other geometries: library projections / SDPA between
+        the fused gather / residual+LN / scatter kernels."""
         b, nq, c = q.shape
         k = min(self.topk_sa, nq)
         top = cabi.topk_desc(mc, k)
+        if FUSED_PRE_ATTENTION and c == 256 and c // self.n_heads == 32 and k <= 448:  # attention kernel: K/V/P in smem
+            w_in_t, w_out_t = self._mha_transposed()
+            t, qkv = cabi.mha_in_proj(q, qp, top, w_in_t, self.pre_attention.in_proj_bias)
+            o = cabi.attention_qkv(qkv, self.n_heads)
+            cabi.mha_out_proj_ln_scatter_(q, o, t, w_out_t, self.pre_attention.out_proj.bias, self.pre_norm.weight,
+                                          self.pre_norm.bias, self.pre_norm.eps, top)
+            return q
         t, x = cabi.rows_gather_add(q, qp, top)           # t = q[top], x = t + qp[top]
         wqk, bqk, wv, bv = self._mha_views()
         h, d = self.n_heads, c // self.n_heads

@@ -294,6 +294,20 @@ def test_background_embed_table_bounds(pkg):
     torch.cuda.synchronize()
 
 
+def test_gelu_colmean(pkg):
+    """MaskPredictor middle (reference :40-45): GELU, then the global half replaced by its per-image token mean."""
+    g = torch.Generator().manual_seed(21)
+    for b, n, c in [(2, 16800, 256), (1, 273, 256), (3, 50, 64), (2, 1000, 96)]:
+        z = torch.randn(b, n, c, generator=g)
+        half = c // 2
+        want = torch.nn.functional.gelu(z.double())
+        want[..., half:] = want[..., half:].mean(dim=1, keepdim=True)
+        got = pkg.cabi.gelu_colmean_(z.to(DEV), half)
+        assert (got.cpu().double() - want).abs().max() < 2e-6
+        again = pkg.cabi.gelu_colmean_(z.to(DEV), half)
+        assert torch.equal(again, got)  # fixed-order reduction: bit-reproducible
+
+
 def test_flatten_tokens(pkg):
     g = torch.Generator().manual_seed(6)
     b, C = 2, 64
@@ -312,13 +326,51 @@ def test_flatten_tokens(pkg):
 
 def test_attention_small(pkg):
     g = torch.Generator().manual_seed(8)
-    for b, n, h in [(2, 300, 8), (1, 37, 2), (3, 700, 4)]:
+    for b, n, h in [(2, 300, 8), (1, 37, 2), (3, 450, 4)]:
         qk = torch.randn(b, n, 2, h, 32, generator=g)
         v = torch.randn(b, n, h, 32, generator=g)
         want = torch.nn.functional.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2),
                                                                 v.transpose(1, 2)).transpose(1, 2).reshape(b, n, h * 32)
         got = pkg.cabi.attention_small(qk.to(DEV), v.to(DEV))
         assert (got.cpu() - want).abs().max() < 2e-5
+        qkv = torch.cat([qk.flatten(2), v.flatten(2)], -1).to(DEV)  # packed (b,n,3C) layout of the fused in-projection
+        assert torch.equal(pkg.cabi.attention_qkv(qkv, h), got)
+    with pytest.raises(RuntimeError, match="do not fit in shared memory"):  # K^T, V and the score tile live in smem
+        pkg.cabi.attention_small(torch.zeros(1, 700, 2, 4, 32, device=DEV), torch.zeros(1, 700, 4, 32, device=DEV))
+
+
+def test_fused_pre_attention_vs_torch_mha(pkg):
+    """The three fused kernels of the 300-token pre-attention (gather + in-projection, attention, out-projection +
+    residual + LayerNorm + scatter) against nn.MultiheadAttention / nn.LayerNorm in fp64 (reference :366-379)."""
+    g = torch.Generator().manual_seed(12)
+    c, heads = 256, 8
+    mha = torch.nn.MultiheadAttention(c, heads, batch_first=True)
+    ln = torch.nn.LayerNorm(c)
+    with torch.no_grad():
+        for p_ in list(mha.parameters()) + list(ln.parameters()):
+            p_.copy_(torch.randn(p_.shape, generator=g) * (0.06 if p_.dim() > 1 else 0.3) + (1.0 if p_ is ln.weight else 0.0))
+    for b, nq, k in [(2, 1000, 300), (1, 77, 77), (3, 400, 37)]:
+        q = torch.randn(b, nq, c, generator=g)
+        qp = torch.randn(b, nq, c, generator=g)
+        top = torch.stack([torch.randperm(nq, generator=g)[:k] for _ in range(b)])
+        ix = top.unsqueeze(-1).expand(-1, -1, c)
+        t = torch.gather(q, 1, ix).double()
+        x = t + torch.gather(qp, 1, ix).double()
+        m64, l64 = mha.double(), ln.double()
+        with torch.no_grad():
+            want = q.double().scatter(1, ix, l64(t + m64(x, x, t)[0]))
+        mha.float(), ln.float()
+        d = lambda z: z.detach().to(DEV).contiguous()
+        t_g, qkv = pkg.cabi.mha_in_proj(d(q), d(qp), d(top), d(mha.in_proj_weight.t()), d(mha.in_proj_bias))
+        assert torch.equal(t_g.cpu(), torch.gather(q, 1, ix))
+        w64, b64 = mha.in_proj_weight.double(), mha.in_proj_bias.double()
+        want_qkv = torch.cat([x @ w64[:2 * c].t() + b64[:2 * c], t @ w64[2 * c:].t() + b64[2 * c:]], -1)
+        assert (qkv.cpu().double() - want_qkv).abs().max() < 2e-5
+        o = pkg.cabi.attention_qkv(qkv, heads)
+        out = d(q).clone()
+        pkg.cabi.mha_out_proj_ln_scatter_(out, o, t_g, d(mha.out_proj.weight.t()), d(mha.out_proj.bias), d(ln.weight),
+                                          d(ln.bias), ln.eps, d(top))
+        assert (out.cpu().double() - want).abs().max() < 5e-5, (b, nq, k)
 
 
 def test_rows_gather_scatter(pkg):
