@@ -354,8 +354,9 @@ def main():
             "config": {"workload": WORKLOAD, "batch_per_gpu": bsz, "global_batch": bsz * world,
                        "parallelism": f"dp{world} (independent replicas, no forward collective)",
                        "weights": "random init (seed 0) + N(0,0.02) sampling-offset weights",
-                       "gemm": {"auto": "3xTF32 (fp32-class accuracy) everywhere: hand-written tcgen05.mma.kind::tf32 GEMM (TMA multicast, in-kernel "
-                                        "operand split, TMEM accumulator) for N<=512 or K>=1024, cuBLAS TF32 on pre-split operands for the wide K=256 GEMMs",
+                       "gemm": {"auto": "3xTF32 (fp32-class accuracy): hand-written persistent tcgen05.mma.kind::tf32 GEMM (TMA, pre-split weight, "
+                                        "activation split in the kernel into tensor memory, double-buffered TMEM accumulator, TMA-store epilogue) for "
+                                        "every projection; GEMMs of <= 2304 rows (latency-bound) on cuBLAS fp32",
                                 "tcgen05": "hand-written tcgen05.mma.kind::tf32 GEMM (TMA, in-kernel 3xTF32 split, TMEM accumulator; fp32-class accuracy)",
                                 "3xtf32": "cuBLAS TF32 tensor cores on 3-way split operands (3xTF32, fp32-class accuracy)",
                                 "fp32": "cuBLAS fp32 SIMT", "tf32": "cuBLAS TF32 (reduced precision)"}[pkg.gemm.MODE], "cuda_graph": runner.graph is not None,
@@ -376,7 +377,7 @@ def main():
                          "algorithmic_bytes_per_step": int(sum(byts)), "kernel_ms_per_step": round(sum(med), 4),
                          "per_layer_us": [round(1000 * x, 1) for x in med]},
             # secondary leg: the dense projections (tensor-bound; 3xTF32 issues 3 TF32 MMA passes per logical product)
-            "roofline_gemm": {"bound": "tensor", "kernels": "sdetr::gemm_3xtf32_p_kernel + cuBLAS TF32 (wide K=256 GEMMs)",
+            "roofline_gemm": {"bound": "tensor", "kernels": "sdetr::gemm_3xtf32_p_kernel<presplit> (+ cuBLAS fp32 for <= 2304-row GEMMs)",
                               "achieved": round(gemm_exec, 1), "peak": round(tf32_peak, 1),
                               "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 dense = half the bf16 rate)",
                               "unit": "TFLOP/s", "frac": round(gemm_exec / tf32_peak, 4),

@@ -269,6 +269,10 @@ int sdetr_gemm_set_trace(long long *device_buffer);
 int sdetr_split_tf32_pair(const float *w, int64_t count, float *w_hi, float *w_lo, sdetr_stream_t stream);
 int sdetr_gemm_3xtf32(const float *A, int64_t lda, const float *W_hi, const float *W_lo, const float *bias, float *C,
                       int64_t ldc, int M, int N, int K, int relu_a, sdetr_stream_t stream);
+/* Same contract as sdetr_gemm_3xtf32 (pre-split weight), on the persistent kernel: one CTA per SM walks the output
+ * tiles, the weight halves arrive as two TMA tiles per stage and only the activation is converted in the kernel. */
+int sdetr_gemm_3xtf32_pre(const float *A, int64_t lda, const float *W_hi, const float *W_lo, const float *bias, float *C,
+                          int64_t ldc, int M, int N, int K, int act, sdetr_stream_t stream);
 
 #ifdef __cplusplus
 }

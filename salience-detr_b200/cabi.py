@@ -52,6 +52,7 @@ SIGNATURES = {
     "sdetr_gemm_set_variant": (_i, [_i]),
     "sdetr_split_tf32_pair": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "sdetr_gemm_3xtf32": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "sdetr_gemm_3xtf32_pre": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
     "sdetr_flatten_tokens": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "sdetr_attention_small": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sdetr_attention_qkv": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
@@ -440,6 +441,25 @@ def gemm_3xtf32_raw(x, w, bias=None, act=0):
                                      _req(bias, "bias", torch.float32) if bias is not None else None, y.data_ptr(), ldc, M, N, K,
                                      int(act), _stream())
     _check(rc, "sdetr_gemm_3xtf32_raw")
+    y = y if ldc == N else y[:, :N]
+    return y.reshape(*x.shape[:-1], N) if ldc == N else y.unflatten(0, x.shape[:-1])
+
+
+def gemm_3xtf32_pre(x, w_hi, w_lo, bias=None, act=0):
+    """y = act(x) @ (w_hi + w_lo).T + bias on the persistent kernel with a pre-split weight (sdetr_split_tf32_pair)."""
+    K = x.shape[-1]
+    N = w_hi.shape[0]
+    if not (x.is_cuda and x.dtype == torch.float32 and x.stride(-1) == 1):
+        raise RuntimeError("gemm_3xtf32_pre needs a CUDA float32 input with unit last stride")
+    x2 = x if x.dim() == 2 else x.reshape(-1, K)
+    M = x2.shape[0]
+    ldc = (N + 3) // 4 * 4
+    y = torch.empty(M, ldc, device=x.device, dtype=torch.float32)
+    rc = lib().sdetr_gemm_3xtf32_pre(x2.data_ptr(), x2.stride(0) if M > 1 else K, _req(w_hi, "w_hi", torch.float32),
+                                     _req(w_lo, "w_lo", torch.float32),
+                                     _req(bias, "bias", torch.float32) if bias is not None else None, y.data_ptr(), ldc, M, N, K,
+                                     int(act), _stream())
+    _check(rc, "sdetr_gemm_3xtf32_pre")
     y = y if ldc == N else y[:, :N]
     return y.reshape(*x.shape[:-1], N) if ldc == N else y.unflatten(0, x.shape[:-1])
 

@@ -700,9 +700,13 @@ constexpr int kPBoxBytes = 2 * kTileBytes;                      // two 128x32 fp
 constexpr int kPSmem = kPRingBytes + kPBoxBytes + 1024 + 256;
 constexpr int kPThreads = 512;
 
+// kPre: the weight arrives pre-split (two TMA tiles W_hi / W_lo per stage, no in-kernel weight conversion): the stage's
+// shared-memory traffic drops from 144 KB (TMA 32 + convert read 32 + convert write 32 + MMA operand reads 48) to 112 KB.
+template <bool kPre>
 __global__ void __launch_bounds__(kPThreads, 1)
 gemm_3xtf32_p_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                     const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
+                     const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_c,
+                     const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *boxes = smem + kPRingBytes;
@@ -747,9 +751,10 @@ gemm_3xtf32_p_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     const int s = it % kPStages;
                     mbar_wait(empty + s, ((it / kPStages) & 1) ^ 1);
                     uint8_t *st = smem + s * kPStageBytes;
-                    mbar_expect_tx(tma_full + s, 2 * kTileBytes);
+                    mbar_expect_tx(tma_full + s, (kPre ? 3 : 2) * kTileBytes);
                     tma_load_2d(&map_a, tma_full + s, st, kb * kBK, m0);
                     tma_load_2d(&map_w, tma_full + s, st + kTileBytes, kb * kBK, n0);
+                    if (kPre) tma_load_2d(&map_w2, tma_full + s, st + 2 * kTileBytes, kb * kBK, n0);
                 }
             }
         }
@@ -792,8 +797,10 @@ gemm_3xtf32_p_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 uint8_t *stage = smem + s * kPStageBytes;
                 float4 *w = reinterpret_cast<float4 *>(stage + kTileBytes), *wlo = reinterpret_cast<float4 *>(stage + 2 * kTileBytes);
                 float4 wv[4];
+                if (!kPre) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) wv[i] = w[i * (32 * kConvWarps) + t];
+                    for (int i = 0; i < 4; ++i) wv[i] = w[i * (32 * kConvWarps) + t];
+                }
                 const uint8_t *arow = stage + r_in * 128;
                 float hi[16], lo[16];
 #pragma unroll
@@ -808,14 +815,16 @@ gemm_3xtf32_p_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     lo[4 * c] = tf32_rn(x.x - hi[4 * c]), lo[4 * c + 1] = tf32_rn(x.y - hi[4 * c + 1]);
                     lo[4 * c + 2] = tf32_rn(x.z - hi[4 * c + 2]), lo[4 * c + 3] = tf32_rn(x.w - hi[4 * c + 3]);
                 }
+                if (!kPre) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 x = wv[i];
-                    float4 h, l;
-                    h.x = tf32_rn(x.x), h.y = tf32_rn(x.y), h.z = tf32_rn(x.z), h.w = tf32_rn(x.w);
-                    l.x = tf32_rn(x.x - h.x), l.y = tf32_rn(x.y - h.y), l.z = tf32_rn(x.z - h.z), l.w = tf32_rn(x.w - h.w);
-                    w[i * (32 * kConvWarps) + t] = h;
-                    wlo[i * (32 * kConvWarps) + t] = l;
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 x = wv[i];
+                        float4 h, l;
+                        h.x = tf32_rn(x.x), h.y = tf32_rn(x.y), h.z = tf32_rn(x.z), h.w = tf32_rn(x.w);
+                        l.x = tf32_rn(x.x - h.x), l.y = tf32_rn(x.y - h.y), l.z = tf32_rn(x.z - h.z), l.w = tf32_rn(x.w - h.w);
+                        w[i * (32 * kConvWarps) + t] = h;
+                        wlo[i * (32 * kConvWarps) + t] = l;
+                    }
                 }
                 const uint32_t slot = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + 64u * (uint32_t)s + 16u * (uint32_t)half;
                 tmem_st16(slot, hi);
@@ -953,7 +962,7 @@ extern "C" int sdetr_gemm_3xtf32_raw(const float *A, int64_t lda, const float *W
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_ts2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2Smem);
         SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "gemm_3xtf32_raw: smem attribute: %s", cudaGetErrorString(e));
-        e = cudaFuncSetAttribute(gemm_3xtf32_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem);
+        e = cudaFuncSetAttribute(gemm_3xtf32_p_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem);
         SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "gemm_3xtf32_raw: smem attribute: %s", cudaGetErrorString(e));
         int dev = 0;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -962,7 +971,7 @@ extern "C" int sdetr_gemm_3xtf32_raw(const float *A, int64_t lda, const float *W
     GemmParams p{bias, C, ldc, M, N, K, act, use_tma_store, g_gemm_dbg};
     if (g_raw_persistent) {
         const int tiles = ((N + kBN - 1) / kBN) * ((M + kBM - 1) / kBM);
-        gemm_3xtf32_p_kernel<<<tiles < sms ? tiles : sms, kPThreads, kPSmem, (cudaStream_t)stream>>>(ma, mw, mc, p);
+        gemm_3xtf32_p_kernel<false><<<tiles < sms ? tiles : sms, kPThreads, kPSmem, (cudaStream_t)stream>>>(ma, mw, mw, mc, p);
         return check_launch("gemm_3xtf32_raw");
     }
     dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM);
@@ -1027,4 +1036,33 @@ extern "C" int sdetr_gemm_3xtf32(const float *A, int64_t lda, const float *W_hi,
                                     : cudaLaunchKernelEx(&cfg, gemm_3xtf32_kernel, ma, mh, ml, mc, p);
     SDETR_REQUIRE(le == cudaSuccess, SDETR_ERR_CUDA, "gemm_3xtf32: launch: %s", cudaGetErrorString(le));
     return check_launch("gemm_3xtf32");
+}
+
+// Persistent kernel on a pre-split weight (W_hi, W_lo from sdetr_split_tf32_pair, cached by the caller per parameter).
+extern "C" int sdetr_gemm_3xtf32_pre(const float *A, int64_t lda, const float *W_hi, const float *W_lo, const float *bias,
+                                     float *C, int64_t ldc, int M, int N, int K, int act, sdetr_stream_t stream) {
+    SDETR_REQUIRE(A && W_hi && W_lo && C, SDETR_ERR_INVALID_ARG, "gemm_3xtf32_pre: null pointer");
+    SDETR_REQUIRE(M >= 0 && N > 0 && K > 0 && act >= 0 && act <= 2, SDETR_ERR_INVALID_ARG, "gemm_3xtf32_pre: bad sizes / activation");
+    SDETR_REQUIRE(K % kBK == 0, SDETR_ERR_UNSUPPORTED, "gemm_3xtf32_pre: K=%d must be a multiple of %d", K, kBK);
+    SDETR_REQUIRE(lda % 4 == 0 && aligned16(A) && aligned16(W_hi) && aligned16(W_lo) && lda >= K && ldc >= N,
+                  SDETR_ERR_INVALID_ARG, "gemm_3xtf32_pre: operands must be 16-byte aligned with 16-byte row pitch");
+    if (M == 0) return SDETR_OK;
+    CUtensorMap ma, mh, ml, mc;
+    SDETR_REQUIRE(make_map(&ma, A, M, K, lda, kBM) && make_map(&mh, W_hi, N, K, K, kBN) && make_map(&ml, W_lo, N, K, K, kBN),
+                  SDETR_ERR_CUDA, "gemm_3xtf32_pre: cuTensorMapEncodeTiled failed");
+    const int use_tma_store = (ldc % 4 == 0) && aligned16(C) && make_map(&mc, C, M, N, ldc, kBM);
+    if (!use_tma_store) mc = ma;
+    static bool attr = false;
+    static int sms = 148;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_p_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem);
+        SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "gemm_3xtf32_pre: smem attribute: %s", cudaGetErrorString(e));
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        attr = true;
+    }
+    GemmParams p{bias, C, ldc, M, N, K, act, use_tma_store, g_gemm_dbg};
+    const int tiles = ((N + kBN - 1) / kBN) * ((M + kBM - 1) / kBM);
+    gemm_3xtf32_p_kernel<true><<<tiles < sms ? tiles : sms, kPThreads, kPSmem, (cudaStream_t)stream>>>(ma, mh, ml, mc, p);
+    return check_launch("gemm_3xtf32_pre");
 }

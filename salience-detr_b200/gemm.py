@@ -2,10 +2,9 @@
 
 These are true dense GEMMs, the only place of the path where tensor cores belong.  ``MODE``:
 
-* ``"auto"`` (default): per shape, whichever of the next two measured faster on B200 (tools/bench_gemm.py,
-  profiles/r1_gemm_shapes.txt): the hand-written kernel for N <= 512 or K >= 1024 (output / offset / class / FFN-2 /
-  enc_output / MaskPredictor projections), cuBLAS 3xTF32 for the wide K = 256 GEMMs (value_proj x6, FFN-1); GEMMs with
-  at most ``SMALL_M`` rows (the coarse levels of the MaskPredictor) are latency-bound and go to cuBLAS fp32.
+* ``"auto"`` (default): the hand-written persistent tcgen05 kernel on a pre-split weight (``sdetr_gemm_3xtf32_pre``; fastest
+  or tied on every shape of the path, tools/bench_gemm.py, profiles/r1_gemm_shapes.txt), except GEMMs with at most
+  ``SMALL_M`` rows (the coarse levels of the MaskPredictor), which are latency-bound and go to cuBLAS fp32.
 * ``"tcgen05"``: the hand-written sm_100a GEMM (``sdetr_gemm_3xtf32``: TMA -> in-kernel TF32 split of the activation
   -> tcgen05.mma.kind::tf32 into TMEM -> epilogue), same 3xTF32 arithmetic without the separate split pass.
 * ``"3xtf32"``: each operand is split into two TF32 pieces by ``sdetr_split_tf32`` and ONE cuBLAS TF32
@@ -28,6 +27,7 @@ from torch.nn import functional as F
 from . import cabi
 
 MODE = "auto"
+PRESPLIT_PERSISTENT = True  # persistent kernel fed a pre-split weight (W_hi / W_lo TMA tiles) instead of splitting W in the kernel
 LONG_K_PRESPLIT = False  # K >= 1024: True = "SS" kernel with the pre-split weight, False = persistent raw-weight kernel "P" (measured equal or faster)
 SMALL_M = 2304  # "auto": at most this many rows -> cuBLAS fp32 (latency-bound; measured faster than either tensor-core path, tools/bench_small.py)
 K_CHUNK = 512  # longest reduction handed to one tensor-core GEMM (its accumulator truncates: error ~ length)
@@ -88,13 +88,16 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, relu_input:
     n, k = weight.shape
     if MODE == "auto" and x.numel() // max(k, 1) <= SMALL_M:
         return F.linear(_act_torch(x, relu_input), weight, bias)
-    own = MODE == "tcgen05" or (MODE == "auto" and (n <= 512 or k >= 1024))
+    own = MODE in ("tcgen05", "auto")
     if own and k % 32 == 0 and x.stride(-1) == 1:
         x2 = x if x.dim() == 2 else x.reshape(-1, x.shape[-1])
         if x2.stride(0) % 4 == 0 or x2.shape[0] == 1:
             if k >= 1024 and LONG_K_PRESPLIT:   # long reductions: 4-stage ring, weight pre-split once (variant "SS")
                 w_hi, w_lo = split_weight_pair(weight)
                 return cabi.gemm_3xtf32(x, w_hi, w_lo, bias, relu_input)
+            if PRESPLIT_PERSISTENT:
+                w_hi, w_lo = split_weight_pair(weight)
+                return cabi.gemm_3xtf32_pre(x, w_hi, w_lo, bias, relu_input)
             # short reductions: both operands split in the kernel, A in TMEM, two CTAs per SM (variant "TS2")
             return cabi.gemm_3xtf32_raw(x, weight if weight.is_contiguous() else weight.contiguous(), bias, relu_input)
     if MODE == "fp32" or k % 4 != 0:

@@ -506,6 +506,8 @@ def test_gemm_tcgen05_3xtf32(pkg):
         assert torch.equal(y3, y)
         y4 = pkg.cabi.gemm_3xtf32_raw(x, w, b, int(relu))
         assert y4.shape == y.shape and (y4.double() - ref).abs().max() < 3e-4
+        y5 = pkg.cabi.gemm_3xtf32_pre(x, w_hi, w_lo, b, int(relu))  # persistent kernel, pre-split weight: same arithmetic
+        assert torch.equal(y5, y4)
     prev = pkg.gemm.MODE
     try:
         pkg.gemm.MODE = "tcgen05"

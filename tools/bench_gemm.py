@@ -25,10 +25,11 @@ tot = {"tcgen05": 0, "3xtf32": 0, "fp32": 0}
 for name, M, K, N, relu in shapes:
     x = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) / K ** 0.5; b = torch.randn(N, device=dev)
     r = {}
-    for mode in ("tcgen05", "tcgen05-P", "3xtf32", "fp32"):
+    for mode in ("tcgen05", "tcgen05-P", "tcgen05-PRE", "3xtf32", "fp32"):
         pkg.gemm.MODE = mode.split("-")[0]
-        pkg.gemm.LONG_K_PRESPLIT = mode != "tcgen05-P"
+        pkg.gemm.LONG_K_PRESPLIT = mode == "tcgen05"
+        pkg.gemm.PRESPLIT_PERSISTENT = mode == "tcgen05-PRE"
         r[mode] = timeit(lambda: pkg.gemm.linear(x, w, b, relu_input=bool(relu)))
         tot[mode] = tot.get(mode, 0) + r[mode]
-    print(f"{name:14s} {M:6d} {K:5d} {N:5d} | {r['tcgen05']:9.1f} | {r['tcgen05-P']:9.1f} | {r['3xtf32']:10.1f} | {r['fp32']:7.1f} | {6*M*N*K/min(r['tcgen05'], r['tcgen05-P'])/1e6:7.1f}")
+    print(f"{name:14s} {M:6d} {K:5d} {N:5d} | {r['tcgen05']:9.1f} | {r['tcgen05-P']:9.1f} | pre {r['tcgen05-PRE']:7.1f} | {r['3xtf32']:10.1f} | {r['fp32']:7.1f} | {6*M*N*K/min(r['tcgen05'], r['tcgen05-P'])/1e6:7.1f}")
 print("sum", {k: round(v, 1) for k, v in tot.items()})
