@@ -442,12 +442,24 @@ __global__ void __launch_bounds__(kMeanThreads) gelu_colsum_kernel(float *__rest
     const bool global_half = cv * 4 >= half;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (rl < lanes) {
-        for (int r = r0 + rl; r < r1; r += lanes) {
-            float *p = z + ((int64_t)b * n + r) * C + cv * 4;
-            float4 x = *reinterpret_cast<const float4 *>(p);
+        float *base = z + (int64_t)b * n * C + cv * 4;
+        int r = r0 + rl;
+        for (; r + 3 * lanes < r1; r += 4 * lanes) {  // four independent rows per iteration: loads in flight together
+            float4 x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[u] = *reinterpret_cast<const float4 *>(base + (int64_t)(r + u * lanes) * C);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                x[u].x = gelu_exact(x[u].x), x[u].y = gelu_exact(x[u].y), x[u].z = gelu_exact(x[u].z), x[u].w = gelu_exact(x[u].w);
+                if (global_half) acc.x += x[u].x, acc.y += x[u].y, acc.z += x[u].z, acc.w += x[u].w;
+                else *reinterpret_cast<float4 *>(base + (int64_t)(r + u * lanes) * C) = x[u];
+            }
+        }
+        for (; r < r1; r += lanes) {
+            float4 x = *reinterpret_cast<const float4 *>(base + (int64_t)r * C);
             x.x = gelu_exact(x.x), x.y = gelu_exact(x.y), x.z = gelu_exact(x.z), x.w = gelu_exact(x.w);
             if (global_half) acc.x += x.x, acc.y += x.y, acc.z += x.z, acc.w += x.w;
-            else *reinterpret_cast<float4 *>(p) = x;
+            else *reinterpret_cast<float4 *>(base + (int64_t)r * C) = x;
         }
     }
     red[threadIdx.x] = acc;
@@ -462,14 +474,39 @@ __global__ void __launch_bounds__(kMeanThreads) gelu_colsum_kernel(float *__rest
     }
 }
 
+// chunks_in partial sums per image (fixed order) -> mean -> broadcast over this CTA's rows
 __global__ void __launch_bounds__(kMeanThreads) colmean_broadcast_kernel(float *__restrict__ z, int n, int C, int half,
-                                                                         int chunks, const float *__restrict__ partial) {
+                                                                         int chunks_in, int chunks,
+                                                                         const float *__restrict__ partial) {
     __shared__ __align__(16) float mean[1024];
+    __shared__ __align__(16) float part[kMeanThreads / 32][1024];
     const int b = blockIdx.y, chunk = blockIdx.x, g = C - half;
-    for (int c = threadIdx.x; c < g; c += kMeanThreads) {
-        float t = 0.f;
-        for (int k = 0; k < chunks; ++k) t += __ldg(partial + ((int64_t)b * chunks + k) * g + c);
-        mean[c] = t / (float)n;
+    // every warp adds a contiguous slice of the partial rows (128-bit loads, lane <-> 4 columns), then the warps' sums
+    // are added in warp order: a fixed order, so the mean is bit-reproducible
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = kMeanThreads / 32;
+        const int per = (chunks_in + warps - 1) / warps, k0 = warp * per, k1 = min(chunks_in, k0 + per);
+        for (int c = lane * 4; c < g; c += 128) {
+            const float *p = partial + (int64_t)b * chunks_in * g + c;
+            float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+            int k = k0;
+            for (; k + 1 < k1; k += 2) {
+                const float4 x = ldg_f4(p + (int64_t)k * g), y = ldg_f4(p + (int64_t)(k + 1) * g);
+                t0.x += x.x, t0.y += x.y, t0.z += x.z, t0.w += x.w;
+                t1.x += y.x, t1.y += y.y, t1.z += y.z, t1.w += y.w;
+            }
+            if (k < k1) {
+                const float4 x = ldg_f4(p + (int64_t)k * g);
+                t0.x += x.x, t0.y += x.y, t0.z += x.z, t0.w += x.w;
+            }
+            *reinterpret_cast<float4 *>(&part[warp][c]) = make_float4(t0.x + t1.x, t0.y + t1.y, t0.z + t1.z, t0.w + t1.w);
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < g; c += kMeanThreads) {
+            float t = part[0][c];
+            for (int w = 1; w < warps; ++w) t += part[w][c];
+            mean[c] = t / (float)n;
+        }
     }
     __syncthreads();
     const int gv = g / 4, lanes = kMeanThreads / gv;
@@ -484,7 +521,7 @@ __global__ void __launch_bounds__(kMeanThreads) colmean_broadcast_kernel(float *
 
 extern "C" size_t sdetr_gelu_colmean_workspace(int batch, int num_rows, int channels, int half) {
     (void)num_rows;
-    return (size_t)batch * 148 * (size_t)(channels - half) * sizeof(float);
+    return (size_t)(batch + 1184) * (size_t)(channels - half) * sizeof(float);  // <= 1184 / batch (+1) partial rows per image
 }
 
 extern "C" int sdetr_gelu_colmean(float *z, int batch, int num_rows, int channels, int half, void *workspace,
@@ -496,16 +533,18 @@ extern "C" int sdetr_gelu_colmean(float *z, int batch, int num_rows, int channel
     SDETR_REQUIRE(channels / 4 <= kMeanThreads, SDETR_ERR_UNSUPPORTED, "gelu_colmean: channels %d > %d", channels, 4 * kMeanThreads);
     SDETR_REQUIRE(workspace_bytes >= sdetr_gelu_colmean_workspace(batch, num_rows, channels, half), SDETR_ERR_WORKSPACE,
                   "gelu_colmean: workspace too small");
-    int chunks = (num_rows + 63) / 64;  // >= 64 rows per CTA, at most one wave
-    const int cap = 148 / batch > 0 ? 148 / batch : 1;
-    if (chunks > cap) chunks = cap;
-    if (chunks < 1) chunks = 1;
+    // pass 1 is a read-modify-write stream: up to 8 resident CTAs per SM so enough loads are in flight;
+    // pass 2 only stores (and every CTA re-adds the partials), one wave is enough
+    int chunks1 = (num_rows + 31) / 32, chunks2 = (num_rows + 63) / 64;
+    const int cap1 = 592 / batch > 0 ? 592 / batch : 1, cap2 = 148 / batch > 0 ? 148 / batch : 1;
+    if (chunks1 > cap1) chunks1 = cap1;
+    if (chunks2 > cap2) chunks2 = cap2;
     cudaStream_t s = (cudaStream_t)stream;
-    gelu_colsum_kernel<<<dim3(chunks, batch), kMeanThreads, 0, s>>>(z, num_rows, channels, half, chunks, (float *)workspace);
+    gelu_colsum_kernel<<<dim3(chunks1, batch), kMeanThreads, 0, s>>>(z, num_rows, channels, half, chunks1, (float *)workspace);
     int rc = check_launch("gelu_colmean/colsum");
     if (rc) return rc;
-    colmean_broadcast_kernel<<<dim3(chunks, batch), kMeanThreads, 0, s>>>(z, num_rows, channels, half, chunks,
-                                                                          (const float *)workspace);
+    colmean_broadcast_kernel<<<dim3(chunks2, batch), kMeanThreads, 0, s>>>(z, num_rows, channels, half, chunks1, chunks2,
+                                                                           (const float *)workspace);
     return check_launch("gelu_colmean/broadcast");
 }
 

@@ -33,6 +33,7 @@ from . import cabi, gemm
 from .ms_deform_attn import MultiScaleDeformableAttention
 
 OVERLAP_VALUE_PROJ = True  # run the all-layer value projection on a side stream, concurrently with the salience filter
+FUSED_GELU_MEAN = True     # MaskPredictor: GELU + token-mean of the global half as two fused launches (else torch ops)
 FUSED_PRE_ATTENTION = True  # C = 256 / head_dim 32: gather+in-proj, attention, out-proj+LN+scatter as three kernels
 SMALL_ATTENTION = False   # hand-written 300-token attention kernel instead of SDPA (measured slower: 35 vs 30 us)
 MHA_GEMM_TENSOR_CORE = False  # pre-attention projections (M = 600 rows): cuBLAS SGEMM measured faster than the tensor-core kernels
@@ -67,7 +68,7 @@ class MaskPredictor(nn.Module):
         x = x if x.is_contiguous() else x.contiguous()
         z = gemm.linear(cabi.add_layernorm(x, None, ln.weight, ln.bias, ln.eps), fc.weight, fc.bias)
         half = self.h_dim // 2
-        if z.dim() == 3 and z.is_contiguous() and self.h_dim % 8 == 0 and self.h_dim <= 1024:
+        if FUSED_GELU_MEAN and z.dim() == 3 and z.is_contiguous() and self.h_dim % 8 == 0 and self.h_dim <= 1024:
             cabi.gelu_colmean_(z, half)  # GELU + global half = token mean, broadcast in place (:40-45), two launches
         else:
             z = F.gelu(z)

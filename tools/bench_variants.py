@@ -20,9 +20,16 @@ def step_ms(runner, n=20):
             a.record(runner.stream); runner.step(); b.record(runner.stream)
         torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
     return statistics.median(ts)
-print("small_attn mha_tc gemm_mode | ms/step")
-for sa, tc, mode in itertools.product((False, True), (False, True), ("auto", "3xtf32")):
-    st.SMALL_ATTENTION, st.MHA_GEMM_TENSOR_CORE, pkg.gemm.MODE = sa, tc, mode
+base = dict(FUSED_PRE_ATTENTION=True, FUSED_GELU_MEAN=True, PRESPLIT_PERSISTENT=True, SMALL_M=2304, OVERLAP_VALUE_PROJ=True)
+variants = [("defaults", {}), ("library pre-attention", dict(FUSED_PRE_ATTENTION=False)), ("torch gelu+mean", dict(FUSED_GELU_MEAN=False)),
+            ("in-kernel weight split", dict(PRESPLIT_PERSISTENT=False)), ("no small-M fp32 route", dict(SMALL_M=0)),
+            ("no value-proj overlap", dict(OVERLAP_VALUE_PROJ=False)), ("defaults again", {})]
+print("variant | ms/step | images/s")
+for name, over in variants:
+    cfg = dict(base, **over)
+    st.FUSED_PRE_ATTENTION, st.FUSED_GELU_MEAN, st.OVERLAP_VALUE_PROJ = cfg["FUSED_PRE_ATTENTION"], cfg["FUSED_GELU_MEAN"], cfg["OVERLAP_VALUE_PROJ"]
+    pkg.gemm.PRESPLIT_PERSISTENT, pkg.gemm.SMALL_M = cfg["PRESPLIT_PERSISTENT"], cfg["SMALL_M"]
     r = EncoderRunner(model, feats, masks, pos)
-    print(f"{int(sa)} {int(tc)} {mode:7s} | {step_ms(r):.3f}")
+    ms = step_ms(r)
+    print(f"{name:26s} | {ms:.3f} | {2000.0 / ms:.1f}")
     del r
