@@ -32,11 +32,12 @@ from torch.nn import functional as F
 from . import cabi, gemm
 from .ms_deform_attn import MultiScaleDeformableAttention
 
-OVERLAP_VALUE_PROJ = True  # run the all-layer value projection on a side stream, concurrently with the salience filter
+OVERLAP_VALUE_PROJ = True  # inside a graph capture: all-layer value projection as a parallel branch beside the salience filter
 FUSED_GELU_MEAN = True     # MaskPredictor: GELU + token-mean of the global half as two fused launches (else torch ops)
 FUSED_PRE_ATTENTION = True  # C = 256 / head_dim 32: gather+in-proj, attention, out-proj+LN+scatter as three kernels
-SMALL_ATTENTION = False   # hand-written 300-token attention kernel instead of SDPA (measured slower: 35 vs 30 us)
-MHA_GEMM_TENSOR_CORE = False  # pre-attention projections (M = 600 rows): cuBLAS SGEMM measured faster than the tensor-core kernels
+# only for geometries the fused pre-attention does not cover (C != 256 or head_dim != 32):
+SMALL_ATTENTION = False   # sdetr_attention_small instead of SDPA between the library projections
+MHA_GEMM_TENSOR_CORE = False  # projections of the 600 rows on the tensor-core GEMM instead of cuBLAS SGEMM (latency-bound: slower)
 TILE_CELL_PX = 64   # edge (image pixels) of the spatial cells that define the MSDA processing order
 MSDA_SCHEDULE = 1   # 0 = query-major, 1 = head-major chunks (see include/sdetr_b200.h)
 
