@@ -205,7 +205,8 @@ int sdetr_flatten_tokens(const float *const *feats_host, const float *const *pos
 
 /* Dense self-attention core of the 300-token pre-attention (salience_transformer.py:372-376; the attention inside
  * nn.MultiheadAttention): out = softmax(Q K^T / sqrt(d)) V per (image, head).  qk (b,n,2,heads,d): projected queries
- * then keys; v (b,n,heads,d); out (b,n,heads*d).  head_dim must be 32; n limited by shared memory (~750). */
+ * then keys; v (b,n,heads,d); out (b,n,heads*d).  head_dim must be 32; K^T, V and the score tile live in shared memory:
+ * n up to ~460, larger n returns SDETR_ERR_UNSUPPORTED. */
 int sdetr_attention_small(const float *qk, const float *v, float *out, int batch, int n, int heads, int head_dim,
                           sdetr_stream_t stream);
 /* Same core on a packed projection buffer qkv (b,n,3,heads,d) (what sdetr_mha_in_proj writes). */
