@@ -142,12 +142,13 @@ int sdetr_topk_desc(const float *score, int segments, int n, int k, int64_t *top
 /* Fused four-way gather (:454-461).  inds: int64, row stride inds_stride (a prefix view of selected_inds).
  * tokens/pos (b,Nv,C), fg (b,Nv), valid_ratios (b,L,2) ->
  * query (b,Nq,C), query_pos (b,Nq,C), fg_q (b,Nq), ref_q (b,Nq,L,2) where ref_q is the gathered row of
- * get_reference_points (:417-432), recomputed from the token's (level,y,x) with identical fp32 arithmetic. */
+ * get_reference_points (:417-432), recomputed from the token's (level,y,x) with identical fp32 arithmetic.
+ * query_sum (b,Nq,C), may be NULL: query + query_pos, the `with_pos_embed` input of the layer's attention (:381). */
 int sdetr_token_gather(const float *tokens, const float *pos, const float *fg, const float *valid_ratios,
                        const int64_t *inds, int64_t inds_stride, const int64_t *spatial_shapes,
                        const int64_t *level_start_index, int batch, int num_value, int channels,
                        int num_levels, int num_query, float *query, float *query_pos, float *fg_q,
-                       float *ref_q, sdetr_stream_t stream);
+                       float *ref_q, float *query_sum, sdetr_stream_t stream);
 
 /* In-place scatter-back (:474-485): tokens[b, inds[b,q], :] = query[b,q,:] for q < min(focus[b], Nq).
  * focus_token_nums (b) int32 on the device (no host sync, unlike the reference's per-image slicing). */
@@ -223,10 +224,13 @@ int sdetr_mha_in_proj(const float *tokens, const float *pos, const int64_t *inde
 
 /* Pre-attention back (salience_transformer.py:373-379): y = LayerNorm(t + attn Wo^T + bo) with (gamma, beta, eps);
  * dst[b,index[b,j],:] = y[b,j,:] (indices unique per image).  attn, t (b,k,C); w_out_t = out_proj.weight TRANSPOSED
- * (C,C); dst (b,num_rows,C), updated in place.  channels must be 256. */
+ * (C,C); dst (b,num_rows,C), updated in place.  channels must be 256.
+ * Optional (both or neither): pos (b,num_rows,C) and dst_sum (b,num_rows,C) -- the same rows of dst_sum receive
+ * y + pos[b,index[b,j],:], keeping a `query + query_pos` buffer (sdetr_token_gather's query_sum) current. */
 int sdetr_mha_out_proj_ln_scatter(const float *attn, const float *t, const float *w_out_t, const float *b_out,
                                   const float *gamma, const float *beta, float eps, const int64_t *index, float *dst,
-                                  int batch, int num_rows, int k, int channels, sdetr_stream_t stream);
+                                  const float *pos, float *dst_sum, int batch, int num_rows, int k, int channels,
+                                  sdetr_stream_t stream);
 
 /* Row gather / scatter by per-image index (the top-k tokens of the pre-attention, salience_transformer.py:368-379):
  * out[b,j,:] = src[b,index[b,j],:]   /   dst[b,index[b,j],:] = src[b,j,:]  (indices unique per image).

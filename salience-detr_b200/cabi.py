@@ -37,7 +37,7 @@ SIGNATURES = {
     "sdetr_order_prefixes": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "sdetr_topk_workspace": (_sz, [_i, _i]),
     "sdetr_topk_desc": (_i, [_vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
-    "sdetr_token_gather": (_i, [_vp] * 5 + [_i64, _vp, _vp] + [_i] * 5 + [_vp] * 5),
+    "sdetr_token_gather": (_i, [_vp] * 5 + [_i64, _vp, _vp] + [_i] * 5 + [_vp] * 6),
     "sdetr_token_scatter": (_i, [_vp, _vp, _vp, _i64, _vp] + [_i] * 4 + [_vp]),
     "sdetr_background_embed": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp] + [_i] * 4 + [_vp, _vp]),
     "sdetr_score_modulate": (_i, [_vp, _i64, _vp, _i64, _vp] + [_i] * 7 + [_vp, _vp]),
@@ -57,7 +57,7 @@ SIGNATURES = {
     "sdetr_attention_small": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sdetr_attention_qkv": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "sdetr_mha_in_proj": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
-    "sdetr_mha_out_proj_ln_scatter": (_i, [_vp] * 6 + [_f, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "sdetr_mha_out_proj_ln_scatter": (_i, [_vp] * 6 + [_f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sdetr_rows_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "sdetr_rows_gather_add": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "sdetr_rows_scatter": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
@@ -246,7 +246,8 @@ def _inds_view(inds, num_query):
     return inds.data_ptr(), inds.stride(0)
 
 
-def token_gather(tokens, pos, fg, valid_ratios, inds, spatial_shapes, level_start_index, num_query):
+def token_gather(tokens, pos, fg, valid_ratios, inds, spatial_shapes, level_start_index, num_query, want_sum=False):
+    """-> (query, query_pos, fg_q, ref_q[, query + query_pos])"""
     b, nv, c = tokens.shape
     L = spatial_shapes.shape[0]
     dev = tokens.device
@@ -254,14 +255,15 @@ def token_gather(tokens, pos, fg, valid_ratios, inds, spatial_shapes, level_star
     qp = torch.empty(b, num_query, c, device=dev, dtype=torch.float32)
     fq = torch.empty(b, num_query, device=dev, dtype=torch.float32)
     rq = torch.empty(b, num_query, L, 2, device=dev, dtype=torch.float32)
+    qs = torch.empty(b, num_query, c, device=dev, dtype=torch.float32) if want_sum else None
     ip, istride = _inds_view(inds, num_query)
     rc = lib().sdetr_token_gather(
         _req(tokens, "tokens", torch.float32), _req(pos, "pos", torch.float32), _req(fg, "fg", torch.float32),
         _req(valid_ratios, "valid_ratios", torch.float32), ip, istride, _req(spatial_shapes, "spatial_shapes", torch.int64),
         _req(level_start_index, "level_start_index", torch.int64), b, nv, c, L, num_query, q.data_ptr(), qp.data_ptr(),
-        fq.data_ptr(), rq.data_ptr(), _stream())
+        fq.data_ptr(), rq.data_ptr(), qs.data_ptr() if want_sum else None, _stream())
     _check(rc, "sdetr_token_gather")
-    return q, qp, fq, rq
+    return (q, qp, fq, rq, qs) if want_sum else (q, qp, fq, rq)
 
 
 def token_scatter_(tokens, query, inds, focus_token_nums):
@@ -511,8 +513,9 @@ def mha_in_proj(tokens, pos, index, w_in_t, b_in):
     return t, qkv
 
 
-def mha_out_proj_ln_scatter_(dst, attn, t, w_out_t, b_out, gamma, beta, eps: float, index):
-    """dst (b,nq,C) <- LayerNorm(t + attn @ w_out_t + b_out) at index (b,k), in place."""
+def mha_out_proj_ln_scatter_(dst, attn, t, w_out_t, b_out, gamma, beta, eps: float, index, pos=None, dst_sum=None):
+    """dst (b,nq,C) <- LayerNorm(t + attn @ w_out_t + b_out) at index (b,k), in place; with pos / dst_sum (b,nq,C) the
+    same rows of dst_sum receive the new row + pos."""
     b, nq, c = dst.shape
     k = index.shape[1]
     if tuple(w_out_t.shape) != (c, c):
@@ -520,7 +523,9 @@ def mha_out_proj_ln_scatter_(dst, attn, t, w_out_t, b_out, gamma, beta, eps: flo
     rc = lib().sdetr_mha_out_proj_ln_scatter(
         _req(attn, "attn", torch.float32), _req(t, "t", torch.float32), _req(w_out_t, "w_out_t", torch.float32),
         _req(b_out, "b_out", torch.float32), _req(gamma, "gamma", torch.float32), _req(beta, "beta", torch.float32),
-        float(eps), _req(index, "index", torch.int64), _req(dst, "dst", torch.float32), b, nq, k, c, _stream())
+        float(eps), _req(index, "index", torch.int64), _req(dst, "dst", torch.float32),
+        _req(pos, "pos", torch.float32) if pos is not None else None,
+        _req(dst_sum, "dst_sum", torch.float32) if dst_sum is not None else None, b, nq, k, c, _stream())
     _check(rc, "sdetr_mha_out_proj_ln_scatter")
     return dst
 

@@ -251,7 +251,8 @@ __global__ void __launch_bounds__(kOutThreads) mha_out_proj_ln_scatter_kernel(
     const float *__restrict__ attn /* (rows, C) */, const float *__restrict__ t /* (rows, C) */,
     const float *__restrict__ w_t /* (C, C) */, const float *__restrict__ bias, const float *__restrict__ gamma,
     const float *__restrict__ beta, float eps, const int64_t *__restrict__ index, float *__restrict__ dst /* (b, nq, C) */,
-    int nq, int k, int rows) {
+    const float *__restrict__ pos /* (b, nq, C) or null */, float *__restrict__ dst_sum /* (b, nq, C) or null */, int nq,
+    int k, int rows) {
     static_assert(C == 256, "thread mapping assumes 64 column groups of 4");
     extern __shared__ __align__(16) float sm_out[];
     float *At = sm_out;                          // [C][8]: At[kk][row]
@@ -348,7 +349,8 @@ __global__ void __launch_bounds__(kOutThreads) mha_out_proj_ln_scatter_kernel(
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
         const float rstd = rsqrtf(ss / (float)C + eps);
         const int b = r / k;
-        float *drow = dst + ((int64_t)b * nq + __ldg(index + r)) * C;
+        const int64_t drow_off = ((int64_t)b * nq + __ldg(index + r)) * C;
+        float *drow = dst + drow_off;
 #pragma unroll
         for (int i = 0; i < C / 128; ++i) {
             const int c = i * 128 + lane * 4;
@@ -357,6 +359,10 @@ __global__ void __launch_bounds__(kOutThreads) mha_out_proj_ln_scatter_kernel(
             o.x = (vv[i].x - mean) * rstd * g.x + bt.x, o.y = (vv[i].y - mean) * rstd * g.y + bt.y;
             o.z = (vv[i].z - mean) * rstd * g.z + bt.z, o.w = (vv[i].w - mean) * rstd * g.w + bt.w;
             *reinterpret_cast<float4 *>(drow + c) = o;
+            if (dst_sum) {  // keep the layer's `query + query_pos` buffer current for the rewritten rows
+                const float4 pp = ldg_f4(pos + drow_off + c);
+                *reinterpret_cast<float4 *>(dst_sum + drow_off + c) = make_float4(o.x + pp.x, o.y + pp.y, o.z + pp.z, o.w + pp.w);
+            }
         }
     }
 }
@@ -447,11 +453,13 @@ extern "C" int sdetr_attention_qkv(const float *qkv, float *out, int batch, int 
 
 extern "C" int sdetr_mha_out_proj_ln_scatter(const float *attn, const float *t, const float *w_out_t, const float *b_out,
                                              const float *gamma, const float *beta, float eps, const int64_t *index,
-                                             float *dst, int batch, int num_rows, int k, int channels,
-                                             sdetr_stream_t stream) {
+                                             float *dst, const float *pos, float *dst_sum, int batch, int num_rows, int k,
+                                             int channels, sdetr_stream_t stream) {
     SDETR_REQUIRE(attn && t && w_out_t && b_out && gamma && beta && index && dst, SDETR_ERR_INVALID_ARG,
                   "mha_out_proj_ln_scatter: null pointer");
     SDETR_REQUIRE(batch > 0 && num_rows > 0 && k >= 0 && k <= num_rows, SDETR_ERR_INVALID_ARG, "mha_out_proj_ln_scatter: bad sizes");
+    SDETR_REQUIRE((pos == nullptr) == (dst_sum == nullptr) && aligned16(pos) && aligned16(dst_sum), SDETR_ERR_INVALID_ARG,
+                  "mha_out_proj_ln_scatter: pos and dst_sum go together (16-byte aligned)");
     SDETR_REQUIRE(channels == 256, SDETR_ERR_UNSUPPORTED, "mha_out_proj_ln_scatter: channels %d (only 256)", channels);
     SDETR_REQUIRE(aligned16(attn) && aligned16(t) && aligned16(w_out_t) && aligned16(b_out) && aligned16(gamma) && aligned16(beta) &&
                       aligned16(dst),
@@ -467,6 +475,6 @@ extern "C" int sdetr_mha_out_proj_ln_scatter(const float *attn, const float *t, 
         attr = true;
     }
     mha_out_proj_ln_scatter_kernel<C><<<(rows + kOutRows - 1) / kOutRows, kOutThreads, smem, (cudaStream_t)stream>>>(
-        attn, t, w_out_t, b_out, gamma, beta, eps, index, dst, num_rows, k, rows);
+        attn, t, w_out_t, b_out, gamma, beta, eps, index, dst, pos, dst_sum, num_rows, k, rows);
     return check_launch("mha_out_proj_ln_scatter");
 }

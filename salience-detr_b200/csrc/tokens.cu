@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(kRowThreads) token_gather_kernel(
     const float *__restrict__ tokens, const float *__restrict__ pos, const float *__restrict__ fg,
     const float *__restrict__ vr, const int64_t *__restrict__ inds, int64_t inds_stride,
     const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi, int batch, int nv, int C, int L, int nq,
-    float *__restrict__ query, float *__restrict__ query_pos, float *__restrict__ fg_q, float *__restrict__ ref_q) {
+    float *__restrict__ query, float *__restrict__ query_pos, float *__restrict__ fg_q, float *__restrict__ ref_q,
+    float *__restrict__ query_sum /* may be null */) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
     if (row >= (int64_t)batch * nq) return;
@@ -63,6 +64,10 @@ __global__ void __launch_bounds__(kRowThreads) token_gather_kernel(
         if (two) a1 = ld_stream_f4(src_t + c + 128), p1 = ld_stream_f4(src_p + c + 128);
         st_stream_f4(dst_t + c, a0), st_stream_f4(dst_p + c, p0);
         if (two) st_stream_f4(dst_t + c + 128, a1), st_stream_f4(dst_p + c + 128, p1);
+        if (query_sum) {
+            st_stream_f4(query_sum + row * C + c, make_float4(a0.x + p0.x, a0.y + p0.y, a0.z + p0.z, a0.w + p0.w));
+            if (two) st_stream_f4(query_sum + row * C + c + 128, make_float4(a1.x + p1.x, a1.y + p1.y, a1.z + p1.z, a1.w + p1.w));
+        }
     }
     if (lane == 0) fg_q[row] = __ldg(fg + (int64_t)b * nv + t);
     // reference points (:417-432): ((x+.5)/(vr_x*W), (y+.5)/(vr_y*H)) of the token's own level, times every
@@ -260,7 +265,7 @@ extern "C" int sdetr_token_gather(const float *tokens, const float *pos, const f
                                   const int64_t *inds, int64_t inds_stride, const int64_t *spatial_shapes,
                                   const int64_t *level_start_index, int batch, int num_value, int channels,
                                   int num_levels, int num_query, float *query, float *query_pos, float *fg_q,
-                                  float *ref_q, sdetr_stream_t stream) {
+                                  float *ref_q, float *query_sum, sdetr_stream_t stream) {
     SDETR_REQUIRE(tokens && pos && fg && valid_ratios && inds && spatial_shapes && level_start_index && query &&
                       query_pos && fg_q && ref_q,
                   SDETR_ERR_INVALID_ARG, "token_gather: null pointer");
@@ -271,7 +276,7 @@ extern "C" int sdetr_token_gather(const float *tokens, const float *pos, const f
     if (num_query == 0) return SDETR_OK;
     token_gather_kernel<<<row_blocks((int64_t)batch * num_query), kRowThreads, 0, (cudaStream_t)stream>>>(
         tokens, pos, fg, valid_ratios, inds, inds_stride, spatial_shapes, level_start_index, batch, num_value, channels,
-        num_levels, num_query, query, query_pos, fg_q, ref_q);
+        num_levels, num_query, query, query_pos, fg_q, ref_q, query_sum);
     return check_launch("token_gather");
 }
 

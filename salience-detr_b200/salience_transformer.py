@@ -34,6 +34,7 @@ from .ms_deform_attn import MultiScaleDeformableAttention
 
 OVERLAP_VALUE_PROJ = True  # inside a graph capture: all-layer value projection as a parallel branch beside the salience filter
 FUSED_GELU_MEAN = True     # MaskPredictor: GELU + token-mean of the global half as two fused launches (else torch ops)
+FUSED_QUERY_SUM = True     # `query + query_pos` written by the gather and kept current by the fused pre-attention (no add kernel)
 FUSED_PRE_ATTENTION = True  # C = 256 / head_dim 32: gather+in-proj, attention, out-proj+LN+scatter as three kernels
 # only for geometries the fused pre-attention does not cover (C != 256 or head_dim != 32):
 SMALL_ATTENTION = False   # sdetr_attention_small instead of SDPA between the library projections
@@ -191,7 +192,7 @@ class SalienceTransformerEncoderLayer(nn.Module):
             self._mha_t_key = key
         return self._mha_t
 
-    def _pre_attention_fast(self, q, qp, mc):
+    def _pre_attention_fast(self, q, qp, mc, qs=None):
         """Top-k salient tokens -> MHA -> LN -> scatter (reference :366-379).  C = 256, head_dim = 32 (every reference
         config): three fused fp32 kernels (csrc/mha_small.cu); other geometries: library projections / SDPA between
         the fused gather / residual+LN / scatter kernels."""
@@ -203,8 +204,8 @@ class SalienceTransformerEncoderLayer(nn.Module):
             t, qkv = cabi.mha_in_proj(q, qp, top, w_in_t, self.pre_attention.in_proj_bias)
             o = cabi.attention_qkv(qkv, self.n_heads)
             cabi.mha_out_proj_ln_scatter_(q, o, t, w_out_t, self.pre_attention.out_proj.bias, self.pre_norm.weight,
-                                          self.pre_norm.bias, self.pre_norm.eps, top)
-            return q
+                                          self.pre_norm.bias, self.pre_norm.eps, top, qp if qs is not None else None, qs)
+            return q, qs
         t, x = cabi.rows_gather_add(q, qp, top)           # t = q[top], x = t + qp[top]
         wqk, bqk, wv, bv = self._mha_views()
         h, d = self.n_heads, c // self.n_heads
@@ -219,12 +220,13 @@ class SalienceTransformerEncoderLayer(nn.Module):
         o = lin(o, self.pre_attention.out_proj.weight, self.pre_attention.out_proj.bias)
         t = cabi.add_layernorm(t, o, self.pre_norm.weight, self.pre_norm.bias, self.pre_norm.eps)
         cabi.rows_scatter_(q, top, t)  # q is this layer's private gather buffer
-        return q
+        return q, None
 
     def forward_fast(self, q, qp, mc, ref_q, vbuf, v_bstride, v_tstride, v_off, num_value, spatial_shapes,
-                     level_start_index, order=None, schedule=MSDA_SCHEDULE):
-        q = self._pre_attention_fast(q, qp, mc)
-        a = self.self_attn.forward_projected(q + qp, ref_q, vbuf, v_bstride, v_tstride, v_off, num_value, spatial_shapes,
+                     level_start_index, order=None, schedule=MSDA_SCHEDULE, qs=None):
+        """``qs``: optional q + qp buffer (from the gather); the fused pre-attention keeps its rewritten rows current."""
+        q, qs = self._pre_attention_fast(q, qp, mc, qs)
+        a = self.self_attn.forward_projected(qs if qs is not None else q + qp, ref_q, vbuf, v_bstride, v_tstride, v_off, num_value, spatial_shapes,
                                              level_start_index, order, schedule)
         q = cabi.add_layernorm(q, a, self.norm1.weight, self.norm1.bias, self.norm1.eps, out=q)
         h = gemm.linear(q, self.linear1.weight, self.linear1.bias)
@@ -305,10 +307,14 @@ class SalienceTransformerEncoder(nn.Module):
         for j, layer in enumerate(self.layers):
             inds = foreground_inds[j]
             nq = inds.shape[1]
-            q, qp, fq, rq = cabi.token_gather(out, pos, fg, vr, inds, spatial_shapes, level_start_index, nq)
+            qs = None
+            if FUSED_QUERY_SUM:
+                q, qp, fq, rq, qs = cabi.token_gather(out, pos, fg, vr, inds, spatial_shapes, level_start_index, nq, want_sum=True)
+            else:
+                q, qp, fq, rq = cabi.token_gather(out, pos, fg, vr, inds, spatial_shapes, level_start_index, nq)
             mc = cabi.class_max_times_fg(gemm.linear(q, self.enhance_mcsp.weight, self.enhance_mcsp.bias), fq)
             q = layer.forward_fast(q, qp, mc, rq, vbuf, nv * wide, wide, j * c, nv, spatial_shapes, level_start_index,
-                                   None if query_orders is None else query_orders[j])
+                                   None if query_orders is None else query_orders[j], qs=qs)
             cabi.token_scatter_(out, q, inds, focus)
         if multi_level_masks is not None:
             cabi.background_embed_(out, mask_u8, inds, self.background_embedding.row_embed.weight,

@@ -248,6 +248,8 @@ def test_gather_scatter_background(pkg, C):
     q, qp, fq, rq = pkg.cabi.token_gather(d(tokens), d(pos), d(fg), d(vr), sel_d[:, :nq], d(st), d(lsi), nq)
     assert torch.equal(q.cpu(), wq) and torch.equal(qp.cpu(), wqp) and torch.equal(fq.cpu(), wfq)
     assert torch.equal(rq.cpu(), wrq)  # same fp32 operations as the reference -> bit-exact
+    q2, qp2, fq2, rq2, qs = pkg.cabi.token_gather(d(tokens), d(pos), d(fg), d(vr), sel_d[:, :nq], d(st), d(lsi), nq, want_sum=True)
+    assert torch.equal(q2, q) and torch.equal(qp2, qp) and torch.equal(qs.cpu(), wq + wqp)  # + the `with_pos_embed` sum
     # reference-points table of the reference (:417-432) gathered the reference's way
     table = orc.reference_points(shapes, vr)
     want_rq = table.view(b, nv, -1).gather(1, inds[..., None].expand(-1, -1, 8)).view(b, nq, 4, 2)
@@ -371,6 +373,11 @@ def test_fused_pre_attention_vs_torch_mha(pkg):
         pkg.cabi.mha_out_proj_ln_scatter_(out, o, t_g, d(mha.out_proj.weight.t()), d(mha.out_proj.bias), d(ln.weight),
                                           d(ln.bias), ln.eps, d(top))
         assert (out.cpu().double() - want).abs().max() < 5e-5, (b, nq, k)
+        # with a `query + pos` side buffer: the rewritten rows (and only those) are refreshed
+        out2, qs = d(q).clone(), d(q + qp)
+        pkg.cabi.mha_out_proj_ln_scatter_(out2, o, t_g, d(mha.out_proj.weight.t()), d(mha.out_proj.bias), d(ln.weight),
+                                          d(ln.bias), ln.eps, d(top), d(qp), qs)
+        assert torch.equal(out2, out) and torch.equal(qs, out + d(qp))
 
 
 def test_rows_gather_scatter(pkg):

@@ -20,14 +20,16 @@ def step_ms(runner, n=20):
             a.record(runner.stream); runner.step(); b.record(runner.stream)
         torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
     return statistics.median(ts)
-base = dict(FUSED_PRE_ATTENTION=True, FUSED_GELU_MEAN=True, PRESPLIT_PERSISTENT=True, SMALL_M=2304, OVERLAP_VALUE_PROJ=True)
-variants = [("defaults", {}), ("library pre-attention", dict(FUSED_PRE_ATTENTION=False)), ("torch gelu+mean", dict(FUSED_GELU_MEAN=False)),
+base = dict(FUSED_QUERY_SUM=True, FUSED_PRE_ATTENTION=True, FUSED_GELU_MEAN=True, PRESPLIT_PERSISTENT=True, SMALL_M=2304, OVERLAP_VALUE_PROJ=True)
+variants = [("defaults", {}), ("separate q+pos add", dict(FUSED_QUERY_SUM=False)), ("defaults (2)", {}), ("separate q+pos add (2)", dict(FUSED_QUERY_SUM=False)),
+            ("library pre-attention", dict(FUSED_PRE_ATTENTION=False)), ("torch gelu+mean", dict(FUSED_GELU_MEAN=False)),
             ("in-kernel weight split", dict(PRESPLIT_PERSISTENT=False)), ("no small-M fp32 route", dict(SMALL_M=0)),
             ("no value-proj overlap", dict(OVERLAP_VALUE_PROJ=False)), ("defaults again", {})]
 print("variant | ms/step | images/s")
 for name, over in variants:
     cfg = dict(base, **over)
     st.FUSED_PRE_ATTENTION, st.FUSED_GELU_MEAN, st.OVERLAP_VALUE_PROJ = cfg["FUSED_PRE_ATTENTION"], cfg["FUSED_GELU_MEAN"], cfg["OVERLAP_VALUE_PROJ"]
+    st.FUSED_QUERY_SUM = cfg["FUSED_QUERY_SUM"]
     pkg.gemm.PRESPLIT_PERSISTENT, pkg.gemm.SMALL_M = cfg["PRESPLIT_PERSISTENT"], cfg["SMALL_M"]
     r = EncoderRunner(model, feats, masks, pos)
     ms = step_ms(r)
