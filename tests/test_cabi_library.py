@@ -78,3 +78,26 @@ def test_product_path_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("the oracle (torch leaves it unspecified)", "").replace(
                     "shared with the oracle", ""), os.path.join(dirpath, f)
+
+
+def test_argument_validation_of_the_later_entry_points(pkg):
+    """Shape / bound checks run on the host before any CUDA call, so they are testable without a GPU."""
+    lib = pkg.cabi.lib()
+    buf = (ctypes.c_float * 1024)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    # a feature map larger than the learned embedding tables is an index error in the reference (nn.Embedding)
+    shapes = (ctypes.c_int64 * 4)(4, 12, 2, 6)
+    rc = lib.sdetr_background_embed(p, p, p, 1, 1, p, p, 8, p, ctypes.cast(shapes, ctypes.c_void_p), p, 1, 60, 64, 2, p, None)
+    assert rc == -1 and b"embedding tables hold 8" in lib.sdetr_last_error()
+    # the fused pre-attention kernels are specialised for the reference's width
+    rc = lib.sdetr_mha_in_proj(p, p, p, 1, 10, 5, 128, p, p, p, p, None)
+    assert rc != 0 and b"only 256" in lib.sdetr_last_error()
+    rc = lib.sdetr_mha_out_proj_ln_scatter(p, p, p, p, p, p, 1e-5, p, p, p, None, 1, 10, 5, 256, None)
+    assert rc == -1 and b"go together" in lib.sdetr_last_error()
+    rc = lib.sdetr_attention_qkv(p, p, 1, 10, 2, 64, None)
+    assert rc != 0 and b"head_dim 64" in lib.sdetr_last_error()
+    rc = lib.sdetr_gelu_colmean(p, 1, 10, 30, 16, p, 1 << 20, None)
+    assert rc == -1 and b"bad sizes" in lib.sdetr_last_error()
+    assert lib.sdetr_gelu_colmean_workspace(2, 16800, 256, 128) >= 2 * 296 * 128 * 4
+    rc = lib.sdetr_gemm_3xtf32_pre(p, 40, p, p, None, p, 8, 4, 8, 40, 0, None)
+    assert rc != 0 and b"multiple of 32" in lib.sdetr_last_error()

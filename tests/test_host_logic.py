@@ -68,3 +68,19 @@ def test_msda_module_init_matches_reference_golden_shapes():
     assert torch.allclose(b[0, 0, :, 0], torch.tensor([1.0, 2.0, 3.0, 4.0])) and b[0, 0, :, 1].abs().max() < 1e-6
     assert m.sampling_offsets.weight.abs().max() == 0 and m.attention_weights.weight.abs().max() == 0
     assert m.im2col_step == 64
+
+
+def test_mha_transposed_weight_cache_follows_parameter_updates():
+    """The fused pre-attention consumes in_proj_weight^T / out_proj.weight^T; the cache must refresh when the
+    parameters are modified in place (optimizer step) or replaced (load_state_dict)."""
+    import salience_detr_b200 as pkg
+    layer = pkg.SalienceTransformerEncoderLayer(embed_dim=64, d_ffn=128, dropout=0.0, n_heads=2, n_levels=4, n_points=4, topk_sa=10)
+    w_in_t, w_out_t = layer._mha_transposed()
+    assert w_in_t.shape == (64, 192) and torch.equal(w_in_t, layer.pre_attention.in_proj_weight.detach().t())
+    assert layer._mha_transposed()[0] is w_in_t  # cached
+    with torch.no_grad():
+        layer.pre_attention.in_proj_weight.add_(1.0)
+        layer.pre_attention.out_proj.weight.mul_(2.0)
+    w_in_t2, w_out_t2 = layer._mha_transposed()
+    assert w_in_t2 is not w_in_t and torch.equal(w_in_t2, layer.pre_attention.in_proj_weight.detach().t())
+    assert torch.equal(w_out_t2, layer.pre_attention.out_proj.weight.detach().t())
