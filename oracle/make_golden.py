@@ -130,6 +130,59 @@ def make_encoder_tiny(name, image_sizes, padded, seed):
         **arrs, **sd)
 
 
+C256 = dict(embed_dim=256, d_ffn=256, n_heads=8, n_levels=4, n_points=4, num_layers=2, num_classes=11,
+            level_filter_ratio=(0.4, 0.8, 1.0, 1.0), layer_filter_ratio=(1.0, 0.5), topk_sa=64,
+            max_num_embedding=80, num_proposals=30)
+C256_IMAGES, C256_PADDED, C256_SEED, C256_ROWS = [(384, 512), (384, 512)], (384, 512), 11, 256
+
+
+def encoder_half_keys(state_dict):
+    return {k: tuple(v.shape) for k, v in state_dict.items()
+            if not (k.startswith("decoder") or k.startswith("tgt_embed") or k.startswith("encoder_bbox_head")
+                    or k.endswith("_filter_ratio"))}
+
+
+def make_encoder_c256(name="encoder_c256.npz"):
+    """Reference width (C = 256, 8 heads of 32) at 4080 tokens per image: exercises the paths that are specialised for
+    the real model (fused pre-attention, persistent tensor-core GEMM).  Weights come from
+    oracle.deterministic_state_dict (regenerated by the tests), inputs from oracle.synthetic_inputs; the fixture holds
+    the reference's outputs: selection, scores, and the encoder memory at C256_ROWS sampled tokens per image plus
+    per-token channel means of all tokens."""
+    import json
+    tr = ref_import.build_transformer(seed=0, **C256)
+    shapes = encoder_half_keys(tr.state_dict())
+    missing = tr.load_state_dict(orc.deterministic_state_dict(shapes, C256_SEED), strict=False)
+    assert not [k for k in missing.unexpected_keys]
+    feats, masks, pos = orc.synthetic_inputs(C256_IMAGES, C256_PADDED, C256["embed_dim"], seed=C256_SEED)
+    captured = {}
+    enc_fwd = tr.encoder.forward
+
+    def spy(**kw):
+        captured.update(kw)
+        captured["memory"] = enc_fwd(**kw)
+        raise _Stop()
+
+    tr.encoder.forward = spy
+    try:
+        with torch.no_grad():
+            tr(feats, masks, pos, None, None, None)
+    except _Stop:
+        pass
+    mem = captured["memory"]
+    nv = mem.shape[1]
+    rows = torch.stack([torch.randperm(nv, generator=torch.Generator().manual_seed(100 + i))[:C256_ROWS] for i in range(mem.shape[0])])
+    np.savez_compressed(
+        os.path.join(OUT, name),
+        shapes_json=np.array(json.dumps({k: list(v) for k, v in shapes.items()})),
+        memory_rows_index=np_(rows),
+        memory_rows=np_(torch.gather(mem, 1, rows[..., None].expand(-1, -1, mem.shape[2]))),
+        memory_row_mean=np_(mem.mean(-1)), memory_row_absmax=np_(mem.abs().amax(-1)),
+        foreground_score=np_(captured["foreground_score"]),
+        focus_token_nums=np_(captured["focus_token_nums"]),
+        selected_inds=np_(captured["foreground_inds"][0]),
+        layer_num_query=np.array([x.shape[1] for x in captured["foreground_inds"]]))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     make_msda_core("msda_core_a.npz", b=2, shapes=[(10, 12), (5, 6), (3, 3), (2, 2)], m=4, d=32, nq=40, p=4, seed=1)
@@ -137,6 +190,7 @@ def main():
     make_msda_module()
     make_encoder_tiny("encoder_tiny_even.npz", [(96, 128), (96, 128)], (96, 128), seed=5)
     make_encoder_tiny("encoder_tiny_ragged.npz", [(96, 128), (72, 90)], (96, 128), seed=6)
+    make_encoder_c256()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
     print("torch", torch.__version__)

@@ -452,3 +452,32 @@ def synthetic_inputs(image_sizes, padded_hw, embed_dim=256, strides=(8, 16, 32, 
         masks.append(m)
         pos.append(sine_pos_embed(m, embed_dim // 2))
     return feats, masks, pos
+
+
+def deterministic_state_dict(shapes: Dict[str, Sequence[int]], seed: int) -> Dict[str, torch.Tensor]:
+    """Weights regenerated from (sorted name order, shape, seed) with the CPU generator, so that a golden fixture made
+    from the reference need not carry a multi-megabyte state_dict: oracle/make_golden.py loads these into the reference
+    model, the tests load the same tensors into the oracle / the CUDA modules.  Scales keep activations O(1):
+    matrices ~ N(0, 1/fan_in), LayerNorm gains 1 + 0.1 N, biases 0.1 N, sampling-offset weights 0.05 N."""
+    out = {}
+    for i, name in enumerate(sorted(shapes)):
+        g = torch.Generator().manual_seed(seed * 100003 + i)
+        shp = tuple(int(v) for v in shapes[name])
+        x = torch.randn(shp, generator=g)
+        if len(shp) == 1:
+            if name.endswith(".weight"):
+                x = 1.0 + 0.1 * x
+            elif name == "alpha":
+                x = 0.3 * x
+            elif name.endswith("sampling_offsets.bias"):
+                x = 0.5 * x
+            else:
+                x = 0.1 * x
+        elif name.endswith("sampling_offsets.weight"):
+            x = 0.05 * x
+        elif name.endswith("_embed.weight") or name == "level_embeds":
+            x = 0.5 * x
+        else:
+            x = x / (shp[-1] ** 0.5)
+        out[name] = x
+    return out

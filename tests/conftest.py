@@ -60,3 +60,20 @@ def _poison_device_memory():
         from tools import nan_trace
         nan_trace.install()
     yield
+
+
+C256_CFG = dict(heads=8, points=4, topk_sa=64, num_layers=2, level_filter_ratio=(0.4, 0.8, 1.0, 1.0),
+                layer_filter_ratio=(1.0, 0.5))
+
+
+def load_c256_golden():
+    """tests/golden/encoder_c256.npz (made by oracle/make_golden.py from the reference at its real width): returns
+    (arrays, state_dict, (feats, masks, pos)) with the weights / inputs regenerated from their seeds."""
+    import json
+    from oracle import oracle as orc
+    z = np.load(os.path.join(GOLDEN, "encoder_c256.npz"), allow_pickle=False)
+    shapes = json.loads(str(z["shapes_json"]))
+    arrs = {k: torch.from_numpy(z[k]) for k in z.files if k != "shapes_json"}
+    sd = orc.deterministic_state_dict(shapes, 11)
+    inputs = orc.synthetic_inputs([(384, 512), (384, 512)], (384, 512), 256, seed=11)
+    return arrs, sd, inputs
