@@ -3,8 +3,10 @@
  *
  * This is the drop-in boundary: plain pointers and sizes, no torch types.  All pointers are DEVICE
  * pointers unless the parameter name ends in `_host`.  Every call is asynchronous on `stream`
- * (a cudaStream_t passed as void*), allocates nothing, never synchronises, and is re-entrant across
- * streams.  Return value: 0 on success, negative sdetr_status on error (message: sdetr_last_error(),
+ * (a cudaStream_t passed as void*) of the CURRENT device, allocates nothing, never synchronises, and is
+ * re-entrant across streams, threads and devices (per-device kernel attributes are set on first use per device).
+ * The only process-global state are the benchmarking knobs sdetr_set_option / sdetr_gemm_set_variant /
+ * sdetr_gemm_set_trace (atomics: a call reads them once at launch).  Return value: 0 on success, negative sdetr_status on error (message: sdetr_last_error(),
  * thread-local).  Launch errors are RETURNED (the reference only printf's them:
  * models/bricks/ops/cuda/ms_deform_im2col_cuda.cuh:937-941, 1310-1314).
  *

@@ -101,6 +101,10 @@ def _req(t: torch.Tensor, name: str, dtype=None):
     # same contract as the reference's AT_ASSERTM checks -> RuntimeError
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.device.index != torch.cuda.current_device():
+        # the call launches on the CURRENT device's current stream; a tensor of another device would be dereferenced there
+        raise RuntimeError(f"{name} lives on {t.device} but cuda:{torch.cuda.current_device()} is current: "
+                           f"wrap the call in `with torch.cuda.device({t.device.index}):`")
     if not t.is_contiguous():
         raise RuntimeError(f"{name} tensor has to be contiguous")
     if dtype is not None and t.dtype != dtype:
@@ -308,6 +312,8 @@ def score_modulate(mem_all, level_start: int, H: int, W: int, coarse_score, Hc: 
     out = torch.empty(b, H * W, c, device=mem_all.device, dtype=torch.float32)
     if not (coarse_score.is_cuda and coarse_score.stride(1) == 1 and coarse_score.dtype == torch.float32):
         raise RuntimeError("coarse_score rows must be contiguous CUDA float32")
+    if not 0 <= alpha_index < alpha.numel():  # the reference raises IndexError on alpha[lvl] (salience_transformer.py:143)
+        raise IndexError(f"alpha has {alpha.numel()} entries, level {alpha_index} asked for")
     rc = lib().sdetr_score_modulate(
         _req(mem_all, "mem", torch.float32) + 4 * level_start * c, nv * c, coarse_score.data_ptr(),
         coarse_score.stride(0), _req(alpha, "alpha", torch.float32), alpha_index, b, H, W, Hc, Wc, c, out.data_ptr(),

@@ -15,6 +15,17 @@ void set_error(const char *fmt, ...) {
     vsnprintf(g_error, sizeof(g_error), fmt, ap);
     va_end(ap);
 }
+int sm_count() {
+    static std::atomic<int> cache[256];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int v = cache[dev & 255].load(std::memory_order_relaxed);
+    if (!v) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cache[dev & 255].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 }  // namespace sdetr
 

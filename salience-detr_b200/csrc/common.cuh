@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/sdetr_b200.h"
 
 namespace sdetr {
@@ -31,6 +33,28 @@ inline int check_launch(const char *what) {
             return (code);              \
         }                               \
     } while (0)
+
+// Per-DEVICE one-time setup (cudaFuncSetAttribute opt-ins are per device): a bit per device ordinal, set after the
+// attribute call succeeded.  Two threads racing on the first use both set the (idempotent) attribute.
+struct PerDeviceOnce {
+    std::atomic<uint64_t> done[4];
+    bool need(int &dev) {
+        if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+        return !((done[(dev >> 6) & 3].load(std::memory_order_acquire) >> (dev & 63)) & 1ull);
+    }
+    void mark(int dev) { done[(dev >> 6) & 3].fetch_or(1ull << (dev & 63), std::memory_order_release); }
+};
+#define SDETR_OPT_IN_SMEM(once, kernel, bytes, what)                                                                  \
+    do {                                                                                                              \
+        int dev_;                                                                                                     \
+        if ((once).need(dev_)) {                                                                                      \
+            cudaError_t e_ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+            SDETR_REQUIRE(e_ == cudaSuccess, SDETR_ERR_CUDA, "%s: smem attribute: %s", what, cudaGetErrorString(e_)); \
+            (once).mark(dev_);                                                                                        \
+        }                                                                                                             \
+    } while (0)
+
+int sm_count();  // SMs of the CURRENT device (cached per device ordinal; api.cu)
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

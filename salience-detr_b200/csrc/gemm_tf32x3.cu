@@ -925,9 +925,9 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 tensor (rows, cols) with row stride ld (floats); box = (kBK cols, box_rows rows), 128-byte swizzle
-static long long *g_gemm_dbg = nullptr;
-static int g_raw_persistent = 1;  // sdetr_gemm_3xtf32_raw: 1 = persistent kernel "P", 0 = "TS2"
-static int g_gemm_variant = 0;  // 0 = SS (operands from shared memory), 1 = TS (split activation in tensor memory)
+static std::atomic<long long *> g_gemm_dbg{nullptr};
+static std::atomic<int> g_raw_persistent{1};  // sdetr_gemm_3xtf32_raw: 1 = persistent kernel "P", 0 = "TS2"
+static std::atomic<int> g_gemm_variant{0};  // 0 = SS (operands from shared memory), 1 = TS (split activation in tensor memory)
 static bool make_map(CUtensorMap *m, const float *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
@@ -957,18 +957,11 @@ extern "C" int sdetr_gemm_3xtf32_raw(const float *A, int64_t lda, const float *W
                   "gemm_3xtf32_raw: cuTensorMapEncodeTiled failed");
     const int use_tma_store = (ldc % 4 == 0) && aligned16(C) && make_map(&mc, C, M, N, ldc, kBM);
     if (!use_tma_store) mc = ma;
-    static bool attr = false;
-    static int sms = 148;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_ts2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2Smem);
-        SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "gemm_3xtf32_raw: smem attribute: %s", cudaGetErrorString(e));
-        e = cudaFuncSetAttribute(gemm_3xtf32_p_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem);
-        SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "gemm_3xtf32_raw: smem attribute: %s", cudaGetErrorString(e));
-        int dev = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        attr = true;
-    }
-    GemmParams p{bias, C, ldc, M, N, K, act, use_tma_store, g_gemm_dbg};
+    static PerDeviceOnce once_t2, once_p;
+    SDETR_OPT_IN_SMEM(once_t2, gemm_3xtf32_ts2_kernel, kT2Smem, "gemm_3xtf32_raw");
+    SDETR_OPT_IN_SMEM(once_p, gemm_3xtf32_p_kernel<false>, kPSmem, "gemm_3xtf32_raw");
+    const int sms = sm_count();
+    GemmParams p{bias, C, ldc, M, N, K, act, use_tma_store, g_gemm_dbg.load()};
     if (g_raw_persistent) {
         const int tiles = ((N + kBN - 1) / kBN) * ((M + kBM - 1) / kBM);
         gemm_3xtf32_p_kernel<false><<<tiles < sms ? tiles : sms, kPThreads, kPSmem, (cudaStream_t)stream>>>(ma, mw, mw, mc, p);
@@ -1013,15 +1006,10 @@ extern "C" int sdetr_gemm_3xtf32(const float *A, int64_t lda, const float *W_hi,
     // the epilogue leaves through TMA bulk stores when C's rows are 16-byte aligned (else plain stores, e.g. N = 91)
     const int use_tma_store = (ldc % 4 == 0) && aligned16(C) && make_map(&mc, C, M, N, ldc, kBM);
     if (!use_tma_store) mc = ma;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
-        SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "gemm_3xtf32: smem attribute: %s", cudaGetErrorString(e));
-        e = cudaFuncSetAttribute(gemm_3xtf32_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmem);
-        SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "gemm_3xtf32: smem attribute: %s", cudaGetErrorString(e));
-        attr = true;
-    }
-    GemmParams p{bias, C, ldc, M, N, K, relu_a, use_tma_store, g_gemm_dbg};
+    static PerDeviceOnce once_ss, once_ts;
+    SDETR_OPT_IN_SMEM(once_ss, gemm_3xtf32_kernel, kGemmSmem, "gemm_3xtf32");
+    SDETR_OPT_IN_SMEM(once_ts, gemm_3xtf32_ts_kernel, kTsSmem, "gemm_3xtf32");
+    GemmParams p{bias, C, ldc, M, N, K, relu_a, use_tma_store, g_gemm_dbg.load()};
     const int mtiles = (M + kBM - 1) / kBM;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((N + kBN - 1) / kBN, (mtiles + 1) & ~1);  // clusters of 2 along M (an odd tail tile is all out-of-bounds)
@@ -1052,16 +1040,10 @@ extern "C" int sdetr_gemm_3xtf32_pre(const float *A, int64_t lda, const float *W
                   SDETR_ERR_CUDA, "gemm_3xtf32_pre: cuTensorMapEncodeTiled failed");
     const int use_tma_store = (ldc % 4 == 0) && aligned16(C) && make_map(&mc, C, M, N, ldc, kBM);
     if (!use_tma_store) mc = ma;
-    static bool attr = false;
-    static int sms = 148;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_p_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem);
-        SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "gemm_3xtf32_pre: smem attribute: %s", cudaGetErrorString(e));
-        int dev = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        attr = true;
-    }
-    GemmParams p{bias, C, ldc, M, N, K, act, use_tma_store, g_gemm_dbg};
+    static PerDeviceOnce once;
+    SDETR_OPT_IN_SMEM(once, gemm_3xtf32_p_kernel<true>, kPSmem, "gemm_3xtf32_pre");
+    const int sms = sm_count();
+    GemmParams p{bias, C, ldc, M, N, K, act, use_tma_store, g_gemm_dbg.load()};
     const int tiles = ((N + kBN - 1) / kBN) * ((M + kBM - 1) / kBM);
     gemm_3xtf32_p_kernel<true><<<tiles < sms ? tiles : sms, kPThreads, kPSmem, (cudaStream_t)stream>>>(ma, mh, ml, mc, p);
     return check_launch("gemm_3xtf32_pre");

@@ -383,12 +383,8 @@ extern "C" int sdetr_mha_in_proj(const float *tokens, const float *pos, const in
     constexpr int C = 256;
     const int rows = batch * k;
     const size_t smem = (size_t)(C * kInPitch + C * kInCols) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(mha_in_proj_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "mha_in_proj: smem attribute: %s", cudaGetErrorString(e));
-        attr = true;
-    }
+    static PerDeviceOnce once;
+    SDETR_OPT_IN_SMEM(once, mha_in_proj_kernel<C>, smem, "mha_in_proj");
     dim3 grid((rows + kInRows - 1) / kInRows, 3 * C / kInCols);
     mha_in_proj_kernel<C><<<grid, kInThreads, smem, (cudaStream_t)stream>>>(tokens, pos, index, num_rows, k, rows, w_in_t, b_in,
                                                                             t_out, qkv);
@@ -402,12 +398,7 @@ static int launch_attention(const float *q, const float *kmat, const float *v, i
     SDETR_REQUIRE(head_dim == 32, SDETR_ERR_UNSUPPORTED, "%s: head_dim %d (only 32)", what, head_dim);
     SDETR_REQUIRE(aligned16(q) && aligned16(kmat) && aligned16(v) && aligned16(out) && stride_qk % 4 == 0 && stride_v % 4 == 0,
                   SDETR_ERR_INVALID_ARG, "%s: 16-byte alignment required", what);
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-            sms = 148;
-    }
+    const int sms = sm_count();
     // one CTA per SM: as many query tiles as fit in one wave
     const int slots = sms / (batch * heads) > 0 ? sms / (batch * heads) : 1;
     int q_tile = (n + slots - 1) / slots;
@@ -425,12 +416,8 @@ static int launch_attention(const float *q, const float *kmat, const float *v, i
     while (q_tile > 8 && smem_for(q_tile) > limit) q_tile -= 4;  // long sequences: smaller query tiles
     SDETR_REQUIRE(smem_for(q_tile) <= limit, SDETR_ERR_UNSUPPORTED, "%s: %d tokens do not fit in shared memory", what, n);
     const size_t smem = smem_for(q_tile);
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(attn_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "%s: smem attribute: %s", what, cudaGetErrorString(e));
-        attr = true;
-    }
+    static PerDeviceOnce once;
+    SDETR_OPT_IN_SMEM(once, attn_rows_kernel, 220 * 1024, what);
     dim3 grid(heads, batch, (n + q_tile - 1) / q_tile);
     attn_rows_kernel<<<grid, kAttThreads, smem, stream>>>(q, kmat, v, stride_qk, stride_v, out, n, heads,
                                                           1.f / sqrtf((float)head_dim), q_tile, n_pad);
@@ -468,12 +455,8 @@ extern "C" int sdetr_mha_out_proj_ln_scatter(const float *attn, const float *t, 
     constexpr int C = 256;
     const int rows = batch * k;
     const size_t smem = (size_t)(C * kOutRows + 2 * kOutChunk * C + kOutRows * C) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(mha_out_proj_ln_scatter_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "mha_out_proj_ln_scatter: smem attribute: %s", cudaGetErrorString(e));
-        attr = true;
-    }
+    static PerDeviceOnce once;
+    SDETR_OPT_IN_SMEM(once, mha_out_proj_ln_scatter_kernel<C>, smem, "mha_out_proj_ln_scatter");
     mha_out_proj_ln_scatter_kernel<C><<<(rows + kOutRows - 1) / kOutRows, kOutThreads, smem, (cudaStream_t)stream>>>(
         attn, t, w_out_t, b_out, gamma, beta, eps, index, dst, pos, dst_sum, num_rows, k, rows);
     return check_launch("mha_out_proj_ln_scatter");

@@ -396,9 +396,9 @@ __global__ void __launch_bounds__(kThreads) msda_fwd_generic_kernel(const MsdaFw
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
-static int g_bcast = 1;   // 0 = shuffle broadcast, 1 = shared-memory broadcast (D=32, L=4, P=4 only)
-static int g_minb = 4;    // tuning knobs (sdetr_set_option)
-static int g_chunk = 64;
+static std::atomic<int> g_bcast{1};  // 0 = shuffle broadcast, 1 = shared-memory broadcast (D=32, L=4, P=4 only)
+static std::atomic<int> g_minb{4};   // tuning knobs (sdetr_set_option)
+static std::atomic<int> g_chunk{64};
 
 template <int D, int L, int P, int MINB>
 static void launch_special(const MsdaFwdParams &p, bool fused, int schedule, cudaStream_t s) {

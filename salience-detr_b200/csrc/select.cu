@@ -708,13 +708,8 @@ extern "C" int sdetr_salience_select(const float *raw_score, const uint8_t *mask
     }
     if (kmax <= kLevelSortMax && bins <= 12000) {
         // fastest path: select + sort per (image, level), rank merge, counting-sort processing order
-        static bool attr_a = false;
-        if (!attr_a) {
-            cudaError_t e = cudaFuncSetAttribute(level_select_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 kLevelSortMax * (int)sizeof(unsigned long long));
-            SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "salience_select: smem attribute: %s", cudaGetErrorString(e));
-            attr_a = true;
-        }
+        static PerDeviceOnce once_a;
+        SDETR_OPT_IN_SMEM(once_a, level_select_sort_kernel, kLevelSortMax * (int)sizeof(unsigned long long), "salience_select");
         unsigned long long *sorted = reinterpret_cast<unsigned long long *>(buf[0]);  // b*K u64 <= two u32 buffers
         level_select_sort_kernel<<<batch * num_levels, kSortThreads, (size_t)next_pow2(kmax) * sizeof(unsigned long long),
                                    s>>>(raw_score, mask, lmin, tb, num_value, K, sorted);
@@ -736,13 +731,8 @@ extern "C" int sdetr_salience_select(const float *raw_score, const uint8_t *mask
         if ((rc = check_launch("salience_select/level_select"))) return rc;
         const int N = next_pow2(K);
         const size_t smem = (size_t)N * sizeof(unsigned long long);
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(merge_bitonic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 kBitonicMax * (int)sizeof(unsigned long long));
-            SDETR_REQUIRE(e == cudaSuccess, SDETR_ERR_CUDA, "salience_select: smem attribute: %s", cudaGetErrorString(e));
-            attr_set = true;
-        }
+        static PerDeviceOnce once_b;
+        SDETR_OPT_IN_SMEM(once_b, merge_bitonic_kernel, kBitonicMax * (int)sizeof(unsigned long long), "salience_select");
         merge_bitonic_kernel<<<batch, kSortThreads, smem, s>>>(buf[0], buf[1], tb, K, N, tile_order ? cell_px : 1,
                                                                cells_x, selected_inds, selected_score, tile_order);
         return check_launch("salience_select/merge_bitonic");

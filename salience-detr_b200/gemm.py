@@ -34,6 +34,13 @@ K_CHUNK = 512  # longest reduction handed to one tensor-core GEMM (its accumulat
 _weight_cache: Dict[int, tuple] = {}
 
 
+def _prune(cache: Dict[int, tuple]):
+    """Drop entries whose parameter has been freed (the caches are keyed by id(), which outlives the object)."""
+    if len(cache) >= 64:
+        for k in [k for k, v in cache.items() if v[2]() is None]:
+            del cache[k]
+
+
 @contextlib.contextmanager
 def _tf32_matmul():
     prev = torch.backends.cuda.matmul.allow_tf32
@@ -57,6 +64,7 @@ def split_weight(weight: Tensor) -> Tensor:
         with torch.no_grad():
             hit = (key, cabi.split_tf32(weight.detach().contiguous(), layout_b=True, chunk=_chunk_of(weight.shape[1])),
                    weakref.ref(weight))
+        _prune(_weight_cache)
         _weight_cache[id(weight)] = hit
     return hit[1]
 
@@ -70,6 +78,7 @@ def split_weight_pair(weight: Tensor) -> Tuple[Tensor, Tensor]:
     if hit is None or hit[0] != key or hit[2]() is not weight:
         with torch.no_grad():
             hit = (key, cabi.split_tf32_pair(weight.detach()), weakref.ref(weight))
+        _prune(_pair_cache)
         _pair_cache[id(weight)] = hit
     return hit[1]
 

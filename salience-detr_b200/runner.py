@@ -34,7 +34,8 @@ class HostPipeline:
 
     def run(self, batches, on_output=None):
         """batches: iterable of (feats_host, pos_host) pinned-memory level lists.  Returns the number processed;
-        ``on_output(i, host_memory)`` (optional) is called once batch i's output is in host memory."""
+        ``on_output(i, host_memory)`` (optional) is called, in batch order, once batch i's output is in host memory.
+        ``host_memory`` is the lane's pinned buffer: consume or copy it before returning -- a later batch overwrites it."""
         n = 0
         for i, (feats_h, pos_h) in enumerate(batches):
             k = i % len(self.lanes)
@@ -65,9 +66,12 @@ class HostPipeline:
             n += 1
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.lanes[0].feats + self.lanes[0].pos)
         self.d2h_bytes = self.host_out[0].numel() * 4
-        for k, ev in enumerate(self.done):
-            if ev is not None:
-                ev.synchronize()
+        depth = len(self.lanes)
+        for i in range(max(0, n - depth), n):   # drain: the last `depth` batches, in batch order
+            k = i % depth
+            self.done[k].synchronize()
+            if on_output is not None:
+                on_output(i, self.host_out[k])
         return n
 
 

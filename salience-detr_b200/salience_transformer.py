@@ -405,6 +405,8 @@ class SalienceTransformer(nn.Module):
         mask (base_transformer.py:74-110) from the padding masks.  One device->host copy."""
         dev = multi_level_masks[0].device
         b = multi_level_masks[0].shape[0]
+        if len(multi_level_masks) != self.num_feature_levels:
+            raise ValueError(f"{len(multi_level_masks)} feature levels given, model built for {self.num_feature_levels}")
         shapes_list = [tuple(int(s) for s in m.shape[-2:]) for m in multi_level_masks]
         L = len(shapes_list)
         sizes = [h * w for h, w in shapes_list]
