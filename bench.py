@@ -162,72 +162,122 @@ def time_gemm_kernels(pkg, runner, reps=10):
 
 
 def use_host_cores():
-    """The CPU arm uses all physical host cores (torchrun pins OMP_NUM_THREADS=1 by default)."""
+    """The CPU arm uses every host core this process may run on (torchrun pins OMP_NUM_THREADS=1 by default)."""
     n = os.cpu_count() or 1
     try:
         n = len(os.sched_getaffinity(0))
     except Exception:
         pass
-    torch.set_num_threads(max(1, n // 2))  # SMT siblings do not help the GEMM / grid_sample kernels
+    torch.set_num_threads(max(1, n))
     return torch.get_num_threads()
 
 
-def cpu_port_step(state_dict, feats, masks, pos, cfg):
-    from oracle import oracle as orc  # CPU baseline leg only
-    with torch.no_grad():
-        mem, _ = orc.encoder_half_forward(state_dict, feats, masks, pos, cfg, core="torch")
-    return mem
+def model_cfg(model):
+    m = model.encoder.layers[0]
+    return dict(heads=m.n_heads, points=m.self_attn.num_points, topk_sa=m.topk_sa, num_layers=model.encoder.num_layers,
+                level_filter_ratio=model.level_filter_ratio.tolist(), layer_filter_ratio=model.layer_filter_ratio.tolist())
+
+
+def reference_step_fn(model, device="cpu"):
+    """One encoder-half forward (salience_transformer.py:106-183) of the REFERENCE on `device`, same weights as `model`.
+    -> (step(feats, masks, pos) -> memory, kind, description).  kind "reference": the unmodified reference modules
+    installed under baseline/_ref (oracle/ref_import.py; on a GPU its pure-PyTorch grid_sample MSDA runs, because its
+    CUDA extension does not build against this torch); kind "port": the oracle's torch restatement (fallback when the
+    install is absent)."""
+    from oracle import ref_import  # reference arm / cpu_baseline / gpu_comparator legs only
+    cfg = model_cfg(model)
+    if ref_import.available():
+        m = model.encoder.layers[0]
+        tr = ref_import.build_transformer(
+            embed_dim=model.embed_dim, d_ffn=m.linear1.out_features, n_heads=m.n_heads, n_levels=model.num_feature_levels,
+            n_points=m.self_attn.num_points, num_layers=model.encoder.num_layers, num_classes=model.num_classes,
+            level_filter_ratio=cfg["level_filter_ratio"], layer_filter_ratio=cfg["layer_filter_ratio"], topk_sa=m.topk_sa,
+            max_num_embedding=model.encoder.background_embedding.row_embed.num_embeddings)
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        res = tr.load_state_dict(sd, strict=False)
+        assert not res.unexpected_keys, res.unexpected_keys  # our parameter names ARE the reference's
+        tr = tr.to(device).eval()
+        return (lambda f, mk, p: ref_import.run_encoder_half(tr, f, mk, p)[0], "reference",
+                "unmodified reference modules (baseline/_ref: models/bricks/salience_transformer.py:106-183 with the "
+                "pure-PyTorch grid_sample MSDA, ms_deform_attn.py:159-212), same weights and inputs")
+    from oracle import oracle as orc
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+
+    def port(f, mk, p):
+        with torch.no_grad():
+            return orc.encoder_half_forward(sd, f, mk, p, cfg, core="torch")[0]
+
+    return port, "port", "oracle port of the reference PyTorch CPU path (baseline/_ref not installed)"
 
 
 def cpu_baseline(pkg, model, budget_s=20.0):
-    """The oracle port of the reference's PyTorch CPU path on this host's cores, bounded sample."""
+    """The reference's CPU path on this host's cores, bounded sample (full bs=2 forwards for about `budget_s`)."""
     from salience_detr_b200.synthetic import make_inputs
-    use_host_cores()
+    cores = use_host_cores()
     feats, masks, pos = make_inputs(WORKLOAD, seed=0)
-    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-    m = model.encoder.layers[0]
-    cfg = dict(heads=m.n_heads, points=m.self_attn.num_points, topk_sa=m.topk_sa, num_layers=model.encoder.num_layers,
-               level_filter_ratio=model.level_filter_ratio.tolist(), layer_filter_ratio=model.layer_filter_ratio.tolist())
-    cpu_port_step(sd, feats, masks, pos, cfg)  # warm-up
+    step, kind, desc = reference_step_fn(model, "cpu")
+    step(feats, masks, pos)  # warm-up
     times = []
     t_end = time.time() + budget_s
     while len(times) < 2 or (time.time() < t_end and len(times) < 10):
         t0 = time.time()
-        cpu_port_step(sd, feats, masks, pos, cfg)
+        step(feats, masks, pos)
         times.append(time.time() - t0)
     b = feats[0].shape[0]
-    return {"value": round(b / statistics.median(times), 4), "unit": "images/s", "cores": torch.get_num_threads(),
-            "kind": "port", "sample": f"{len(times)} full bs={b} encoder forwards of {WORKLOAD} (median), torch CPU fp32"}
+    return {"value": round(b / statistics.median(times), 4), "unit": "images/s", "cores": cores, "kind": kind,
+            "sample": f"{len(times)} full bs={b} encoder forwards of {WORKLOAD} (median), torch CPU fp32; {desc}"}
+
+
+def gpu_comparator(model, feats, masks, pos, steps=10, warmup=3):
+    """What the reference really executes on this image ON THE B200: its own modules (pure-PyTorch MSDA, ~40 host syncs
+    and ~1000 launches per forward), same weights / inputs, CUDA-event timed like tools/benchmark_model.py:44-61."""
+    step, kind, desc = reference_step_fn(model, feats[0].device)
+    if kind != "reference":
+        return {"unavailable": "baseline/_ref not installed"}
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False  # fp32 like the reference's default
+    try:
+        for _ in range(warmup):
+            mem = step(feats, masks, pos)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            mem = step(feats, masks, pos)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    b = feats[0].shape[0]
+    ms = statistics.median(ts)
+    return {"value": round(1000.0 * b / ms, 2), "unit": "images/s", "ms_per_step": round(ms, 3), "steps": steps,
+            "impl": desc + "; fp32 (allow_tf32 off), eager, no CUDA graph", "memory_checksum": float(mem.double().abs().mean())}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (oracle port), rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path, all host cores, rank 0 only."""
     if rank != 0:
         return
-    import salience_detr_b200 as pkg
     from salience_detr_b200.synthetic import build_model, make_inputs
-    use_host_cores()
+    cores = use_host_cores()
     model = build_model()
     feats, masks, pos = make_inputs(WORKLOAD, seed=0)
-    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-    m = model.encoder.layers[0]
-    cfg = dict(heads=m.n_heads, points=m.self_attn.num_points, topk_sa=m.topk_sa, num_layers=model.encoder.num_layers,
-               level_filter_ratio=model.level_filter_ratio.tolist(), layer_filter_ratio=model.layer_filter_ratio.tolist())
+    step, kind, desc = reference_step_fn(model, "cpu")
     for _ in range(args.warmup):
-        cpu_port_step(sd, feats, masks, pos, cfg)
+        step(feats, masks, pos)
     t0 = time.time()
     for _ in range(args.steps):
-        cpu_port_step(sd, feats, masks, pos, cfg)
+        step(feats, masks, pos)
     dt = time.time() - t0
     b = feats[0].shape[0]
     val = round(args.steps * b / dt, 4)
-    cores = torch.get_num_threads()
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1000 * dt / args.steps, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "impl": "oracle port of the reference PyTorch CPU path "
-                       "(grid_sample MSDA, ms_deform_attn.py:159-212); the reference is Python and does not travel"},
-            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
+            "config": {"workload": WORKLOAD, "impl": desc},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": kind,
                              "sample": f"{args.steps} full bs={b} encoder forwards"},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -386,6 +436,7 @@ def main():
                               "kernel_ms_per_step": round(gemm_ms, 4)},
         }
         if world == 1 and not args.skip_cpu_baseline:
+            line["gpu_comparator"] = gpu_comparator(model, feats, masks, pos)
             line["cpu_baseline"] = cpu_baseline(pkg, model)
         print(json.dumps(line), flush=True)
     if world > 1:

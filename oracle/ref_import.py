@@ -16,11 +16,56 @@ import sys
 import types
 import warnings
 
-REFERENCE_ROOT = os.environ.get("SDETR_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASELINE_REF = os.path.join(_REPO, "baseline", "_ref")  # git-ignored install of the reference's hot-path modules
+# the Python modules of the path; everything else of the reference stays where it is
+PATH_MODULES = ("base_transformer.py", "basic.py", "ms_deform_attn.py", "position_encoding.py", "salience_transformer.py")
+
+
+def _has(root: str) -> bool:
+    return os.path.isfile(os.path.join(root, "models", "bricks", "salience_transformer.py"))
+
+
+def _resolve_root() -> str:
+    env = os.environ.get("SDETR_REFERENCE_ROOT")
+    if env:
+        return env
+    for root in ("/root/reference", BASELINE_REF):  # the tree itself in the build container, the install on the GPU box
+        if _has(root):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _resolve_root()
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "models", "bricks", "salience_transformer.py"))
+    return _has(REFERENCE_ROOT)
+
+
+def install(src: str = "/root/reference", dst: str = BASELINE_REF) -> bool:
+    """Install the UNMODIFIED Python modules of the path from the reference tree into the git-ignored
+    ``baseline/_ref`` (which travels to the GPU box; /root/reference does not).  The reference has no setup.py /
+    pyproject, so `pip install --target` does not apply: this copies the five files byte for byte.  The CUDA
+    extension sources (models/bricks/ops/cuda) are NOT installed: they do not compile against torch 2.11 (SURVEY.md
+    fact 2), so the reference's own `load(...)` fails, warns and falls back to its pure-PyTorch MSDA
+    (ms_deform_attn.py:13-26,361-372) -- which is the path the reference really runs on this image."""
+    import filecmp
+    import shutil
+
+    if not _has(src):
+        return _has(dst)
+    out = os.path.join(dst, "models", "bricks")
+    os.makedirs(out, exist_ok=True)
+    for name in PATH_MODULES:
+        a, b = os.path.join(src, "models", "bricks", name), os.path.join(out, name)
+        if not (os.path.exists(b) and filecmp.cmp(a, b, shallow=False)):
+            shutil.copyfile(a, b)
+    with open(os.path.join(dst, "README"), "w") as f:
+        f.write("Unmodified copies of xiuqhou/Salience-DETR models/bricks/{%s} (reference arm of bench.py and the\n"
+                "drop-in tests; written by oracle/ref_import.install(), git-ignored, never imported by the product).\n"
+                % ",".join(PATH_MODULES))
+    return True
 
 
 def _install_stub():
@@ -56,6 +101,35 @@ def load():
         import models.bricks.position_encoding as pe  # noqa
         import models.bricks.base_transformer as bt  # noqa
     return types.SimpleNamespace(msda=msda, st=st, pe=pe, bt=bt)
+
+
+class _Stop(Exception):
+    pass
+
+
+def run_encoder_half(tr, feats, masks, pos):
+    """Run the reference ``SalienceTransformer.forward`` up to the end of the encoder (salience_transformer.py:106-183)
+    and return (memory, kwargs the filter handed to the encoder).  The decoder half is cut off by an exception raised
+    from a wrapper around ``encoder.forward`` -- the reference code itself is untouched."""
+    import torch
+
+    captured = {}
+    enc_fwd = tr.encoder.forward
+
+    def spy(**kw):
+        captured.update(kw)
+        captured["memory"] = enc_fwd(**kw)
+        raise _Stop()
+
+    tr.encoder.forward = spy
+    try:
+        with torch.no_grad():
+            tr(feats, masks, pos, None, None, None)
+    except _Stop:
+        pass
+    finally:
+        del tr.encoder.forward  # drop the instance attribute: the class's forward is visible again
+    return captured.pop("memory"), captured
 
 
 def build_transformer(embed_dim=256, d_ffn=2048, n_heads=8, n_levels=4, n_points=4, num_layers=6,
