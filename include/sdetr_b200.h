@@ -206,6 +206,30 @@ int sdetr_flatten_tokens(const float *const *feats_host, const float *const *pos
                          const float *keep, const int32_t *level_size_host, int batch, int channels, int num_levels,
                          float *feat_tok, float *lpos_tok, float *x_tok, sdetr_stream_t stream);
 
+/* Same, with the position embedding already in token layout (b,Nv,C) (sdetr_sine_pos_tokens): only the feature maps are
+ * transposed; lpos_tok = pos_tokens + level_embeds[l]. */
+int sdetr_flatten_tokens_pos(const float *const *feats_host, const float *pos_tokens, const float *level_embeds,
+                             const float *keep, const int32_t *level_size_host, int batch, int channels, int num_levels,
+                             float *feat_tok, float *lpos_tok, float *x_tok, sdetr_stream_t stream);
+
+/* Everything the path derives from the padding masks, in two launches (replaces ~60 ATen launches and makes a fresh-mask
+ * batch cheap).  mask (b,Nv) uint8 (1 = padding), levels given by host (H_l, W_l).
+ *   valid_token_nums[b,l] = #valid tokens;  focus_token_nums[b,l] = int(float(valid) * level_filter_ratio[l])
+ *     (salience_transformer.py:116-119: fp32 multiply, truncation);
+ *   valid_ratios[b,l] = (valid W of the first row / W_l, valid H of the first column / H_l)   (base_transformer.py:48-56);
+ *   keep[b,t] = 1.0 iff the token is not padded and its proposal centre ((x+.5)/valid_W, (y+.5)/valid_H) and size
+ *     0.05 * 2^l lie in (0.01, 0.99)   (base_transformer.py:84-108);
+ *   ynorm / xnorm[b,t] = (cumsum of the valid mask along y / x + pos_offset) / (last + pos_eps) * pos_scale, the
+ *     normalised coordinates of PositionEmbeddingSine (models/bricks/position_encoding.py:48-56), fp32, same op order. */
+int sdetr_mask_plan(const uint8_t *mask, int batch, int num_value, int num_levels, const int32_t *level_h_host,
+                    const int32_t *level_w_host, const float *level_filter_ratio_host, float pos_offset, float pos_eps,
+                    float pos_scale, float *ynorm, float *xnorm, int32_t *valid_token_nums, int32_t *focus_token_nums,
+                    float *valid_ratios, float *keep, sdetr_stream_t stream);
+/* pos_tokens[r, :] = [sin/cos(ynorm[r] / dim_ty[j]) (j < F) | sin/cos(xnorm[r] / dim_tx[j])], sin on even j, cos on odd j
+ * (position_encoding.py:58-64); rows = b*Nv, F = num_pos_feats (multiple of 4), dim_t* = temperature^(2 (j//2) / F). */
+int sdetr_sine_pos_tokens(const float *ynorm, const float *xnorm, const float *dim_ty, const float *dim_tx, int64_t rows,
+                          int num_pos_feats, float *pos_tokens, sdetr_stream_t stream);
+
 /* Dense self-attention core of the 300-token pre-attention (salience_transformer.py:372-376; the attention inside
  * nn.MultiheadAttention): out = softmax(Q K^T / sqrt(d)) V per (image, head).  qk (b,n,2,heads,d): projected queries
  * then keys; v (b,n,heads,d); out (b,n,heads*d).  head_dim must be 32; K^T, V and the score tile live in shared memory:
@@ -280,6 +304,22 @@ int sdetr_gemm_3xtf32(const float *A, int64_t lda, const float *W_hi, const floa
  * tiles, the weight halves arrive as two TMA tiles per stage and only the activation is converted in the kernel. */
 int sdetr_gemm_3xtf32_pre(const float *A, int64_t lda, const float *W_hi, const float *W_lo, const float *bias, float *C,
                           int64_t ldc, int M, int N, int K, int act, sdetr_stream_t stream);
+
+/* ---- "3xFP16": the same error-compensated product on tcgen05.mma.kind::f16 -----------------------------------------
+ * An fp16 significand is as wide as a TF32 one (11 bits), so  A_hi.W_hi + A_hi.W_lo + A_lo.W_hi  with
+ * hi = fp16(x), lo = fp16(x - hi) keeps the 22 significand bits per operand of 3xTF32 at twice the MMA rate and half the
+ * operand bytes.  Exponent range is restored by exact power-of-two scalings: the kernel multiplies the activation by 16
+ * before the split (full accuracy for 2^-7 <= |x| < 4094, absolute error floor 2^-29 below, inf/NaN above), the caller
+ * scales the weight by `scale` = 2^s with max|scale * W| in [2^13, 2^14) when splitting, and the epilogue multiplies the
+ * fp32 accumulator by 2^-(4+s) before the bias.  Replaces the same reference projections as sdetr_gemm_3xtf32
+ * (models/bricks/ms_deform_attn.py:316,322-328,375; salience_transformer.py:347-351,462,16-47; base_transformer.py:111).
+ * W (N,K) fp32 contiguous -> W_hi, W_lo (N,K) fp16 (2-byte elements, 16-byte aligned). */
+int sdetr_split_f16_pair(const float *W, int64_t count, float scale, void *W_hi, void *W_lo, sdetr_stream_t stream);
+/* C[M,N] = act(A)[M,K] . W^T + bias, W given as the pair above and the `w_scale` it was split with; K % 64 == 0;
+ * A (M,K) fp32 with row pitch lda (floats, multiple of 4); act: 0 none, 1 ReLU, 2 exact GELU applied to A on load;
+ * C row pitch ldc (TMA stores when ldc % 4 == 0). */
+int sdetr_gemm_f16x3_pre(const float *A, int64_t lda, const void *W_hi, const void *W_lo, float w_scale, const float *bias,
+                         float *C, int64_t ldc, int M, int N, int K, int act, sdetr_stream_t stream);
 
 #ifdef __cplusplus
 }

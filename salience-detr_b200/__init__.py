@@ -18,6 +18,7 @@ from .ms_deform_attn import (  # noqa: F401
     ms_deform_attn_forward,
 )
 from . import gemm  # noqa: F401
+from .position_encoding import PositionEmbeddingSine  # noqa: F401
 from .salience_transformer import (  # noqa: F401
     EncoderPlan,
     MaskPredictor,

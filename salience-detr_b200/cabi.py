@@ -53,6 +53,11 @@ SIGNATURES = {
     "sdetr_split_tf32_pair": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "sdetr_gemm_3xtf32": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
     "sdetr_gemm_3xtf32_pre": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "sdetr_flatten_tokens_pos": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "sdetr_mask_plan": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sdetr_sine_pos_tokens": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
+    "sdetr_split_f16_pair": (_i, [_vp, _i64, _f, _vp, _vp, _vp]),
+    "sdetr_gemm_f16x3_pre": (_i, [_vp, _i64, _vp, _vp, _f, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
     "sdetr_flatten_tokens": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "sdetr_attention_small": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sdetr_attention_qkv": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
@@ -148,6 +153,16 @@ def msda_forward_plain(value, spatial_shapes, level_start_index, sampling_loc, a
     return out
 
 
+KERNEL_TIMERS = None  # measurement aid (bench.py): {"msda": [(event_before, event_after), ...]} filled per launch
+
+
+def _timer_event():
+    """CUDA event that can be recorded inside a stream capture AND timed after the graph has run (external event node)."""
+    ev = torch.cuda.Event(enable_timing=True, external=torch.cuda.is_current_stream_capturing())
+    ev.record()
+    return ev
+
+
 def msda_fused_forward(value_buf, value_batch_stride, value_token_stride, value_offset, spatial_shapes,
                        level_start_index, ref_points, proj, heads, head_dim, levels, points, num_value,
                        query_order=None, schedule=0, want_loc_attn=False):
@@ -163,6 +178,7 @@ def msda_fused_forward(value_buf, value_batch_stride, value_token_stride, value_
         attn = torch.empty(b, nq, heads, levels, points, device=proj.device, dtype=torch.float32)
     if not value_buf.is_cuda or value_buf.dtype != torch.float32:
         raise RuntimeError("value must be a CUDA float32 tensor")
+    t0 = _timer_event() if KERNEL_TIMERS is not None else None
     rc = lib().sdetr_msda_fused_forward(
         value_buf.data_ptr() + 4 * value_offset, value_batch_stride, value_token_stride,
         _req(spatial_shapes, "spatial_shapes", torch.int64), _req(level_start_index, "level_start_index", torch.int64),
@@ -171,6 +187,8 @@ def msda_fused_forward(value_buf, value_batch_stride, value_token_stride, value_
         heads, head_dim, levels, nq, points,
         _req(query_order, "query_order", torch.int32) if query_order is not None else None, schedule, _stream())
     _check(rc, "sdetr_msda_fused_forward")
+    if t0 is not None:
+        KERNEL_TIMERS.setdefault("msda", []).append((t0, _timer_event()))
     return (out, loc, attn) if want_loc_attn else out
 
 
@@ -435,6 +453,53 @@ def flatten_tokens(feats, pos, level_embeds, keep):
     return out
 
 
+def flatten_tokens_pos(feats, pos_tokens, level_embeds, keep):
+    """Per-level (b,C,H,W) feats + token-layout position embedding (b,Nv,C) -> (feat_tok, lpos_tok, x_tok)."""
+    L = len(feats)
+    b, c = feats[0].shape[:2]
+    sizes = [f.shape[2] * f.shape[3] for f in feats]
+    nv = sum(sizes)
+    fp = (ctypes.c_void_p * L)(*[_req(f, "feat", torch.float32) for f in feats])
+    out = [torch.empty(b, nv, c, device=feats[0].device, dtype=torch.float32) for _ in range(3)]
+    if tuple(pos_tokens.shape) != (b, nv, c):
+        raise RuntimeError(f"pos_tokens must be {(b, nv, c)}, got {tuple(pos_tokens.shape)}")
+    rc = lib().sdetr_flatten_tokens_pos(fp, _req(pos_tokens, "pos_tokens", torch.float32),
+                                        _req(level_embeds, "level_embeds", torch.float32), _req(keep, "keep", torch.float32),
+                                        _host_i32(sizes), b, c, L, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), _stream())
+    _check(rc, "sdetr_flatten_tokens_pos")
+    return out
+
+
+def mask_plan(mask_u8, shapes, level_filter_ratio, pos_offset=-0.5, pos_eps=1e-6, pos_scale=2 * 3.141592653589793):
+    """mask_u8 (b,Nv) -> dict(valid (b,L) i32, focus (b,L) i32, valid_ratios (b,L,2), keep (b,Nv), ynorm, xnorm (b,Nv))."""
+    b, nv = mask_u8.shape
+    L = len(shapes)
+    dev = mask_u8.device
+    f32 = dict(device=dev, dtype=torch.float32)
+    out = dict(valid=torch.empty(b, L, device=dev, dtype=torch.int32), focus=torch.empty(b, L, device=dev, dtype=torch.int32),
+               valid_ratios=torch.empty(b, L, 2, **f32), keep=torch.empty(b, nv, **f32), ynorm=torch.empty(b, nv, **f32),
+               xnorm=torch.empty(b, nv, **f32))
+    ratios = (ctypes.c_float * L)(*[float(r) for r in level_filter_ratio])
+    rc = lib().sdetr_mask_plan(_req(mask_u8, "mask", torch.uint8), b, nv, L, _host_i32([h for h, _ in shapes]),
+                               _host_i32([w for _, w in shapes]), ratios, float(pos_offset), float(pos_eps), float(pos_scale),
+                               out["ynorm"].data_ptr(), out["xnorm"].data_ptr(), out["valid"].data_ptr(), out["focus"].data_ptr(),
+                               out["valid_ratios"].data_ptr(), out["keep"].data_ptr(), _stream())
+    _check(rc, "sdetr_mask_plan")
+    return out
+
+
+def sine_pos_tokens(ynorm, xnorm, dim_ty, dim_tx):
+    """(b,Nv) normalised coordinates -> (b,Nv,2F) sine position embedding in token layout."""
+    b, nv = ynorm.shape
+    f = dim_ty.numel()
+    pos = torch.empty(b, nv, 2 * f, device=ynorm.device, dtype=torch.float32)
+    rc = lib().sdetr_sine_pos_tokens(_req(ynorm, "ynorm", torch.float32), _req(xnorm, "xnorm", torch.float32),
+                                     _req(dim_ty, "dim_ty", torch.float32), _req(dim_tx, "dim_tx", torch.float32), b * nv, f,
+                                     pos.data_ptr(), _stream())
+    _check(rc, "sdetr_sine_pos_tokens")
+    return pos
+
+
 def gemm_3xtf32_raw(x, w, bias=None, act=0):
     """y = act(x) @ w.T + bias, both operands split inside the kernel (w: raw fp32 (N,K) contiguous)."""
     K = x.shape[-1]
@@ -468,6 +533,41 @@ def gemm_3xtf32_pre(x, w_hi, w_lo, bias=None, act=0):
                                      _req(bias, "bias", torch.float32) if bias is not None else None, y.data_ptr(), ldc, M, N, K,
                                      int(act), _stream())
     _check(rc, "sdetr_gemm_3xtf32_pre")
+    y = y if ldc == N else y[:, :N]
+    return y.reshape(*x.shape[:-1], N) if ldc == N else y.unflatten(0, x.shape[:-1])
+
+
+def split_f16_pair(w):
+    """(N,K) fp32 -> (W_hi, W_lo, scale): fp16 pair of scale * W with scale = 2^s such that max|scale * W| is in
+    [2^13, 2^14) (one host read of max|W|; done once per parameter version by gemm.split_weight_f16)."""
+    import math
+    w = w.contiguous()
+    amax = float(w.abs().max())
+    if not math.isfinite(amax):
+        raise RuntimeError("split_f16_pair: weight has non-finite entries")
+    scale = 2.0 ** (13 - math.frexp(amax)[1] + 1) if amax > 0 else 1.0  # frexp: amax = m * 2^e, 0.5 <= m < 1
+    hi = torch.empty(w.shape, device=w.device, dtype=torch.float16)
+    lo = torch.empty_like(hi)
+    _check(lib().sdetr_split_f16_pair(_req(w, "w", torch.float32), w.numel(), scale, hi.data_ptr(), lo.data_ptr(), _stream()),
+           "sdetr_split_f16_pair")
+    return hi, lo, scale
+
+
+def gemm_f16x3_pre(x, w_hi, w_lo, w_scale, bias=None, act=0):
+    """y = act(x) @ W.T + bias on the persistent tcgen05.mma.kind::f16 kernel (3xFP16, fp32-class accuracy)."""
+    K = x.shape[-1]
+    N = w_hi.shape[0]
+    if not (x.is_cuda and x.dtype == torch.float32 and x.stride(-1) == 1):
+        raise RuntimeError("gemm_f16x3_pre needs a CUDA float32 input with unit last stride")
+    x2 = x if x.dim() == 2 else x.reshape(-1, K)
+    M = x2.shape[0]
+    ldc = (N + 3) // 4 * 4
+    y = torch.empty(M, ldc, device=x.device, dtype=torch.float32)
+    rc = lib().sdetr_gemm_f16x3_pre(x2.data_ptr(), x2.stride(0) if M > 1 else K, _req(w_hi, "w_hi", torch.float16),
+                                    _req(w_lo, "w_lo", torch.float16), float(w_scale),
+                                    _req(bias, "bias", torch.float32) if bias is not None else None, y.data_ptr(), ldc, M, N, K,
+                                    int(act), _stream())
+    _check(rc, "sdetr_gemm_f16x3_pre")
     y = y if ldc == N else y[:, :N]
     return y.reshape(*x.shape[:-1], N) if ldc == N else y.unflatten(0, x.shape[:-1])
 

@@ -1,0 +1,311 @@
+// Dense projection GEMM of the path, third generation -- sdetr_gemm_f16x3_pre ("3xFP16", fp32-class accuracy).
+//
+//   C[M,N] = act(A)[M,K] . W[N,K]^T + bias        fp32 in / fp32 out
+//
+// Same projections as gemm_tf32x3.cu (models/bricks/ms_deform_attn.py:316,322-328,375; salience_transformer.py:347-351,
+// :462, :16-47; base_transformer.py:111).  The 3xTF32 kernel there is bound by shared-memory bandwidth and by the TF32
+// tensor rate (profiles/r1_gemm_tcgen05_presplit_ncu_full.txt).  An fp16 significand is as wide as a TF32 one (11 bits),
+// so the same error-compensated product
+//
+//       x = hi + lo,  hi = fp16(x),  lo = fp16(x - hi)          C ~= A_hi.W_hi + A_hi.W_lo + A_lo.W_hi  (fp32 accumulate)
+//
+// keeps 22 significand bits per operand exactly like 3xTF32 (Ootomo & Yokota, "Recovering single precision accuracy from
+// Tensor Cores ...", 2022), but runs on tcgen05.mma.kind::f16: twice the K per instruction at the same issue cost and half
+// the operand bytes through shared memory.  What fp16 lacks is exponent range; it is restored with exact power-of-two
+// scalings: the activation is multiplied by 16 before the split (full accuracy for 2^-7 <= |x| < 4094, an ABSOLUTE error
+// floor of 2^-29 below that, inf -> NaN above: documented domain of this entry point), the weight by a per-tensor 2^s that
+// puts max|W| in [2^13, 2^14) when it is pre-split (cached per parameter), and the epilogue multiplies the accumulator by
+// the exact inverse 2^-(4+s) before adding the bias.
+//
+// Structure = the persistent kernel "P" of gemm_tf32x3.cu (one 512-thread CTA per SM walking a strided tile list; warp 0
+// TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..11 converters, warps 12..15 epilogue; double-buffered
+// accumulator in tensor memory; TMA-store epilogue), with a k-block of 64:
+//   stage (64 KB, x3): A raw fp32 as two 128x32 boxes (16 KB each, 128-byte swizzle) + W_hi + W_lo as 128x64 fp16 tiles
+//                      (16 KB each, 128-byte rows);
+//   converters:        thread (row, half) reads its 32 floats swizzle-aware, scales, splits, packs to f16x2 and writes
+//                      16 + 16 columns of the stage's TMEM slot with tcgen05.st (A operand comes from tensor memory);
+//   MMA:               4 k-steps (K = 16) x {hi.hi, hi.lo, lo.hi} = 12 tcgen05.mma.kind::f16 of 128x128x16 per k-block;
+//   TMEM map (512):    accumulators [0,128) and [128,256); A slot s at [256 + 64 s, 256 + 64 (s+1)): 32 columns A_hi
+//                      (64 halves) then 32 columns A_lo.
+// Shared-memory traffic per 128x128x64 block: TMA 64 KB + converter reads 32 KB + MMA operand reads 48 KB = 144 KB
+// (3xTF32: 224 KB for the same K) and 12 instead of 24 MMA instructions.
+#include <cuda_fp16.h>
+
+#include "umma.cuh"
+
+namespace sdetr {
+
+constexpr int kHM = 128, kHN = 128, kHK = 64;
+constexpr int kHStages = 3;
+constexpr int kHBox = 128 * 32 * 4;               // 16 KB: one A box (128 rows x 32 fp32) == one W tile (128 rows x 64 fp16)
+constexpr int kHStageBytes = 4 * kHBox;           // A box 0, A box 1, W_hi, W_lo
+constexpr int kHRingBytes = kHStages * kHStageBytes;  // 192 KB
+constexpr int kHOutBoxes = 2 * kHBox;             // two 128x32 fp32 staging boxes for the TMA stores
+constexpr int kHSmem = kHRingBytes + kHOutBoxes + 1024 + 256;
+constexpr int kHThreads = 512;
+constexpr int kHConvWarps = 8;
+constexpr float kActScale = 16.f;                 // activation pre-scale (exact), see header comment
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 << 4), A = B = f16 (format 0), both K-major, N, M
+constexpr uint32_t kIdescF16 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kHN >> 3) << 17) | ((uint32_t)(kHM >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_c),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16u(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+
+// (x0, x1) -> packed hi (f16x2: x0 in the low half = the lower k index) and packed lo of the residuals
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+struct HGemmParams {
+    const float *bias;
+    float *C;
+    int64_t ldc;
+    int M, N, K, act, use_tma_store;
+    float out_scale;  // 1 / (kActScale * weight scale), a power of two
+};
+
+__global__ void __launch_bounds__(kHThreads, 1)
+gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_whi,
+                  const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_c,
+                  const HGemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *boxes = smem + kHRingBytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kHRingBytes + kHOutBoxes);
+    uint64_t *tma_full = bars, *conv_full = bars + kHStages, *empty = bars + 2 * kHStages;
+    uint64_t *acc_full = bars + 3 * kHStages, *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nk = p.K / kHK;
+    const int n_tiles = (p.N + kHN - 1) / kHN, m_tiles = (p.M + kHM - 1) / kHM;
+    const int tiles = n_tiles * m_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kHStages; ++s) {
+            mbar_init(tma_full + s, 1);
+            mbar_init(conv_full + s, 32 * kHConvWarps);
+            mbar_init(empty + s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(acc_full + b, 1);
+            mbar_init(acc_empty + b, 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * kHM, n0 = (tile % n_tiles) * kHN;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int s = it % kHStages;
+                    mbar_wait(empty + s, ((it / kHStages) & 1) ^ 1);
+                    uint8_t *st = smem + s * kHStageBytes;
+                    mbar_expect_tx(tma_full + s, 4 * kHBox);
+                    tma_load_2d(&map_a, tma_full + s, st, kb * kHK, m0);
+                    tma_load_2d(&map_a, tma_full + s, st + kHBox, kb * kHK + 32, m0);
+                    tma_load_2d(&map_whi, tma_full + s, st + 2 * kHBox, kb * kHK, n0);
+                    tma_load_2d(&map_wlo, tma_full + s, st + 3 * kHBox, kb * kHK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t it = 0, tc = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tc) {
+                const uint32_t buf = tc & 1;
+                mbar_wait(acc_empty + buf, ((tc >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc = tmem_base + buf * 128u;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int s = it % kHStages;
+                    mbar_wait(conv_full + s, (it / kHStages) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t base = smem_u32(smem + s * kHStageBytes);
+                    const uint32_t a_hi = tmem_base + 256u + 64u * (uint32_t)s, a_lo = a_hi + 32u;
+                    const uint64_t d_hi = umma_desc(base + 2 * kHBox), d_lo = umma_desc(base + 3 * kHBox);
+#pragma unroll
+                    for (int k = 0; k < kHK / 16; ++k) {  // UMMA_K = 16 halves = 32 bytes = 2 sixteen-byte units, 8 TMEM columns
+                        umma_f16_ts(acc, a_hi + 8u * k, d_hi + 2 * k, kIdescF16, (kb | k) != 0);
+                        umma_f16_ts(acc, a_hi + 8u * k, d_lo + 2 * k, kIdescF16, 1);
+                        umma_f16_ts(acc, a_lo + 8u * k, d_hi + 2 * k, kIdescF16, 1);
+                    }
+                    umma_commit(empty + s);
+                }
+                umma_commit(acc_full + buf);
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ===== converters: landed fp32 A boxes -> scaled, split, packed f16x2 -> TMEM slot =====
+        const int q = warp & 3, half = (warp - 4) >> 2, r_in = q * 32 + lane;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < nk; ++kb, ++it) {
+                const int s = it % kHStages;
+                mbar_wait(tma_full + s, (it / kHStages) & 1);
+                const uint8_t *arow = smem + s * kHStageBytes + half * kHBox + r_in * 128;
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {  // logical 16-byte chunk c of this row sits at physical chunk c ^ (row & 7)
+                    float4 x = *reinterpret_cast<const float4 *>(arow + ((c ^ (r_in & 7)) << 4));
+                    if (p.act == 1) {
+                        x.x = fmaxf(x.x, 0.f), x.y = fmaxf(x.y, 0.f), x.z = fmaxf(x.z, 0.f), x.w = fmaxf(x.w, 0.f);
+                    } else if (p.act == 2) {
+                        x.x = gelu_erf(x.x), x.y = gelu_erf(x.y), x.z = gelu_erf(x.z), x.w = gelu_erf(x.w);
+                    }
+                    split2(x.x * kActScale, x.y * kActScale, hi[2 * c], lo[2 * c]);
+                    split2(x.z * kActScale, x.w * kActScale, hi[2 * c + 1], lo[2 * c + 1]);
+                }
+                const uint32_t slot = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + 64u * (uint32_t)s + 16u * (uint32_t)half;
+                tmem_st16u(slot, hi);
+                tmem_st16u(slot + 32u, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(conv_full + s);
+            }
+        }
+    } else if (warp >= 12) {
+        // ===== epilogue: TMEM -> registers -> * 2^-(4+s) + bias -> swizzled box -> TMA store (or direct stores) =====
+        const int q = warp & 3, r_in = q * 32 + lane;
+        const bool elected = threadIdx.x == 12 * 32;
+        const float sc = p.out_scale;
+        uint32_t tc = 0, box_it = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tc) {
+            const int m0 = (tile / n_tiles) * kHM, n0 = (tile % n_tiles) * kHN;
+            const uint32_t buf = tc & 1;
+            mbar_wait(acc_full + buf, (tc >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = m0 + r_in;
+#pragma unroll 1
+            for (int c = 0; c < kHN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128u + (uint32_t)(c * 32), r);
+                if (c == kHN / 32 - 1) {  // last read of this accumulator: hand it back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(acc_empty + buf);
+                }
+                const int col0 = n0 + c * 32;
+                if (col0 >= p.N) continue;  // uniform across the CTA
+                if (p.use_tma_store) {
+                    // the two staging boxes alternate per ISSUED store (a skipped column block must not advance the counter)
+                    uint8_t *box = boxes + (box_it++ & 1) * kHBox;
+                    if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // box free again
+                    named_bar_sync(1, 128);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o = make_float4(__uint_as_float(r[j]) * sc, __uint_as_float(r[j + 1]) * sc,
+                                               __uint_as_float(r[j + 2]) * sc, __uint_as_float(r[j + 3]) * sc);
+                        if (p.bias && col0 + j + 3 < p.N) {
+                            const float4 bv = ldg_f4(p.bias + col0 + j);
+                            o.x += bv.x, o.y += bv.y, o.z += bv.z, o.w += bv.w;
+                        } else if (p.bias) {
+                            if (col0 + j < p.N) o.x += __ldg(p.bias + col0 + j);
+                            if (col0 + j + 1 < p.N) o.y += __ldg(p.bias + col0 + j + 1);
+                            if (col0 + j + 2 < p.N) o.z += __ldg(p.bias + col0 + j + 2);
+                        }
+                        *reinterpret_cast<float4 *>(box + r_in * 128 + (((j >> 2) ^ (r_in & 7)) << 4)) = o;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    named_bar_sync(1, 128);
+                    if (elected) {
+                        tma_store_2d(&map_c, box, col0, m0);  // clips rows >= M and columns >= N
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                } else if (row < p.M) {
+                    float *crow = p.C + (int64_t)row * p.ldc;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < p.N) crow[col0 + j] = __uint_as_float(r[j]) * sc + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
+                }
+            }
+        }
+        if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
+
+// weight split: (N,K) fp32 -> W_hi = fp16(scale * W), W_lo = fp16(scale * W - W_hi)   (scale: a power of two)
+__global__ void split_f16_pair_kernel(const float *__restrict__ w, int64_t n, float scale, __half *__restrict__ hi,
+                                      __half *__restrict__ lo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = w[i] * scale;
+    const __half h = __float2half_rn(x);
+    hi[i] = h, lo[i] = __float2half_rn(x - __half2float(h));
+}
+
+}  // namespace sdetr
+
+using namespace sdetr;
+
+extern "C" int sdetr_split_f16_pair(const float *w, int64_t count, float scale, void *w_hi, void *w_lo, sdetr_stream_t stream) {
+    SDETR_REQUIRE(w && w_hi && w_lo, SDETR_ERR_INVALID_ARG, "split_f16_pair: null pointer");
+    SDETR_REQUIRE(scale > 0.f, SDETR_ERR_INVALID_ARG, "split_f16_pair: scale must be positive (a power of two)");
+    if (count <= 0) return SDETR_OK;
+    split_f16_pair_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        w, count, scale, reinterpret_cast<__half *>(w_hi), reinterpret_cast<__half *>(w_lo));
+    return check_launch("split_f16_pair");
+}
+
+extern "C" int sdetr_gemm_f16x3_pre(const float *A, int64_t lda, const void *W_hi, const void *W_lo, float w_scale,
+                                    const float *bias, float *C, int64_t ldc, int M, int N, int K, int act,
+                                    sdetr_stream_t stream) {
+    SDETR_REQUIRE(A && W_hi && W_lo && C, SDETR_ERR_INVALID_ARG, "gemm_f16x3_pre: null pointer");
+    SDETR_REQUIRE(M >= 0 && N > 0 && K > 0 && act >= 0 && act <= 2, SDETR_ERR_INVALID_ARG, "gemm_f16x3_pre: bad sizes / activation");
+    SDETR_REQUIRE(K % kHK == 0, SDETR_ERR_UNSUPPORTED, "gemm_f16x3_pre: K=%d must be a multiple of %d", K, kHK);
+    SDETR_REQUIRE(w_scale > 0.f, SDETR_ERR_INVALID_ARG, "gemm_f16x3_pre: weight scale must be positive");
+    SDETR_REQUIRE(lda % 4 == 0 && aligned16(A) && aligned16(W_hi) && aligned16(W_lo) && lda >= K && ldc >= N,
+                  SDETR_ERR_INVALID_ARG, "gemm_f16x3_pre: operands must be 16-byte aligned with 16-byte row pitch");
+    if (M == 0) return SDETR_OK;
+    CUtensorMap ma, mh, ml, mc;
+    SDETR_REQUIRE(make_map_2d(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, A, M, K, lda, 32, kHM) &&
+                      make_map_2d(&mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, W_hi, N, K, K, kHK, kHN) &&
+                      make_map_2d(&ml, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, W_lo, N, K, K, kHK, kHN),
+                  SDETR_ERR_CUDA, "gemm_f16x3_pre: cuTensorMapEncodeTiled failed");
+    const int use_tma_store = (ldc % 4 == 0) && aligned16(C) &&
+                              make_map_2d(&mc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C, M, N, ldc, 32, kHM);
+    if (!use_tma_store) mc = ma;
+    static PerDeviceOnce once;
+    SDETR_OPT_IN_SMEM(once, gemm_f16x3_kernel, kHSmem, "gemm_f16x3_pre");
+    const int sms = sm_count();
+    HGemmParams p{bias, C, ldc, M, N, K, act, use_tma_store, 1.f / (kActScale * w_scale)};
+    const int tiles = ((N + kHN - 1) / kHN) * ((M + kHM - 1) / kHM);
+    gemm_f16x3_kernel<<<tiles < sms ? tiles : sms, kHThreads, kHSmem, (cudaStream_t)stream>>>(ma, mh, ml, mc, p);
+    return check_launch("gemm_f16x3_pre");
+}

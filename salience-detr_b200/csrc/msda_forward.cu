@@ -212,10 +212,10 @@ struct SlotLoop {
 };
 
 // ---- the specialised kernel -------------------------------------------------------------------------
-template <int D, int L, int P, bool FUSED, bool HEAD_MAJOR, int MINB, bool SMEM_BCAST = false>
-__global__ void __launch_bounds__(kThreads, MINB) msda_fwd_kernel(const MsdaFwdParams p) {
+template <int D, int L, int P, bool FUSED, bool HEAD_MAJOR, int MINB, bool SMEM_BCAST = false, int THREADS = kThreads>
+__global__ void __launch_bounds__(THREADS, MINB) msda_fwd_kernel(const MsdaFwdParams p) {
     constexpr int LANES = D / 4;
-    constexpr int GROUPS = kThreads / LANES;
+    constexpr int GROUPS = THREADS / LANES;
     constexpr int NP = L * P;
     constexpr int SLOTS = (NP + LANES - 1) / LANES;
     const int lane = threadIdx.x % LANES;
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_kernel(const MsdaFwdP
         const float *vbase = p.value + (int64_t)b * p.v_bstride + (int64_t)m * D + lane * 4;
         if constexpr (SMEM_BCAST) {
             static_assert(!SMEM_BCAST || (NP == 16 && LANES == 8), "shared-memory broadcast variant: 16 points, 8 lanes");
-            __shared__ __align__(16) char bc_smem[GROUPS * (kWStride + kPkStride)];
+            extern __shared__ __align__(16) char bc_smem[];  // GROUPS * (kWStride + kPkStride) bytes (dynamic)
             char *wsm = bc_smem + grp * kWStride;
             char *pksm = bc_smem + GROUPS * kWStride + grp * kPkStride;
 #pragma unroll
@@ -399,6 +399,7 @@ __global__ void __launch_bounds__(kThreads) msda_fwd_generic_kernel(const MsdaFw
 static std::atomic<int> g_bcast{1};  // 0 = shuffle broadcast, 1 = shared-memory broadcast (D=32, L=4, P=4 only)
 static std::atomic<int> g_minb{4};   // tuning knobs (sdetr_set_option)
 static std::atomic<int> g_chunk{64};
+static std::atomic<int> g_threads{256};  // head-major schedule: threads per CTA (256 x 4 CTAs/SM, 512 x 2, 1024 x 1)
 
 template <int D, int L, int P, int MINB>
 static void launch_special(const MsdaFwdParams &p, bool fused, int schedule, cudaStream_t s) {
@@ -440,15 +441,28 @@ static int msda_forward_dispatch(MsdaFwdParams p, bool fused, int head_dim, int 
     if (fused) special = (p.proj_stride % 4 == 0) && aligned16(p.proj);
     else special = aligned16(p.loc) && aligned16(p.attn);
     if (special && head_dim == 32 && levels == 4 && points == 4 && g_bcast == 1) {
-        constexpr int GROUPS = kThreads / 8;
+        const int threads = schedule == 1 ? g_threads.load() : kThreads;
+        const int groups = threads / 8;
+        const size_t smem = (size_t)groups * (kWStride + kPkStride);
         if (schedule == 1) {
             dim3 grid((p.nq + p.chunk - 1) / p.chunk, p.heads, p.batch);
-            if (fused) msda_fwd_kernel<32, 4, 4, true, true, 4, true><<<grid, kThreads, 0, s>>>(p);
-            else msda_fwd_kernel<32, 4, 4, false, true, 4, true><<<grid, kThreads, 0, s>>>(p);
+            if (threads == 1024) {
+                static PerDeviceOnce o1, o2;
+                SDETR_OPT_IN_SMEM(o1, (msda_fwd_kernel<32, 4, 4, true, true, 1, true, 1024>), smem, "msda_forward");
+                SDETR_OPT_IN_SMEM(o2, (msda_fwd_kernel<32, 4, 4, false, true, 1, true, 1024>), smem, "msda_forward");
+                if (fused) msda_fwd_kernel<32, 4, 4, true, true, 1, true, 1024><<<grid, 1024, smem, s>>>(p);
+                else msda_fwd_kernel<32, 4, 4, false, true, 1, true, 1024><<<grid, 1024, smem, s>>>(p);
+            } else if (threads == 512) {
+                if (fused) msda_fwd_kernel<32, 4, 4, true, true, 2, true, 512><<<grid, 512, smem, s>>>(p);
+                else msda_fwd_kernel<32, 4, 4, false, true, 2, true, 512><<<grid, 512, smem, s>>>(p);
+            } else {
+                if (fused) msda_fwd_kernel<32, 4, 4, true, true, 4, true><<<grid, kThreads, smem, s>>>(p);
+                else msda_fwd_kernel<32, 4, 4, false, true, 4, true><<<grid, kThreads, smem, s>>>(p);
+            }
         } else {
-            dim3 grid((unsigned)(((int64_t)p.nq * p.heads + GROUPS - 1) / GROUPS), p.batch);
-            if (fused) msda_fwd_kernel<32, 4, 4, true, false, 4, true><<<grid, kThreads, 0, s>>>(p);
-            else msda_fwd_kernel<32, 4, 4, false, false, 4, true><<<grid, kThreads, 0, s>>>(p);
+            dim3 grid((unsigned)(((int64_t)p.nq * p.heads + groups - 1) / groups), p.batch);
+            if (fused) msda_fwd_kernel<32, 4, 4, true, false, 4, true><<<grid, kThreads, smem, s>>>(p);
+            else msda_fwd_kernel<32, 4, 4, false, false, 4, true><<<grid, kThreads, smem, s>>>(p);
         }
     } else if (special && head_dim == 32 && levels == 4 && points == 4) {
         if (g_minb == 3) launch_special<32, 4, 4, 3>(p, fused, schedule, s);
@@ -481,6 +495,9 @@ extern "C" int sdetr_set_option(const char *name, int value) {
     } else if (eq("msda_smem_broadcast")) {
         SDETR_REQUIRE(value == 0 || value == 1, SDETR_ERR_INVALID_ARG, "set_option: msda_smem_broadcast in {0,1}");
         g_bcast = value;
+    } else if (eq("msda_threads")) {
+        SDETR_REQUIRE(value == 256 || value == 512 || value == 1024, SDETR_ERR_INVALID_ARG, "set_option: msda_threads in {256,512,1024}");
+        g_threads = value;
     } else if (eq("msda_chunk")) {
         SDETR_REQUIRE(value >= 8 && value <= 4096, SDETR_ERR_INVALID_ARG, "set_option: msda_chunk in 8..4096");
         g_chunk = value;

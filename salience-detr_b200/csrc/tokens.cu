@@ -610,7 +610,9 @@ struct FlattenArgs {
 __global__ void __launch_bounds__(256) flatten_tokens_kernel(FlattenArgs a, const float *__restrict__ level_embeds,
                                                              const float *__restrict__ keep, int nv, int C,
                                                              float *__restrict__ feat_tok, float *__restrict__ lpos_tok,
-                                                             float *__restrict__ x_tok) {
+                                                             float *__restrict__ x_tok, const float *__restrict__ pos_tok) {
+    // pos_tok != nullptr: the position embedding is already in token layout (b,Nv,C) (sdetr_sine_pos_tokens) -- only the
+    // feature maps are transposed here
     __shared__ float sf[32][33], sp[32][33];
     int l = 0;
 #pragma unroll
@@ -619,13 +621,13 @@ __global__ void __launch_bounds__(256) flatten_tokens_kernel(FlattenArgs a, cons
     const int t0 = ((int)blockIdx.x - a.tile0[l]) * 32, c0 = blockIdx.y * 32, b = blockIdx.z;
     const int hw = a.size[l];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-    const float *f = a.feat[l] + ((int64_t)b * C + c0) * hw, *p = a.pos[l] + ((int64_t)b * C + c0) * hw;
+    const float *f = a.feat[l] + ((int64_t)b * C + c0) * hw, *p = pos_tok ? nullptr : a.pos[l] + ((int64_t)b * C + c0) * hw;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int c = ty + 8 * i, t = t0 + tx;
         const bool ok = t < hw && c0 + c < C;
         sf[c][tx] = ok ? __ldg(f + (int64_t)c * hw + t) : 0.f;
-        sp[c][tx] = ok ? __ldg(p + (int64_t)c * hw + t) + __ldg(level_embeds + l * C + c0 + c) : 0.f;
+        if (!pos_tok) sp[c][tx] = ok ? __ldg(p + (int64_t)c * hw + t) + __ldg(level_embeds + l * C + c0 + c) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -633,7 +635,8 @@ __global__ void __launch_bounds__(256) flatten_tokens_kernel(FlattenArgs a, cons
         const int t = t0 + ty + 8 * i, c = c0 + tx;
         if (t < hw && c < C) {
             const int64_t row = (int64_t)b * nv + a.start[l] + t;
-            const float fv = sf[tx][ty + 8 * i], pv = sp[tx][ty + 8 * i];
+            const float fv = sf[tx][ty + 8 * i];
+            const float pv = pos_tok ? __ldg(pos_tok + row * C + c) + __ldg(level_embeds + l * C + c) : sp[tx][ty + 8 * i];
             feat_tok[row * C + c] = fv;
             lpos_tok[row * C + c] = pv;
             x_tok[row * C + c] = (fv + pv) * __ldg(keep + row);
@@ -642,10 +645,11 @@ __global__ void __launch_bounds__(256) flatten_tokens_kernel(FlattenArgs a, cons
 }
 }  // namespace sdetr
 
-extern "C" int sdetr_flatten_tokens(const float *const *feats_host, const float *const *pos_host, const float *level_embeds,
-                                    const float *keep, const int32_t *level_size_host, int batch, int channels,
-                                    int num_levels, float *feat_tok, float *lpos_tok, float *x_tok, sdetr_stream_t stream) {
-    SDETR_REQUIRE(feats_host && pos_host && level_embeds && keep && level_size_host && feat_tok && lpos_tok && x_tok,
+static int flatten_tokens_impl(const float *const *feats_host, const float *const *pos_host, const float *pos_tokens,
+                               const float *level_embeds, const float *keep, const int32_t *level_size_host, int batch,
+                               int channels, int num_levels, float *feat_tok, float *lpos_tok, float *x_tok,
+                               sdetr_stream_t stream) {
+    SDETR_REQUIRE(feats_host && (pos_host || pos_tokens) && level_embeds && keep && level_size_host && feat_tok && lpos_tok && x_tok,
                   SDETR_ERR_INVALID_ARG, "flatten_tokens: null pointer");
     SDETR_REQUIRE(batch > 0 && channels > 0 && num_levels > 0 && num_levels <= kMaxLevels, SDETR_ERR_INVALID_ARG,
                   "flatten_tokens: bad sizes");
@@ -653,16 +657,32 @@ extern "C" int sdetr_flatten_tokens(const float *const *feats_host, const float 
     a.L = num_levels;
     int nv = 0, tiles = 0;
     for (int l = 0; l < num_levels; ++l) {
-        SDETR_REQUIRE(feats_host[l] && pos_host[l] && level_size_host[l] > 0, SDETR_ERR_INVALID_ARG,
+        SDETR_REQUIRE(feats_host[l] && (pos_tokens || pos_host[l]) && level_size_host[l] > 0, SDETR_ERR_INVALID_ARG,
                       "flatten_tokens: level %d", l);
-        a.feat[l] = feats_host[l], a.pos[l] = pos_host[l], a.size[l] = level_size_host[l], a.start[l] = nv, a.tile0[l] = tiles;
+        a.feat[l] = feats_host[l], a.pos[l] = pos_tokens ? nullptr : pos_host[l], a.size[l] = level_size_host[l], a.start[l] = nv, a.tile0[l] = tiles;
         nv += level_size_host[l];
         tiles += (level_size_host[l] + 31) / 32;
     }
     a.tile0[num_levels] = tiles;
     dim3 grid(tiles, (channels + 31) / 32, batch);
-    flatten_tokens_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, level_embeds, keep, nv, channels, feat_tok, lpos_tok, x_tok);
+    flatten_tokens_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, level_embeds, keep, nv, channels, feat_tok, lpos_tok, x_tok,
+                                                                  pos_tokens);
     return check_launch("flatten_tokens");
+}
+
+extern "C" int sdetr_flatten_tokens(const float *const *feats_host, const float *const *pos_host, const float *level_embeds,
+                                    const float *keep, const int32_t *level_size_host, int batch, int channels,
+                                    int num_levels, float *feat_tok, float *lpos_tok, float *x_tok, sdetr_stream_t stream) {
+    return flatten_tokens_impl(feats_host, pos_host, nullptr, level_embeds, keep, level_size_host, batch, channels, num_levels,
+                               feat_tok, lpos_tok, x_tok, stream);
+}
+
+extern "C" int sdetr_flatten_tokens_pos(const float *const *feats_host, const float *pos_tokens, const float *level_embeds,
+                                        const float *keep, const int32_t *level_size_host, int batch, int channels,
+                                        int num_levels, float *feat_tok, float *lpos_tok, float *x_tok, sdetr_stream_t stream) {
+    SDETR_REQUIRE(pos_tokens, SDETR_ERR_INVALID_ARG, "flatten_tokens_pos: null position tokens");
+    return flatten_tokens_impl(feats_host, nullptr, pos_tokens, level_embeds, keep, level_size_host, batch, channels, num_levels,
+                               feat_tok, lpos_tok, x_tok, stream);
 }
 
 // ---- pre-attention gather: t = q[top], x = t + pos[top] (salience_transformer.py:368-371) -----------------------------

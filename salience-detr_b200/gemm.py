@@ -2,9 +2,10 @@
 
 These are true dense GEMMs, the only place of the path where tensor cores belong.  ``MODE``:
 
-* ``"auto"`` (default): the hand-written persistent tcgen05 kernel on a pre-split weight (``sdetr_gemm_3xtf32_pre``; fastest
-  or tied on every shape of the path, tools/bench_gemm.py, profiles/r1_gemm_shapes.txt), except GEMMs with at most
-  ``SMALL_M`` rows (the coarse levels of the MaskPredictor), which are latency-bound and go to cuBLAS fp32.
+* ``"auto"`` (default): the hand-written persistent tcgen05 kernels on a pre-split weight -- ``OWN_KERNEL = "f16x3"``:
+  ``sdetr_gemm_f16x3_pre`` (3xFP16 on ``tcgen05.mma.kind::f16``: same 22-bit operands as 3xTF32 at twice the MMA rate, for
+  K % 64 == 0); ``"tf32x3"`` (or K % 64 != 0): ``sdetr_gemm_3xtf32_pre`` -- except GEMMs with at most ``SMALL_M`` rows (the
+  coarse levels of the MaskPredictor), which are latency-bound and go to cuBLAS fp32.
 * ``"tcgen05"``: the hand-written sm_100a GEMM (``sdetr_gemm_3xtf32``: TMA -> in-kernel TF32 split of the activation
   -> tcgen05.mma.kind::tf32 into TMEM -> epilogue), same 3xTF32 arithmetic without the separate split pass.
 * ``"3xtf32"``: each operand is split into two TF32 pieces by ``sdetr_split_tf32`` and ONE cuBLAS TF32
@@ -27,6 +28,7 @@ from torch.nn import functional as F
 from . import cabi
 
 MODE = "auto"
+OWN_KERNEL = __import__("os").environ.get("SDETR_GEMM_KERNEL", "f16x3")  # "auto" / "tcgen05" own-kernel flavour: "f16x3" (3xFP16, K % 64 == 0) or "tf32x3" (3xTF32)
 PRESPLIT_PERSISTENT = True  # persistent kernel fed a pre-split weight (W_hi / W_lo TMA tiles) instead of splitting W in the kernel
 LONG_K_PRESPLIT = False  # K >= 1024: True = "SS" kernel with the pre-split weight, False = persistent raw-weight kernel "P" (measured equal or faster)
 SMALL_M = 2304  # "auto": at most this many rows -> cuBLAS fp32 (latency-bound; measured faster than either tensor-core path, tools/bench_small.py)
@@ -83,6 +85,21 @@ def split_weight_pair(weight: Tensor) -> Tuple[Tensor, Tensor]:
     return hit[1]
 
 
+_f16_cache: Dict[int, tuple] = {}
+
+
+def split_weight_f16(weight: Tensor):
+    """(N,K) -> cached (W_hi fp16, W_lo fp16, power-of-two scale); one host read of max|W| per parameter version."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape))
+    hit = _f16_cache.get(id(weight))
+    if hit is None or hit[0] != key or hit[2]() is not weight:
+        with torch.no_grad():
+            hit = (key, cabi.split_f16_pair(weight.detach()), weakref.ref(weight))
+        _prune(_f16_cache)
+        _f16_cache[id(weight)] = hit
+    return hit[1]
+
+
 _ACT = {None: 0, "relu": 1, "gelu": 2}
 
 
@@ -104,6 +121,9 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, relu_input:
             if k >= 1024 and LONG_K_PRESPLIT:   # long reductions: 4-stage ring, weight pre-split once (variant "SS")
                 w_hi, w_lo = split_weight_pair(weight)
                 return cabi.gemm_3xtf32(x, w_hi, w_lo, bias, relu_input)
+            if OWN_KERNEL == "f16x3" and MODE == "auto" and k % 64 == 0:
+                w_hi, w_lo, w_scale = split_weight_f16(weight)
+                return cabi.gemm_f16x3_pre(x, w_hi, w_lo, w_scale, bias, relu_input)
             if PRESPLIT_PERSISTENT:
                 w_hi, w_lo = split_weight_pair(weight)
                 return cabi.gemm_3xtf32_pre(x, w_hi, w_lo, bias, relu_input)

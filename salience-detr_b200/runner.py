@@ -33,7 +33,8 @@ class HostPipeline:
         self.h2d_bytes = self.d2h_bytes = 0
 
     def run(self, batches, on_output=None):
-        """batches: iterable of (feats_host, pos_host) pinned-memory level lists.  Returns the number processed;
+        """batches: iterable of (feats_host, pos_host) pinned-memory level lists (pos_host None / empty when the runners
+        derive the position embedding from the masks on the device).  Returns the number processed;
         ``on_output(i, host_memory)`` (optional) is called, in batch order, once batch i's output is in host memory.
         ``host_memory`` is the lane's pinned buffer: consume or copy it before returning -- a later batch overwrites it."""
         n = 0
@@ -46,7 +47,7 @@ class HostPipeline:
                 self.done[k].synchronize()
                 on_output(i - len(self.lanes), self.host_out[k])
             with torch.cuda.stream(self.h2d):
-                for dst, src in zip(lane.feats + lane.pos, list(feats_h) + list(pos_h)):
+                for dst, src in zip(lane.feats + lane.pos, list(feats_h) + list(pos_h or [])):
                     dst.copy_(src, non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(self.h2d)
@@ -81,7 +82,9 @@ class EncoderRunner:
         self.model = model.eval()
         self.dev = feats[0].device
         self.feats = [f.clone() for f in feats]      # static device buffers (graph inputs)
-        self.pos = [p.clone() for p in pos]
+        # pos None: the sine position embedding is derived from the masks on the device, once per plan, in token layout
+        # (model.attach_position_embedding) -- nothing to copy per step
+        self.pos = [p.clone() for p in pos] if pos is not None else []
         self.masks = [m.clone() for m in masks]
         self.use_order = use_order
         with torch.no_grad():
@@ -97,14 +100,14 @@ class EncoderRunner:
         with torch.cuda.stream(s), torch.no_grad():
             for _ in range(max(1, warmup)):          # also sizes cuBLAS workspaces before capture
                 n0 = cabi.launch_count()
-                self.memory, _ = self.model.forward_encoder(self.feats, self.masks, self.pos, plan=self.plan,
+                self.memory, _ = self.model.forward_encoder(self.feats, self.masks, self.pos or None, plan=self.plan,
                                                             use_order=self.use_order)
                 self.launches_per_step = cabi.launch_count() - n0
         s.synchronize()
         if use_graph:
             g = torch.cuda.CUDAGraph()
             with torch.no_grad(), torch.cuda.graph(g, stream=s):
-                self.memory, _ = self.model.forward_encoder(self.feats, self.masks, self.pos, plan=self.plan,
+                self.memory, _ = self.model.forward_encoder(self.feats, self.masks, self.pos or None, plan=self.plan,
                                                             use_order=self.use_order)
             self.graph = g
         torch.cuda.current_stream(self.dev).wait_stream(s)
@@ -115,14 +118,14 @@ class EncoderRunner:
             if self.graph is not None:
                 self.graph.replay()
             else:
-                self.memory, _ = self.model.forward_encoder(self.feats, self.masks, self.pos, plan=self.plan,
+                self.memory, _ = self.model.forward_encoder(self.feats, self.masks, self.pos or None, plan=self.plan,
                                                             use_order=self.use_order)
         return self.memory
 
     # -- host I/O ------------------------------------------------------------------------------------------------
-    def bind_host(self, feats_h: Sequence[torch.Tensor], pos_h: Sequence[torch.Tensor]):
-        """Pinned host staging for ``run_host`` (feature maps and position embeddings per level)."""
-        self._host_in = [t.pin_memory() if not t.is_pinned() else t for t in list(feats_h) + list(pos_h)]
+    def bind_host(self, feats_h: Sequence[torch.Tensor], pos_h: Optional[Sequence[torch.Tensor]] = None):
+        """Pinned host staging for ``run_host`` (feature maps and -- unless derived on the device -- position embeddings)."""
+        self._host_in = [t.pin_memory() if not t.is_pinned() else t for t in list(feats_h) + list(pos_h or [])]
         self._host_out = torch.empty(self.memory.shape, dtype=self.memory.dtype, pin_memory=True)
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self._host_in)
         self.d2h_bytes = self._host_out.numel() * self._host_out.element_size()

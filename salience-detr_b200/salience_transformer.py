@@ -33,6 +33,10 @@ from . import cabi, gemm
 from .ms_deform_attn import MultiScaleDeformableAttention
 
 OVERLAP_VALUE_PROJ = True  # inside a graph capture: all-layer value projection as a parallel branch beside the salience filter
+VALUE_PROJ_PER_LAYER = True  # each layer's value_proj as its own GEMM on a side stream beside that layer's (latency-bound)
+# pre-attention, joined right before the sampling kernel: the 45.7 MB it writes are still in the 126 MB L2 when the
+# sampling kernel gathers from them (one 6-layer GEMM up front writes 274 MB, which L2 cannot hold), and the value rows
+# are 1 KB apart instead of 6 KB
 FUSED_GELU_MEAN = True     # MaskPredictor: GELU + token-mean of the global half as two fused launches (else torch ops)
 FUSED_QUERY_SUM = True     # `query + query_pos` written by the gather and kept current by the fused pre-attention (no add kernel)
 FUSED_PRE_ATTENTION = True  # C = 256 / head_dim 32: gather+in-proj, attention, out-proj+LN+scatter as three kernels
@@ -223,11 +227,12 @@ class SalienceTransformerEncoderLayer(nn.Module):
         return q, None
 
     def forward_fast(self, q, qp, mc, ref_q, vbuf, v_bstride, v_tstride, v_off, num_value, spatial_shapes,
-                     level_start_index, order=None, schedule=MSDA_SCHEDULE, qs=None):
-        """``qs``: optional q + qp buffer (from the gather); the fused pre-attention keeps its rewritten rows current."""
+                     level_start_index, order=None, schedule=MSDA_SCHEDULE, qs=None, value_ready=None):
+        """``qs``: optional q + qp buffer (from the gather); the fused pre-attention keeps its rewritten rows current.
+        ``value_ready``: optional callable returning the value buffer, run right before the sampling launch."""
         q, qs = self._pre_attention_fast(q, qp, mc, qs)
         a = self.self_attn.forward_projected(qs if qs is not None else q + qp, ref_q, vbuf, v_bstride, v_tstride, v_off, num_value, spatial_shapes,
-                                             level_start_index, order, schedule)
+                                             level_start_index, order, schedule, value_ready=value_ready)
         q = cabi.add_layernorm(q, a, self.norm1.weight, self.norm1.bias, self.norm1.eps, out=q)
         h = gemm.linear(q, self.linear1.weight, self.linear1.bias)
         f = gemm.linear(h, self.linear2.weight, self.linear2.bias, relu_input=True)  # ReLU fused into the operand split
@@ -259,6 +264,13 @@ class SalienceTransformerEncoder(nn.Module):
             rx = xs[None, None, :].expand(1, h, w).reshape(1, -1) / (valid_ratios[:, None, lvl, 0] * w)
             refs.append(torch.stack((rx, ry), -1))
         return torch.cat(refs, 1)[:, :, None] * valid_ratios[:, None]
+
+    def _side_stream(self, device):
+        streams = self.__dict__.setdefault("_side_streams", {})
+        key = str(device)
+        if key not in streams:
+            streams[key] = torch.cuda.Stream(device=device)
+        return streams[key]
 
     def _value_projection(self):
         """[6*C, C] weight / [6*C] bias of all layers' value_proj (rebuilt when any of them changes)."""
@@ -294,12 +306,20 @@ class SalienceTransformerEncoder(nn.Module):
         b, nv, c = query.shape
         L = spatial_shapes.shape[0]
         M = self.layers[0].self_attn.num_heads
+        query = query.contiguous()  # the reference hands over a transposed view (base_transformer.py:21-26)
         mask_u8 = query_key_padding_mask.to(torch.uint8).contiguous()
         focus = focus_token_nums.to(torch.int32).contiguous()
-        # one GEMM for the value projections of all layers; zero the padded rows once
-        vbuf = value_buffer if value_buffer is not None else self.project_values(query, mask_u8)
-        wide = vbuf.shape[-1]
+        per_layer = VALUE_PROJ_PER_LAYER and value_buffer is None
+        if per_layer:
+            cur = torch.cuda.current_stream(query.device)
+            side = self._side_stream(query.device)
+            vbuf, wide = None, c
+        else:  # one GEMM for the value projections of all layers; zero the padded rows once
+            vbuf = value_buffer if value_buffer is not None else self.project_values(query, mask_u8)
+            wide = vbuf.shape[-1]
         out = query.clone()  # `value` stays the original tokens (:452); `out` is updated in place
+        spatial_shapes = spatial_shapes.to(torch.int64).contiguous()
+        level_start_index = level_start_index.to(torch.int64).contiguous()
         pos = query_pos.contiguous()
         fg = foreground_score.contiguous()
         vr = valid_ratios.contiguous()
@@ -312,9 +332,23 @@ class SalienceTransformerEncoder(nn.Module):
                 q, qp, fq, rq, qs = cabi.token_gather(out, pos, fg, vr, inds, spatial_shapes, level_start_index, nq, want_sum=True)
             else:
                 q, qp, fq, rq = cabi.token_gather(out, pos, fg, vr, inds, spatial_shapes, level_start_index, nq)
+            ready = None
+            if per_layer:
+                # fork: this layer's value_proj (all Nv tokens, ms_deform_attn.py:316-319) runs beside the gather / class
+                # head / 300-token pre-attention; `ready` joins it right before the sampling kernel
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    vj = layer.self_attn.project_value(query, None)
+                    cabi.zero_masked_rows_(vj, c, c, mask_u8, b * nv)
+
+                def ready(vj=vj):
+                    cur.wait_stream(side)
+                    vj.record_stream(cur)
+                    return vj
             mc = cabi.class_max_times_fg(gemm.linear(q, self.enhance_mcsp.weight, self.enhance_mcsp.bias), fq)
-            q = layer.forward_fast(q, qp, mc, rq, vbuf, nv * wide, wide, j * c, nv, spatial_shapes, level_start_index,
-                                   None if query_orders is None else query_orders[j], qs=qs)
+            q = layer.forward_fast(q, qp, mc, rq, vbuf, nv * wide, wide, 0 if per_layer else j * c, nv, spatial_shapes,
+                                   level_start_index, None if query_orders is None else query_orders[j], qs=qs,
+                                   value_ready=ready)
             cabi.token_scatter_(out, q, inds, focus)
         if multi_level_masks is not None:
             cabi.background_embed_(out, mask_u8, inds, self.background_embedding.row_embed.weight,
@@ -381,6 +415,9 @@ class SalienceTransformer(nn.Module):
         self.encoder_class_head = nn.Linear(self.embed_dim, num_classes)
         self.encoder.enhance_mcsp = self.encoder_class_head
         self.enc_mask_predictor = MaskPredictor(self.embed_dim, self.embed_dim)
+        # not a sub-module of the reference transformer (the detector owns it, salience_detr.py:150-176); attach one
+        # (``position_encoding.PositionEmbeddingSine``) to let forward_encoder derive the embeddings from the masks
+        self.__dict__["position_embedding"] = None
         self.init_weights()
 
     def init_weights(self):
@@ -399,10 +436,23 @@ class SalienceTransformer(nn.Module):
         return streams[key]
 
     # -- plan ------------------------------------------------------------------------------------------------
+    def _ratios_host(self):
+        """Host copies of the two ratio buffers (one device read per buffer version, not one per plan)."""
+        key = (self.level_filter_ratio.data_ptr(), self.level_filter_ratio._version, self.layer_filter_ratio.data_ptr(),
+               self.layer_filter_ratio._version)
+        if self.__dict__.get("_ratio_key") != key:
+            self.__dict__["_ratio_key"] = key
+            self.__dict__["_ratio_host"] = (self.level_filter_ratio.detach().float().cpu().numpy().copy(),
+                                            self.layer_filter_ratio.detach().float().cpu().numpy().copy())
+        return self.__dict__["_ratio_host"]
+
     @torch.no_grad()
     def make_plan(self, multi_level_masks: Sequence[Tensor]) -> EncoderPlan:
-        """Token budgets (:117-121, :161-165), level tables (base_transformer.py:34-56) and the proposal keep
-        mask (base_transformer.py:74-110) from the padding masks.  One device->host copy."""
+        """Token budgets (:117-121, :161-165), level tables (base_transformer.py:34-56), the proposal keep mask
+        (base_transformer.py:74-110) and the normalised coordinates of the sine position embedding from the padding
+        masks.  CUDA masks: two launches (``sdetr_mask_plan``) + ONE device->host copy of b*L ints.  CPU masks (host-logic
+        tests only): the same arithmetic in torch ops."""
+        import numpy as np
         dev = multi_level_masks[0].device
         b = multi_level_masks[0].shape[0]
         if len(multi_level_masks) != self.num_feature_levels:
@@ -414,30 +464,60 @@ class SalienceTransformer(nn.Module):
         spatial_shapes = torch.tensor(shapes_list, dtype=torch.int64, device=dev)
         level_start_index = torch.tensor(starts, dtype=torch.int64, device=dev)
         mask_flat = flatten_levels(multi_level_masks)
-        valid = torch.stack([(~m).sum((1, 2)) for m in multi_level_masks], -1)           # (b,L) int64
-        focus = (valid * self.level_filter_ratio).int()                                  # fp32 multiply, truncate
-        vr, keep = [], []
-        for lvl, m in enumerate(multi_level_masks):
-            h, w = shapes_list[lvl]
-            vh, vw = (~m[:, :, 0]).sum(1), (~m[:, 0, :]).sum(1)
-            vr.append(torch.stack([vw.float() / w, vh.float() / h], -1))
-            gy = (torch.arange(h, dtype=torch.float32, device=dev) + 0.5)[None, :, None] / vh[:, None, None]
-            gx = (torch.arange(w, dtype=torch.float32, device=dev) + 0.5)[None, None, :] / vw[:, None, None]
-            ok = (gy > 0.01) & (gy < 0.99) & (gx > 0.01) & (gx < 0.99) & (0.01 < 0.05 * 2.0 ** lvl < 0.99)
-            keep.append((ok & ~m).flatten(1))
-        host = torch.cat([focus.max(0)[0].flatten(), focus.sum(-1).flatten()]).cpu().tolist()  # the one sync
-        level_token_nums, focus_host = host[:L], host[L:]
+        mask_u8 = mask_flat.to(torch.uint8).contiguous()
+        level_ratio, layer_ratio = self._ratios_host()
+        scratch = {}
+        if mask_flat.is_cuda:
+            pe = getattr(self, "position_embedding", None)
+            mp = cabi.mask_plan(mask_u8, shapes_list, level_ratio.tolist(), *((pe.offset, pe.eps, pe.scale) if pe is not None
+                                                                              else (-0.5, 1e-6, 2 * 3.141592653589793)))
+            focus = mp["focus"]
+            focus_np = focus.cpu().numpy()                                               # the one sync
+            keep, valid_ratios = mp["keep"].unsqueeze(-1), mp["valid_ratios"]
+            scratch["ynorm"], scratch["xnorm"] = mp["ynorm"], mp["xnorm"]
+            focus_sum = focus.sum(-1).to(torch.int32).contiguous()
+        else:
+            valid = torch.stack([(~m).sum((1, 2)) for m in multi_level_masks], -1)       # (b,L) int64
+            focus = (valid * self.level_filter_ratio).int()                              # fp32 multiply, truncate
+            vr, keep = [], []
+            for lvl, m in enumerate(multi_level_masks):
+                h, w = shapes_list[lvl]
+                vh, vw = (~m[:, :, 0]).sum(1), (~m[:, 0, :]).sum(1)
+                vr.append(torch.stack([vw.float() / w, vh.float() / h], -1))
+                gy = (torch.arange(h, dtype=torch.float32, device=dev) + 0.5)[None, :, None] / vh[:, None, None]
+                gx = (torch.arange(w, dtype=torch.float32, device=dev) + 0.5)[None, None, :] / vw[:, None, None]
+                ok = (gy > 0.01) & (gy < 0.99) & (gx > 0.01) & (gx < 0.99) & (0.01 < 0.05 * 2.0 ** lvl < 0.99)
+                keep.append((ok & ~m).flatten(1))
+            keep = torch.cat(keep, 1).unsqueeze(-1).float()
+            valid_ratios = torch.stack(vr, 1).contiguous()
+            focus_np = focus.numpy()
+            focus_sum = focus.sum(-1).to(torch.int32).contiguous()
+        level_token_nums = [int(x) for x in focus_np.max(0)]
+        focus_host = [int(x) for x in focus_np.sum(-1)]
         K = sum(level_token_nums)
-        ratios = self.layer_filter_ratio.detach().float().cpu()
-        layer_nq = (K * ratios).to(torch.int64).tolist()                                 # :164
+        layer_nq = [int(x) for x in (np.float32(K) * layer_ratio.astype(np.float32)).astype(np.int64)]  # :164, fp32 multiply
         return EncoderPlan(
             shapes_list=shapes_list, spatial_shapes=spatial_shapes, level_start_index=level_start_index,
             level_start=starts, level_size=sizes, level_width=[w for _, w in shapes_list],
             level_stride=(self.level_strides + [self.level_strides[-1] * 2] * L)[:L], mask_flat=mask_flat,
-            mask_u8=mask_flat.to(torch.uint8).contiguous(), keep=torch.cat(keep, 1).unsqueeze(-1).float(),
-            valid_ratios=torch.stack(vr, 1).contiguous(), level_token_nums=level_token_nums,
-            focus_token_nums=focus.sum(-1).to(torch.int32).contiguous(), focus_host=focus_host, num_selected=K,
-            layer_num_query=layer_nq)
+            mask_u8=mask_u8, keep=keep, valid_ratios=valid_ratios, level_token_nums=level_token_nums,
+            focus_token_nums=focus_sum, focus_host=focus_host, num_selected=K, layer_num_query=layer_nq, scratch=scratch)
+
+    def attach_position_embedding(self, module) -> "SalienceTransformer":
+        """Attach the detector's position-embedding module WITHOUT registering it as a sub-module (the reference
+        transformer's state_dict has no such entry)."""
+        self.__dict__["position_embedding"] = module
+        return self
+
+    def position_tokens(self, plan: EncoderPlan) -> Tensor:
+        """(b,Nv,C) sine position embedding of the plan's masks in token layout (computed once per plan, on the device,
+        by ``self.position_embedding`` -- the detector's module, models/detectors/salience_detr.py:172-176)."""
+        pe = getattr(self, "position_embedding", None)
+        if pe is None:
+            raise RuntimeError("no position embeddings given and no `position_embedding` module attached to the transformer")
+        if "pos_tokens" not in plan.scratch:
+            plan.scratch["pos_tokens"] = pe.tokens(plan.scratch["ynorm"], plan.scratch["xnorm"])
+        return plan.scratch["pos_tokens"]
 
     # -- salience filter (:112-168) ------------------------------------------------------------------------------
     def salience_filter(self, feat: Tensor, lpos: Tensor, plan: EncoderPlan, want_order: bool = True,
@@ -478,7 +558,7 @@ class SalienceTransformer(nn.Module):
         return raw, inds, score, fg, order
 
     # -- encoder half ---------------------------------------------------------------------------------------------
-    def forward_encoder(self, multi_level_feats, multi_level_masks, multi_level_pos_embeds,
+    def forward_encoder(self, multi_level_feats, multi_level_masks, multi_level_pos_embeds=None,
                         plan: Optional[EncoderPlan] = None, use_order: bool = True):
         """(b,C,H_l,W_l) feats, (b,H_l,W_l) bool masks, (b,C,H_l,W_l) pos -> memory (b,Nv,C) + aux dict.
 
@@ -487,7 +567,12 @@ class SalienceTransformer(nn.Module):
             plan = self.make_plan(multi_level_masks)
         grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         x = None
-        if grad or multi_level_feats[0].dtype != torch.float32:
+        if multi_level_pos_embeds is None:  # position embedding computed on the device from the masks, in token layout
+            if grad:
+                raise RuntimeError("training path: pass the per-level position embeddings explicitly")
+            feat, lpos, x = cabi.flatten_tokens_pos([f.contiguous() for f in multi_level_feats], self.position_tokens(plan),
+                                                    self.level_embeds.detach().contiguous(), plan.keep.view(plan.keep.shape[0], -1))
+        elif grad or multi_level_feats[0].dtype != torch.float32:
             feat = flatten_levels(multi_level_feats)
             lpos = flatten_levels([p + e.view(1, -1, 1, 1) for p, e in zip(multi_level_pos_embeds, self.level_embeds)])
         else:  # one fused pass: token layout + level embedding + (feat + pos) * keep
@@ -495,7 +580,7 @@ class SalienceTransformer(nn.Module):
                                                 [p.contiguous() for p in multi_level_pos_embeds],
                                                 self.level_embeds.detach().contiguous(), plan.keep.view(plan.keep.shape[0], -1))
         vbuf = None
-        if OVERLAP_VALUE_PROJ and not grad and feat.is_cuda and torch.cuda.is_current_stream_capturing():
+        if OVERLAP_VALUE_PROJ and not VALUE_PROJ_PER_LAYER and not grad and feat.is_cuda and torch.cuda.is_current_stream_capturing():
             # fork: the (large) value projection only needs the tokens, so it becomes a parallel branch of the captured
             # CUDA graph, running beside the salience filter's many small kernels (eager calls stay on one stream)
             cur = torch.cuda.current_stream(feat.device)

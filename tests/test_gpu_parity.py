@@ -33,6 +33,7 @@ def _restore_global_state(pkg):
     mode = pkg.gemm.MODE
     yield
     pkg.gemm.MODE = mode
+    pkg.gemm.OWN_KERNEL = os.environ.get("SDETR_GEMM_KERNEL", "f16x3")
     pkg.cabi.set_option("msda_smem_broadcast", 1)
     pkg.cabi.lib().sdetr_gemm_set_variant(0)
     pkg.cabi.lib().sdetr_gemm_set_variant(3)
@@ -526,6 +527,61 @@ def test_gemm_tcgen05_3xtf32(pkg):
         pkg.gemm.MODE = prev
 
 
+def test_gemm_f16x3_accuracy_and_range(pkg):
+    """3xFP16 persistent kernel (tcgen05.mma.kind::f16 on hi/lo fp16 pairs, power-of-two range scalings) against an fp64
+    reference: the same fp32-class error as 3xTF32 / SGEMM on O(1) data, across the documented activation range
+    (2^-7 .. 4094 relative accuracy, absolute floor below), with the fused input activations, ragged N, strided rows,
+    many tiles per CTA, and bit-reproducible."""
+    g = torch.Generator().manual_seed(7)
+    F = torch.nn.functional
+    for rows, K, N, act in [(128, 64, 128, None), (300, 256, 384, None), (4097, 256, 256, None), (1000, 2048, 256, "relu"),
+                            (333, 256, 91, None), (50, 64, 1, None), (22726, 256, 1536, None), (513, 128, 64, "gelu"),
+                            (36264, 256, 91, None), (40000, 64, 33, None)]:
+        x = torch.randn(rows, K, generator=g).to(DEV)
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+        b = torch.randn(N, generator=g).to(DEV)
+        w_hi, w_lo, sc = pkg.cabi.split_f16_pair(w)
+        assert 2 ** 13 <= float(w.abs().max()) * sc < 2 ** 14
+        assert ((w_hi.float() + w_lo.float()) / sc - w).abs().max() < 2e-7 * float(w.abs().max())  # 22-bit weight
+        y = pkg.cabi.gemm_f16x3_pre(x, w_hi, w_lo, sc, b, {None: 0, "relu": 1, "gelu": 2}[act])
+        xa = x.double() if act is None else (F.relu(x.double()) if act == "relu" else F.gelu(x.double()))
+        ref = F.linear(xa, w.double(), b.double())
+        err = (y.double() - ref).abs().max().item()
+        pkg.gemm.MODE = "fp32"
+        e32 = (pkg.gemm.linear(x if act is None else (F.relu(x) if act == "relu" else F.gelu(x)), w, b).double() - ref).abs().max().item()
+        assert err < 3e-4 and err < 32 * e32 + 1e-6, (rows, K, N, err, e32)
+        assert torch.equal(pkg.cabi.gemm_f16x3_pre(x, w_hi, w_lo, sc, b, {None: 0, "relu": 1, "gelu": 2}[act]), y)
+    # range: tiny, huge and mixed-magnitude activations; relative error of the result stays fp32-class
+    K, N = 256, 256
+    w = (torch.randn(N, K, generator=g) / 16).to(DEV)
+    w_hi, w_lo, sc = pkg.cabi.split_f16_pair(w)
+    for scale in (1e-3, 1e-2, 1.0, 100.0, 3000.0):
+        x = (torch.randn(2000, K, generator=g) * scale).clamp(-4000, 4000).to(DEV)
+        y = pkg.cabi.gemm_f16x3_pre(x, w_hi, w_lo, sc)
+        ref = x.double() @ w.double().t()
+        rel = ((y.double() - ref).abs().max() / ref.abs().max()).item()
+        assert rel < (2e-6 if scale >= 1e-2 else 2e-5), (scale, rel)  # below 2^-7 the absolute floor 2^-29 takes over
+    x = torch.randn(2000, K, generator=g).to(DEV) * torch.logspace(-4, 3, K).to(DEV)  # 7 decades inside one row
+    y = pkg.cabi.gemm_f16x3_pre(x, w_hi, w_lo, sc)
+    ref = x.double() @ w.double().t()
+    assert ((y.double() - ref).abs().max() / ref.abs().max()).item() < 2e-6
+    # strided rows (a column slice of a wider buffer), no bias; weight with a large dynamic range
+    wide = torch.randn(777, K + 64, generator=g).to(DEV)
+    w2 = (torch.randn(N, K, generator=g) * torch.logspace(-6, 0, K)).to(DEV)
+    h2, l2, s2 = pkg.cabi.split_f16_pair(w2)
+    y2 = pkg.cabi.gemm_f16x3_pre(wide[:, 64:], h2, l2, s2)
+    ref2 = wide[:, 64:].double() @ w2.double().t()
+    assert ((y2.double() - ref2).abs().max() / ref2.abs().max()).item() < 2e-6
+    # gemm.linear routes to it in the default mode, and to 3xTF32 when K % 64 != 0
+    pkg.gemm.MODE, pkg.gemm.OWN_KERNEL = "auto", "f16x3"
+    x = torch.randn(2, 3000, 256, generator=g).to(DEV)
+    y = pkg.gemm.linear(x, w, None)
+    assert y.shape == (2, 3000, 256) and (y.double() - x.double() @ w.double().t()).abs().max() < 1e-4
+    w96 = torch.randn(128, 96, generator=g).to(DEV) / 10
+    x96 = torch.randn(5000, 96, generator=g).to(DEV)
+    assert (pkg.gemm.linear(x96, w96).double() - x96.double() @ w96.double().t()).abs().max() < 1e-4
+
+
 # ---- module level ---------------------------------------------------------------------------------------------------
 @pytest.fixture(params=["fp32", "3xtf32", "tcgen05", "auto"])
 def gemm_mode(pkg, request):
@@ -852,6 +908,45 @@ def test_encoder_half_c256_vs_reference_golden(pkg):
         assert (rows.cpu() - g["memory_rows"]).abs().max() < tol_mem, mode
         assert (mem_inj.mean(-1).cpu() - g["memory_row_mean"]).abs().max() < tol_mem
         assert (mem_inj.abs().amax(-1).cpu() - g["memory_row_absmax"]).abs().max() < 2 * tol_mem
+
+
+def test_mask_plan_and_sine_position_tokens(pkg):
+    """Device-side plan (sdetr_mask_plan: budgets, valid ratios, keep mask, normalised coordinates) against the torch
+    restatement of the reference arithmetic (salience_transformer.py:116-121,161-165; base_transformer.py:48-56,74-110),
+    and the fused sine position embedding in token layout against PositionEmbeddingSine (position_encoding.py:48-65),
+    on even, ragged and non-rectangular masks; then the encoder half with the embedding derived on the device."""
+    from salience_detr_b200.synthetic import build_model, make_inputs, sine_position_embedding
+    model = build_model(layers=2).to(DEV)
+    pe = pkg.PositionEmbeddingSine(128, temperature=10000, normalize=True, offset=-0.5)
+    model.attach_position_embedding(pe)
+    cpu_model = build_model(layers=2)
+    for config in ("cpu_512", "resnet50_800_1333_bs2", "resnet50_800_1333_bs2_ragged", "resnet50_5scale_bs2", "holes"):
+        if config == "holes":  # arbitrary (non-rectangular) padding: the scans must be true cumulative sums
+            feats, masks, pos = make_inputs("resnet50_800_1333_bs2_ragged")
+            g = torch.Generator().manual_seed(3)
+            masks = [m | (torch.rand(m.shape, generator=g) < 0.2) for m in masks]
+            masks = [m & ~torch.zeros_like(m).index_fill_(2, torch.tensor([0]), True) & ~torch.zeros_like(m).index_fill_(1, torch.tensor([0]), True)
+                     for m in masks]  # keep the first row / column valid (non-zero valid sizes)
+            pos = [sine_position_embedding(m, 128) for m in masks]
+        else:
+            feats, masks, pos = make_inputs(config)
+        want = cpu_model.make_plan(masks)
+        got = model.make_plan([m.to(DEV) for m in masks])
+        assert got.level_token_nums == want.level_token_nums and got.focus_host == want.focus_host
+        assert got.layer_num_query == want.layer_num_query and got.num_selected == want.num_selected
+        assert torch.equal(got.focus_token_nums.cpu(), want.focus_token_nums)
+        assert torch.equal(got.valid_ratios.cpu(), want.valid_ratios)
+        assert torch.equal(got.keep.cpu(), want.keep)
+        tok = model.position_tokens(got)
+        ref = torch.cat([p.flatten(2) for p in pos], 2).transpose(1, 2)
+        assert (tok.cpu() - ref).abs().max() < 3e-6, config
+        m0 = masks[0].to(DEV)  # the module's reference-signature forward
+        assert (pe(m0).cpu() - pos[0]).abs().max() < 3e-6
+    feats, masks, pos = make_inputs("cpu_512", seed=2, device=DEV)
+    with torch.no_grad():
+        a, _ = model.forward_encoder(feats, masks, pos)
+        b2, _ = model.forward_encoder(feats, masks, None)
+    assert (a - b2).abs().max() < 2e-5
 
 
 # ---- the benched callable at the benched configuration --------------------------------------------------------------------
