@@ -331,6 +331,81 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_train(args, rank, world, local):
+    """--mode train (BASELINE.json configs[2]: training step, bs=2 per GPU, batch-sharded, NCCL gradient all-reduce):
+    encoder-half forward (training path: torch autograd around the MSDA forward / backward kernels) + backward of
+    loss = memory.square().mean() + bucketed all-reduce overlapped with the backward (dist.GradientBuckets) + SGD step.
+    An extra measurement, not the headline metric."""
+    import torch.distributed as dist
+    import salience_detr_b200 as pkg
+    from salience_detr_b200 import dist as sdist
+    from salience_detr_b200.synthetic import build_model, make_inputs
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    sdist.bind_to_gpu_numa_node(local)
+    sdist.init_from_env("nccl", dev)
+    model = build_model().to(dev).train()
+    feats, masks, pos = make_inputs(WORKLOAD, seed=sdist.shard_batch_seed(0, rank), device=dev)
+    params = [p for p in model.parameters() if p.requires_grad]
+    gb = sdist.GradientBuckets(params, bucket_bytes=args.bucket_mb << 20)
+    opt = torch.optim.SGD(params, lr=1e-5, foreach=True)
+    bsz = feats[0].shape[0]
+
+    def step(comm=True):
+        gb.active = comm and world > 1
+        gb.zero_()
+        mem, _ = model.forward_encoder(feats, masks, pos)
+        loss = mem.square().mean()
+        loss.backward()
+        gb.finish()
+        opt.step()
+        return loss
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return sdist.max_over_ranks(e0.elapsed_time(e1), dev)
+
+    steps, warmup = args.steps or 10, max(3, args.warmup or 3)
+    with ClockSampler(local) as clk:
+        ms = timed(step, steps, warmup)
+    ms_nocomm = timed(lambda: step(False), steps, 1) if world > 1 else ms
+    n0 = pkg.cabi.launch_count()
+    loss = step()
+    launches = pkg.cabi.launch_count() - n0
+    reached = sum(p.numel() * 4 for p in params if p.grad is not None and bool((p.grad != 0).any()))
+    if rank == 0:
+        print(json.dumps({
+            "metric": "images/sec encoder fwd+bwd+grad-allreduce+SGD @ 800x1333 bs=2/GPU (training path)",
+            "value": round(sdist.aggregate_throughput(bsz, steps, world, ms), 2), "unit": "images/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": round(ms / steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD + " training step", "batch_per_gpu": bsz, "global_batch": bsz * world,
+                       "parallelism": f"dp{world}: batch-sharded replicas, gradient all-reduce (mean) in {len(gb.buckets)} "
+                                      f"bucket(s) of <= {args.bucket_mb} MiB launched from autograd hooks, overlapped with backward",
+                       "loss": "memory.square().mean() (the salience-supervision / detection losses are outside the path)"},
+            "clocks": clk.summary(),
+            "allreduce": {"bytes_per_step": gb.total_bytes, "buckets": len(gb.buckets),
+                          "ms_per_step_without_allreduce": round(ms_nocomm / steps, 3),
+                          "exposed_ms_per_step": round((ms - ms_nocomm) / steps, 3),
+                          "bytes_with_nonzero_gradient": reached},
+            "gpu_launches_per_step": launches, "loss": float(loss)}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -341,6 +416,8 @@ def main():
     ap.add_argument("--no-order", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--gemm", default="auto", choices=["auto", "tcgen05", "3xtf32", "fp32", "tf32"])
+    ap.add_argument("--mode", default="forward", choices=["forward", "train"])
+    ap.add_argument("--bucket-mb", type=int, default=32)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -349,6 +426,10 @@ def main():
         args.steps = args.steps if args.steps is not None else 5
         args.warmup = args.warmup if args.warmup is not None else 1
         return run_reference(args, rank, world)
+    if args.mode == "train":
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --mode train needs a GPU")
+        return run_train(args, rank, world, local)
     args.steps = args.steps if args.steps is not None else 50
     args.warmup = max(3, args.warmup if args.warmup is not None else 10)
 

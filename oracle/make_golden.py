@@ -130,6 +130,40 @@ def make_encoder_tiny(name, image_sizes, padded, seed):
         **arrs, **sd)
 
 
+def make_encoder_tiny_grads(name, image_sizes, padded, seed):
+    """Gradients of the reference's own autograd through lines 106-183 for the tiny model of ``make_encoder_tiny`` (same
+    seed -> same weights and inputs): d loss / d parameter for every parameter the loss reaches and d loss / d feats,
+    loss = memory.square().mean().  Pins the training path (MSDA backward kernel inside torch autograd)."""
+    tr = ref_import.build_transformer(seed=seed, **TINY).train()  # dropout = 0.0: train() only enables grad paths
+    with torch.no_grad():
+        for layer in tr.encoder.layers:
+            layer.self_attn.sampling_offsets.weight.normal_(0, 0.05)
+            layer.self_attn.attention_weights.weight.normal_(0, 0.5)
+    feats, masks, pos = orc.synthetic_inputs(image_sizes, padded, TINY["embed_dim"], seed=seed)
+    feats = [f.requires_grad_(True) for f in feats]
+    captured = {}
+    enc_fwd = tr.encoder.forward
+
+    def spy(**kw):
+        captured["memory"] = enc_fwd(**kw)
+        raise _Stop()
+
+    tr.encoder.forward = spy
+    try:
+        tr(feats, masks, pos, None, None, None)
+    except _Stop:
+        pass
+    loss = captured["memory"].square().mean()
+    loss.backward()
+    out = {"loss": np_(loss)}
+    for n, p in tr.named_parameters():
+        if p.grad is not None:
+            out["grad." + n] = np_(p.grad)
+    for i, f in enumerate(feats):
+        out[f"grad_feat{i}"] = np_(f.grad)
+    np.savez_compressed(os.path.join(OUT, name), **out)
+
+
 C256 = dict(embed_dim=256, d_ffn=256, n_heads=8, n_levels=4, n_points=4, num_layers=2, num_classes=11,
             level_filter_ratio=(0.4, 0.8, 1.0, 1.0), layer_filter_ratio=(1.0, 0.5), topk_sa=64,
             max_num_embedding=80, num_proposals=30)
@@ -191,6 +225,7 @@ def main():
     make_encoder_tiny("encoder_tiny_even.npz", [(96, 128), (96, 128)], (96, 128), seed=5)
     make_encoder_tiny("encoder_tiny_ragged.npz", [(96, 128), (72, 90)], (96, 128), seed=6)
     make_encoder_c256()
+    make_encoder_tiny_grads("encoder_tiny_even_grads.npz", [(96, 128), (96, 128)], (96, 128), seed=5)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
     print("torch", torch.__version__)

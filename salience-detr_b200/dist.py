@@ -79,6 +79,89 @@ def allreduce_gradients_(params: Iterable[torch.nn.Parameter], bucket_bytes: int
     flush()
 
 
+class GradientBuckets:
+    """Bucketed gradient all-reduce OVERLAPPED with the backward pass (the one collective of the training configuration:
+    DDP / accelerate in the reference, main.py:144, util/engine.py:58).
+
+    Parameters are packed, in reverse registration order (~ the order their gradients become ready), into flat fp32
+    buckets of about ``bucket_bytes``; every ``p.grad`` is a VIEW into its bucket, so autograd accumulates straight into
+    the communication buffer (no flatten / copy-back passes).  A post-accumulate hook counts ready gradients and launches
+    the bucket's asynchronous ``all_reduce`` (NCCL over NVLink/NVSwitch on its own stream) as soon as the last one lands,
+    while autograd keeps running the backward of earlier layers.  ``finish()`` waits for the handles and turns sums into
+    means.  Over NVSwitch the cost is per-launch latency, not per-link bandwidth: few large buckets.
+
+    Usage per step:  buckets.zero_();  loss.backward();  buckets.finish();  optimizer.step()"""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 32 << 20, process_group=None):
+        self.group = process_group
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+        self.world = dist.get_world_size(process_group) if self.active else 1
+        params = [p for p in params if p.requires_grad]
+        self.buckets = []      # [(flat buffer, [params])]
+        self._bucket_of = {}
+        cur, size = [], 0
+        for p in reversed(params):
+            cur.append(p)
+            size += p.numel() * 4
+            if size >= bucket_bytes:
+                self._close(cur)
+                cur, size = [], 0
+        if cur:
+            self._close(cur)
+        self._pending = [0] * len(self.buckets)
+        self._handles = []
+        self.launch_order = []
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
+
+    def _close(self, ps):
+        n = sum(p.numel() for p in ps)
+        flat = torch.zeros(n, dtype=torch.float32, device=ps[0].device)
+        off = 0
+        for p in ps:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+            self._bucket_of[p] = len(self.buckets)
+        self.buckets.append((flat, list(ps)))
+
+    def zero_(self):
+        """Start of a step: clear the communication buffers (= all gradients) and the ready counters."""
+        for flat, _ in self.buckets:
+            flat.zero_()
+        self._pending = [len(ps) for _, ps in self.buckets]
+        self._handles, self.launch_order = [], []
+
+    def _on_grad(self, p):
+        i = self._bucket_of[p]
+        self._pending[i] -= 1
+        if self._pending[i] == 0:
+            self._launch(i)
+
+    def _launch(self, i):
+        self.launch_order.append(i)
+        if self.active:
+            self._handles.append(dist.all_reduce(self.buckets[i][0], group=self.group, async_op=True))
+
+    def finish(self):
+        """After backward: flush buckets whose parameters got no gradient this step, wait, sum -> mean."""
+        for i, n in enumerate(self._pending):
+            if n > 0:  # some parameter of the bucket was not reached by the loss: its slice is zero on every rank
+                self._pending[i] = 0
+                self._launch(i)
+        for h in self._handles:
+            h.wait()
+        if self.world > 1:
+            for flat, _ in self.buckets:
+                flat.div_(self.world)
+
+    @property
+    def total_bytes(self) -> int:
+        return sum(f.numel() * 4 for f, _ in self.buckets)
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+
+
 def bind_to_gpu_numa_node(device_index: int) -> dict:
     """Pin this process (and hence its later pinned-host allocations, first touch) to the CPUs of the NUMA node the GPU
     hangs off.  One rank per GPU launched by torchrun otherwise floats over both sockets: on the 8-GPU hosts GPUs 4-7 sit

@@ -799,15 +799,36 @@ def test_encoder_runner_graph_matches_eager(pkg):
 
 
 def test_encoder_training_path_gradients(pkg):
+    """Training path (torch autograd around the MSDA forward / backward kernels) against the REFERENCE's own autograd
+    (tests/golden/encoder_tiny_even_grads.npz, oracle/make_golden.py::make_encoder_tiny_grads): loss and the gradient of
+    every parameter the loss reaches, and of the input feature maps."""
     g, sd = load_golden("encoder_tiny_even")
+    gg, _ = load_golden("encoder_tiny_even_grads")
     tr = _tiny_model(pkg, sd).train()
     feats, masks, pos = _golden_inputs(g)
+    feats = [f.clone().requires_grad_(True) for f in feats]
     mem, _ = tr.forward_encoder(feats, masks, pos)
     assert (mem.detach().cpu() - g["memory"]).abs().max() < 2e-4  # dropout = 0 -> same values
-    mem.square().mean().backward()
-    for name, p in tr.named_parameters():
-        if name.startswith("encoder.layers") or name in ("level_embeds",):
-            assert p.grad is not None and torch.isfinite(p.grad).all(), name
+    loss = mem.square().mean()
+    assert abs(loss.item() - gg["loss"].item()) < 1e-5
+    loss.backward()
+    params = dict(tr.named_parameters())
+    checked = 0
+    for key, want in gg.items():
+        if key.startswith("grad."):
+            got = params[key[5:]].grad
+        elif key.startswith("grad_feat"):
+            got = feats[int(key[9:])].grad
+        else:
+            continue
+        assert got is not None, key
+        err = (got.cpu() - want).abs().max().item()
+        assert err <= 2e-3 * want.abs().max().item() + 1e-7, (key, err, want.abs().max().item())
+        checked += 1
+    assert checked == len(gg) - 1 and checked >= 70
+    for name, p in params.items():  # parameters the reference's loss does not reach stay without gradient here too
+        if ("grad." + name) not in gg:
+            assert p.grad is None or p.grad.abs().max() == 0, name
 
 
 # ---- error behaviour of the boundary (reference: AT_ASSERTM -> RuntimeError, .cu:20-30,42-44) ---------------------------
