@@ -561,7 +561,7 @@ def test_gemm_f16x3_accuracy_and_range(pkg):
         ref = x.double() @ w.double().t()
         rel = ((y.double() - ref).abs().max() / ref.abs().max()).item()
         assert rel < (2e-6 if scale >= 1e-2 else 2e-5), (scale, rel)  # below 2^-7 the absolute floor 2^-29 takes over
-    x = torch.randn(2000, K, generator=g).to(DEV) * torch.logspace(-4, 3, K).to(DEV)  # 7 decades inside one row
+    x = torch.randn(2000, K, generator=g).to(DEV) * torch.logspace(-4, 2, K).to(DEV)  # 6 decades inside one row (|x| < 4094)
     y = pkg.cabi.gemm_f16x3_pre(x, w_hi, w_lo, sc)
     ref = x.double() @ w.double().t()
     assert ((y.double() - ref).abs().max() / ref.abs().max()).item() < 2e-6
@@ -998,8 +998,9 @@ def test_config2_whole_path_benched_callable(pkg, config):
     assert pkg.gemm.MODE == "auto"
     runner = EncoderRunner(model, feats, masks, pos, use_graph=True, use_order=True)
     assert runner.graph is not None
-    got_graph = runner.step().clone()
+    got_graph = runner.step()   # asynchronous on the runner's stream
     torch.cuda.synchronize()
+    got_graph = got_graph.clone()
     plan = runner.plan
     if focus is not None:
         assert plan.focus_host == [int(f) for f in focus]
