@@ -87,6 +87,25 @@ int sdetr_msda_fused_forward(const float *value, int64_t value_batch_stride, int
                              int head_dim, int num_levels, int num_query, int num_points,
                              const int32_t *query_order, int schedule, sdetr_stream_t stream);
 
+/* Same with 4-d reference BOXES (cx, cy, w, h), the decoder's cross-attention (ms_deform_attn.py:345-349):
+ * ref_boxes (b,Nq,L,4), 16-byte aligned;  loc = ref_xy + off / P * ref_wh * 0.5  (the reference's operation order). */
+int sdetr_msda_fused_forward_boxes(const float *value, int64_t value_batch_stride, int64_t value_token_stride,
+                                   const int64_t *spatial_shapes, const int64_t *level_start_index,
+                                   const float *ref_boxes, const float *proj, int64_t proj_stride, float *output,
+                                   float *loc_out, float *attn_out, int batch, int num_value, int num_heads, int head_dim,
+                                   int num_levels, int num_query, int num_points, const int32_t *query_order, int schedule,
+                                   sdetr_stream_t stream);
+
+/* Two-stage proposal selection, NMS on token indices (SalienceTransformer.nms_on_topk_index, salience_transformer.py:
+ * 249-295 = torchvision.ops.batched_nms over boxes (x-1,y-1,x+1,y+1) on each (image, level) grid).  topk_index (b,k) int64:
+ * candidate tokens in descending score order (the rank decides who suppresses whom).  kept_index (b,k) int64 receives the
+ * surviving tokens in the same order (first kept_count[b] entries valid), keep_flag (b,k) uint8 (nullable) the per-
+ * candidate verdict.  k < 65535; the rank table (2 bytes per token) lives in shared memory: num_value up to ~98 000. */
+int sdetr_nms_topk_index(const int64_t *topk_index, int batch, int k, int num_value, int num_levels,
+                         const int32_t *level_h_host, const int32_t *level_w_host, float iou_threshold, int64_t *kept_index,
+                         int32_t *kept_count, uint8_t *keep_flag, sdetr_stream_t stream);
+
+
 /* MSDA core backward.  Replaces `_C.ms_deform_attn_backward`
  *   (ms_deform_attn_cuda.cu:75-145; kernels ms_deform_im2col_cuda.cuh:76-148, 290-392).
  * grad_output (b,Nq,M*D) -> grad_value (b,Nv,M,D), grad_sampling_loc, grad_attn_weight (shapes of the
@@ -320,6 +339,9 @@ int sdetr_split_f16_pair(const float *W, int64_t count, float scale, void *W_hi,
  * C row pitch ldc (TMA stores when ldc % 4 == 0). */
 int sdetr_gemm_f16x3_pre(const float *A, int64_t lda, const void *W_hi, const void *W_lo, float w_scale, const float *bias,
                          float *C, int64_t ldc, int M, int N, int K, int act, sdetr_stream_t stream);
+/* benchmarking knob: 0 (default) = always the streaming kernel, 1 = K <= 256 and >= 2 output tiles per work unit use the
+ * activation-stationary kernel (the split activation panel stays in tensor memory across the unit's output tiles) */
+int sdetr_gemm_f16x3_set_as(int enable);
 
 #ifdef __cplusplus
 }

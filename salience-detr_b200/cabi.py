@@ -31,6 +31,8 @@ SIGNATURES = {
     "sdetr_msda_forward": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
     "sdetr_msda_forward_ex": (_i, [_vp, _i64, _i64] + [_vp] * 5 + [_i] * 7 + [_vp, _i, _vp]),
     "sdetr_msda_fused_forward": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp] + [_i] * 7 + [_vp, _i, _vp]),
+    "sdetr_msda_fused_forward_boxes": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp] + [_i] * 7 + [_vp, _i, _vp]),
+    "sdetr_nms_topk_index": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
     "sdetr_msda_backward": (_i, [_vp] * 9 + [_i] * 7 + [_vp]),
     "sdetr_salience_select_workspace": (_sz, [_i, _i, _i]),
     "sdetr_salience_select": (_i, [_vp] * 7 + [_i] * 4 + [_vp] * 5 + [_sz, _vp]),
@@ -57,6 +59,7 @@ SIGNATURES = {
     "sdetr_mask_plan": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sdetr_sine_pos_tokens": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
     "sdetr_split_f16_pair": (_i, [_vp, _i64, _f, _vp, _vp, _vp]),
+    "sdetr_gemm_f16x3_set_as": (_i, [_i]),
     "sdetr_gemm_f16x3_pre": (_i, [_vp, _i64, _vp, _vp, _f, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
     "sdetr_flatten_tokens": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "sdetr_attention_small": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -179,7 +182,10 @@ def msda_fused_forward(value_buf, value_batch_stride, value_token_stride, value_
     if not value_buf.is_cuda or value_buf.dtype != torch.float32:
         raise RuntimeError("value must be a CUDA float32 tensor")
     t0 = _timer_event() if KERNEL_TIMERS is not None else None
-    rc = lib().sdetr_msda_fused_forward(
+    if ref_points.shape[-1] not in (2, 4):
+        raise ValueError(f"Last dim of reference_points must be 2 or 4, but get {ref_points.shape[-1]} instead.")
+    fn = lib().sdetr_msda_fused_forward if ref_points.shape[-1] == 2 else lib().sdetr_msda_fused_forward_boxes
+    rc = fn(
         value_buf.data_ptr() + 4 * value_offset, value_batch_stride, value_token_stride,
         _req(spatial_shapes, "spatial_shapes", torch.int64), _req(level_start_index, "level_start_index", torch.int64),
         _req(ref_points, "reference_points", torch.float32), proj.data_ptr(), proj.stride(1), out.data_ptr(),
@@ -190,6 +196,20 @@ def msda_fused_forward(value_buf, value_batch_stride, value_token_stride, value_
     if t0 is not None:
         KERNEL_TIMERS.setdefault("msda", []).append((t0, _timer_event()))
     return (out, loc, attn) if want_loc_attn else out
+
+
+def nms_topk_index(topk_index, shapes, iou_threshold=0.3):
+    """topk_index (b,k) int64, candidates in descending score order -> (kept_index (b,k), kept_count (b,) int32, keep_flag (b,k) u8)."""
+    b, k = topk_index.shape
+    dev = topk_index.device
+    kept = torch.empty(b, k, device=dev, dtype=torch.int64)
+    count = torch.empty(b, device=dev, dtype=torch.int32)
+    flag = torch.empty(b, k, device=dev, dtype=torch.uint8)
+    rc = lib().sdetr_nms_topk_index(_req(topk_index, "topk_index", torch.int64), b, k, sum(h * w for h, w in shapes), len(shapes),
+                                    _host_i32([h for h, _ in shapes]), _host_i32([w for _, w in shapes]), float(iou_threshold),
+                                    kept.data_ptr(), count.data_ptr(), flag.data_ptr(), _stream())
+    _check(rc, "sdetr_nms_topk_index")
+    return kept, count, flag
 
 
 def msda_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output):

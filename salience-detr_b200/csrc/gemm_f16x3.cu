@@ -260,6 +260,225 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
 }
 
+// ---- "AS": activation-stationary variant for K <= 256 ---------------------------------------------------------------------
+// The streaming kernel above re-reads the activation panel for every 128-column tile of the output, and its time follows
+// the L2 -> SM traffic, not the tensor pipe: FFN-1 at layer 0 (22726 x 256 -> 2048) moves 16 x 23 MB of A, 364 MB of W and
+// 186 MB of C = 922 MB and takes 98 us, i.e. the ~9 TB/s the L2 sustains (148 SMs x ~42 B/clk, B300_MICROARCH.md "LTS
+// throughput cap"); the MMAs alone would need 30 us.  With K <= 256 the whole split activation panel of a 128-row block fits
+// in tensor memory (4 k-blocks x 64 columns = 256 columns, beside the double-buffered 2 x 128-column accumulator), so here a
+// CTA converts a panel ONCE and walks a group of up to G output tiles of that panel; per tile only the weight streams in
+// (32 KB per k-block instead of 64 KB) and the converter warps are idle instead of re-splitting the same rows.
+//   work unit  = (128-row panel, group of G consecutive 128-column tiles), units strided over the persistent CTAs;
+//   shared memory: A ring 2 x 32 KB (two fp32 boxes per k-block), W ring 4 x 32 KB (W_hi + W_lo tile), 2 store boxes;
+//   warp 0: W producer, warp 3: A producer (its own thread, so the next panel is prefetched while W streams),
+//   warp 1: MMA issuer, warps 4..11: converters (panel k-block j is rewritten as soon as the LAST tile's MMAs on k-block j
+//   have completed: per-k-block `panel_free` commits), warps 12..15: epilogue (as above).
+constexpr int kASlots = 2, kWSlots = 4;
+constexpr int kSlotBytes = 2 * kHBox;                                   // 32 KB
+constexpr int kAsRingBytes = (kASlots + kWSlots) * kSlotBytes;          // 192 KB
+constexpr int kAsSmem = kAsRingBytes + kHOutBoxes + 1024 + 256;
+constexpr int kMaxKb = 4;
+
+__global__ void __launch_bounds__(kHThreads, 1)
+gemm_f16x3_as_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_whi,
+                     const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_c,
+                     const HGemmParams p, const int group /* tiles per unit */) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *a_ring = smem, *w_ring = smem + kASlots * kSlotBytes;
+    uint8_t *boxes = smem + kAsRingBytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kAsRingBytes + kHOutBoxes);
+    uint64_t *a_full = bars, *a_empty = a_full + kASlots, *w_full = a_empty + kASlots, *w_empty = w_full + kWSlots;
+    uint64_t *panel_full = w_empty + kWSlots, *panel_free = panel_full + kMaxKb;
+    uint64_t *acc_full = panel_free + kMaxKb, *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nk = p.K / kHK;  // 1..4
+    const int n_tiles = (p.N + kHN - 1) / kHN, m_tiles = (p.M + kHM - 1) / kHM;
+    const int n_groups = (n_tiles + group - 1) / group;
+    const int units = m_tiles * n_groups;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kASlots; ++s) mbar_init(a_full + s, 1), mbar_init(a_empty + s, 32 * kHConvWarps);
+        for (int s = 0; s < kWSlots; ++s) mbar_init(w_full + s, 1), mbar_init(w_empty + s, 1);
+        for (int j = 0; j < kMaxKb; ++j) mbar_init(panel_full + j, 32 * kHConvWarps), mbar_init(panel_free + j, 1);
+        for (int b = 0; b < 2; ++b) mbar_init(acc_full + b, 1), mbar_init(acc_empty + b, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== W producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int t0 = (u % n_groups) * group, t1 = min(n_tiles, t0 + group);
+                for (int t = t0; t < t1; ++t)
+                    for (int kb = 0; kb < nk; ++kb, ++it) {
+                        const int s = it % kWSlots;
+                        mbar_wait(w_empty + s, ((it / kWSlots) & 1) ^ 1);
+                        uint8_t *st = w_ring + s * kSlotBytes;
+                        mbar_expect_tx(w_full + s, kSlotBytes);
+                        tma_load_2d(&map_whi, w_full + s, st, kb * kHK, t * kHN);
+                        tma_load_2d(&map_wlo, w_full + s, st + kHBox, kb * kHK, t * kHN);
+                    }
+            }
+        }
+    } else if (warp == 3) {
+        // ===== A producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int m0 = (u / n_groups) * kHM;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int s = it % kASlots;
+                    mbar_wait(a_empty + s, ((it / kASlots) & 1) ^ 1);
+                    uint8_t *st = a_ring + s * kSlotBytes;
+                    mbar_expect_tx(a_full + s, kSlotBytes);
+                    tma_load_2d(&map_a, a_full + s, st, kb * kHK, m0);
+                    tma_load_2d(&map_a, a_full + s, st + kHBox, kb * kHK + 32, m0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t wit = 0, tc = 0, uc = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x, ++uc) {
+                const int t0 = (u % n_groups) * group, t1 = min(n_tiles, t0 + group);
+                for (int t = t0; t < t1; ++t, ++tc) {
+                    const uint32_t buf = tc & 1;
+                    mbar_wait(acc_empty + buf, ((tc >> 1) & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t acc = tmem_base + buf * 128u;
+                    for (int kb = 0; kb < nk; ++kb, ++wit) {
+                        if (t == t0) mbar_wait(panel_full + kb, uc & 1);  // this unit's panel k-block has been converted
+                        const int s = wit % kWSlots;
+                        mbar_wait(w_full + s, (wit / kWSlots) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t base = smem_u32(w_ring + s * kSlotBytes);
+                        const uint32_t a_hi = tmem_base + 256u + 64u * (uint32_t)kb, a_lo = a_hi + 32u;
+                        const uint64_t d_hi = umma_desc(base), d_lo = umma_desc(base + kHBox);
+#pragma unroll
+                        for (int k = 0; k < kHK / 16; ++k) {
+                            umma_f16_ts(acc, a_hi + 8u * k, d_hi + 2 * k, kIdescF16, (kb | k) != 0);
+                            umma_f16_ts(acc, a_hi + 8u * k, d_lo + 2 * k, kIdescF16, 1);
+                            umma_f16_ts(acc, a_lo + 8u * k, d_hi + 2 * k, kIdescF16, 1);
+                        }
+                        umma_commit(w_empty + s);
+                        if (t == t1 - 1) umma_commit(panel_free + kb);  // last reader of panel k-block kb in this unit
+                    }
+                    umma_commit(acc_full + buf);
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ===== converters: one panel per unit =====
+        const int q = warp & 3, half = (warp - 4) >> 2, r_in = q * 32 + lane;
+        uint32_t it = 0, uc = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x, ++uc) {
+            for (int kb = 0; kb < nk; ++kb, ++it) {
+                const int s = it % kASlots;
+                mbar_wait(a_full + s, (it / kASlots) & 1);
+                const uint8_t *arow = a_ring + s * kSlotBytes + half * kHBox + r_in * 128;
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 x = *reinterpret_cast<const float4 *>(arow + ((c ^ (r_in & 7)) << 4));
+                    if (p.act == 1) {
+                        x.x = fmaxf(x.x, 0.f), x.y = fmaxf(x.y, 0.f), x.z = fmaxf(x.z, 0.f), x.w = fmaxf(x.w, 0.f);
+                    } else if (p.act == 2) {
+                        x.x = gelu_erf(x.x), x.y = gelu_erf(x.y), x.z = gelu_erf(x.z), x.w = gelu_erf(x.w);
+                    }
+                    split2(x.x * kActScale, x.y * kActScale, hi[2 * c], lo[2 * c]);
+                    split2(x.z * kActScale, x.w * kActScale, hi[2 * c + 1], lo[2 * c + 1]);
+                }
+                mbar_arrive(a_empty + s);                      // the fp32 boxes are in registers: the slot may be refilled
+                mbar_wait(panel_free + kb, (uc & 1) ^ 1);      // the previous unit's MMAs no longer read this k-block
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t slot = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + 64u * (uint32_t)kb + 16u * (uint32_t)half;
+                tmem_st16u(slot, hi);
+                tmem_st16u(slot + 32u, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(panel_full + kb);
+            }
+        }
+    } else if (warp >= 12) {
+        // ===== epilogue (same as the streaming kernel, tiles in the MMA warp's order) =====
+        const int q = warp & 3, r_in = q * 32 + lane;
+        const bool elected = threadIdx.x == 12 * 32;
+        const float sc = p.out_scale;
+        uint32_t tc = 0, box_it = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int m0 = (u / n_groups) * kHM;
+            const int t0 = (u % n_groups) * group, t1 = min(n_tiles, t0 + group);
+            for (int t = t0; t < t1; ++t, ++tc) {
+                const int n0 = t * kHN;
+                const uint32_t buf = tc & 1;
+                mbar_wait(acc_full + buf, (tc >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int row = m0 + r_in;
+#pragma unroll 1
+                for (int c = 0; c < kHN / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128u + (uint32_t)(c * 32), r);
+                    if (c == kHN / 32 - 1) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        mbar_arrive(acc_empty + buf);
+                    }
+                    const int col0 = n0 + c * 32;
+                    if (col0 >= p.N) continue;
+                    if (p.use_tma_store) {
+                        uint8_t *box = boxes + (box_it++ & 1) * kHBox;
+                        if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        named_bar_sync(1, 128);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 o = make_float4(__uint_as_float(r[j]) * sc, __uint_as_float(r[j + 1]) * sc,
+                                                   __uint_as_float(r[j + 2]) * sc, __uint_as_float(r[j + 3]) * sc);
+                            if (p.bias && col0 + j + 3 < p.N) {
+                                const float4 bv = ldg_f4(p.bias + col0 + j);
+                                o.x += bv.x, o.y += bv.y, o.z += bv.z, o.w += bv.w;
+                            } else if (p.bias) {
+                                if (col0 + j < p.N) o.x += __ldg(p.bias + col0 + j);
+                                if (col0 + j + 1 < p.N) o.y += __ldg(p.bias + col0 + j + 1);
+                                if (col0 + j + 2 < p.N) o.z += __ldg(p.bias + col0 + j + 2);
+                            }
+                            *reinterpret_cast<float4 *>(box + r_in * 128 + (((j >> 2) ^ (r_in & 7)) << 4)) = o;
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        named_bar_sync(1, 128);
+                        if (elected) {
+                            tma_store_2d(&map_c, box, col0, m0);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    } else if (row < p.M) {
+                        float *crow = p.C + (int64_t)row * p.ldc;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.N) crow[col0 + j] = __uint_as_float(r[j]) * sc + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
+                    }
+                }
+            }
+        }
+        if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
+
 // weight split: (N,K) fp32 -> W_hi = fp16(scale * W), W_lo = fp16(scale * W - W_hi)   (scale: a power of two)
 __global__ void split_f16_pair_kernel(const float *__restrict__ w, int64_t n, float scale, __half *__restrict__ hi,
                                       __half *__restrict__ lo) {
@@ -273,6 +492,28 @@ __global__ void split_f16_pair_kernel(const float *__restrict__ w, int64_t n, fl
 }  // namespace sdetr
 
 using namespace sdetr;
+
+static std::atomic<int> g_f16_as{0};  // 1: K <= 256 goes to the activation-stationary kernel (measured: +4 % on FFN-1, -3 % on the 6-layer value projection -- profiles/r2_gemm_shapes_f16x3_as.txt -- so off by default)
+
+extern "C" int sdetr_gemm_f16x3_set_as(int enable) {
+    g_f16_as = enable ? 1 : 0;
+    return SDETR_OK;
+}
+
+// tiles per work unit: the largest group whose units fill whole waves of `sms` CTAs well (>= 85 %), else the best filling
+static int pick_group(int m_tiles, int n_tiles, int sms) {
+    int best = 1;
+    double best_eff = 0.0;
+    for (int g = n_tiles; g >= 1; g = (g > 1 ? (g + 1) / 2 : 0)) {
+        const long long units = (long long)m_tiles * ((n_tiles + g - 1) / g);
+        const long long waves = (units + sms - 1) / sms;
+        const double eff = (double)units / (double)(waves * sms);
+        if (eff >= 0.85) return g;
+        if (eff > best_eff) best_eff = eff, best = g;
+        if (g == 1) break;
+    }
+    return best;
+}
 
 extern "C" int sdetr_split_f16_pair(const float *w, int64_t count, float scale, void *w_hi, void *w_lo, sdetr_stream_t stream) {
     SDETR_REQUIRE(w && w_hi && w_lo, SDETR_ERR_INVALID_ARG, "split_f16_pair: null pointer");
@@ -301,11 +542,19 @@ extern "C" int sdetr_gemm_f16x3_pre(const float *A, int64_t lda, const void *W_h
     const int use_tma_store = (ldc % 4 == 0) && aligned16(C) &&
                               make_map_2d(&mc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C, M, N, ldc, 32, kHM);
     if (!use_tma_store) mc = ma;
-    static PerDeviceOnce once;
+    static PerDeviceOnce once, once_as;
     SDETR_OPT_IN_SMEM(once, gemm_f16x3_kernel, kHSmem, "gemm_f16x3_pre");
+    SDETR_OPT_IN_SMEM(once_as, gemm_f16x3_as_kernel, kAsSmem, "gemm_f16x3_pre");
     const int sms = sm_count();
     HGemmParams p{bias, C, ldc, M, N, K, act, use_tma_store, 1.f / (kActScale * w_scale)};
-    const int tiles = ((N + kHN - 1) / kHN) * ((M + kHM - 1) / kHM);
+    const int n_tiles = (N + kHN - 1) / kHN, m_tiles = (M + kHM - 1) / kHM;
+    const int group = (g_f16_as.load() && K <= kMaxKb * kHK) ? pick_group(m_tiles, n_tiles, sms) : 1;
+    if (group >= 2) {  // a one-tile unit re-uses nothing: the streaming kernel pipelines it better
+        const long long units = (long long)m_tiles * ((n_tiles + group - 1) / group);
+        gemm_f16x3_as_kernel<<<(int)(units < sms ? units : sms), kHThreads, kAsSmem, (cudaStream_t)stream>>>(ma, mh, ml, mc, p, group);
+        return check_launch("gemm_f16x3_pre/as");
+    }
+    const int tiles = n_tiles * m_tiles;
     gemm_f16x3_kernel<<<tiles < sms ? tiles : sms, kHThreads, kHSmem, (cudaStream_t)stream>>>(ma, mh, ml, mc, p);
     return check_launch("gemm_f16x3_pre");
 }

@@ -32,7 +32,24 @@ struct MsdaFwdParams {
     float *out;
     const int32_t *order;
     int batch, nv, heads, nq, chunk;
+    int ref_dim;  // fused variant: 2 = reference points, 4 = reference boxes (cx, cy, w, h) (ms_deform_attn.py:345-349)
 };
+
+// fused variant: raw offset -> sampling location.  2-d: ref + off / (W_l, H_l) (ms_deform_attn.py:339-344);
+// 4-d: ref_xy + off / P * ref_wh * 0.5 (:345-349), same operation order as the reference
+template <int P>
+__device__ __forceinline__ void fused_location(const float *__restrict__ rrow, int l, int ref_dim, float ox, float oy, float Wf,
+                                               float Hf, float &x, float &y) {
+    if (ref_dim == 2) {
+        const float2 r = __ldg(reinterpret_cast<const float2 *>(rrow) + l);
+        x = r.x + __fdividef(ox, Wf);
+        y = r.y + __fdividef(oy, Hf);
+    } else {
+        const float4 r = __ldg(reinterpret_cast<const float4 *>(rrow) + l);
+        x = r.x + __fmul_rn(__fmul_rn(__fdiv_rn(ox, (float)P), r.z), 0.5f);
+        y = r.y + __fmul_rn(__fmul_rn(__fdiv_rn(oy, (float)P), r.w), 0.5f);
+    }
+}
 
 constexpr int kThreads = 256;
 
@@ -195,19 +212,17 @@ struct SlotLoop {
     // FUSED: (lx, ly) raw offsets -> locations (needs ref), la normalised; then the setup of every slot
     static __device__ __forceinline__ void run(PointSetup (&st)[SLOTS], float (&lx)[SLOTS], float (&ly)[SLOTS],
                                                float (&la)[SLOTS], const LevelGeom (&geo)[L], int lane,
-                                               const float *__restrict__ rrow, float inv_sum) {
+                                               const float *__restrict__ rrow, float inv_sum, int ref_dim) {
         int l, H, W;
         float Hf, Wf;
         slot_geom<L, P, LANES, SLOT>(geo, lane, l, H, W, Hf, Wf);
         if constexpr (FUSED) {
-            const float2 r = __ldg(reinterpret_cast<const float2 *>(rrow) + l);
-            lx[SLOT] = r.x + __fdividef(lx[SLOT], Wf);  // loc = ref + off / (W_l, H_l) (ms_deform_attn.py:339-344)
-            ly[SLOT] = r.y + __fdividef(ly[SLOT], Hf);
+            fused_location<P>(rrow, l, ref_dim, lx[SLOT], ly[SLOT], Wf, Hf, lx[SLOT], ly[SLOT]);
             la[SLOT] = la[SLOT] * inv_sum;
         }
         st[SLOT] = make_setup(lx[SLOT], ly[SLOT], la[SLOT], H, W, Hf, Wf);
         if constexpr (SLOT + 1 < SLOTS)
-            SlotLoop<L, P, LANES, SLOTS, FUSED, SLOT + 1>::run(st, lx, ly, la, geo, lane, rrow, inv_sum);
+            SlotLoop<L, P, LANES, SLOTS, FUSED, SLOT + 1>::run(st, lx, ly, la, geo, lane, rrow, inv_sum, ref_dim);
     }
 };
 
@@ -283,7 +298,7 @@ __global__ void __launch_bounds__(THREADS, MINB) msda_fwd_kernel(const MsdaFwdPa
             for (int s = 0; s < SLOTS; ++s) la[s] = __expf(la[s] - mx), sum += la[s];
             sum = group_sum<LANES>(sum);
             inv_sum = __frcp_rn(sum);
-            rrow = p.ref + row * (2 * L);
+            rrow = p.ref + row * (p.ref_dim * L);
         } else {
 #pragma unroll
             for (int s = 0; s < SLOTS; ++s) {
@@ -295,7 +310,7 @@ __global__ void __launch_bounds__(THREADS, MINB) msda_fwd_kernel(const MsdaFwdPa
             }
         }
         PointSetup st[SLOTS];
-        SlotLoop<L, P, LANES, SLOTS, FUSED>::run(st, lx, ly, la, geo, lane, rrow, inv_sum);
+        SlotLoop<L, P, LANES, SLOTS, FUSED>::run(st, lx, ly, la, geo, lane, rrow, inv_sum, p.ref_dim);
         if constexpr (FUSED) {
             if (active) {
 #pragma unroll
@@ -333,6 +348,118 @@ __global__ void __launch_bounds__(THREADS, MINB) msda_fwd_kernel(const MsdaFwdPa
     }
 }
 
+// ---- "W32": one WARP per (image, query, head), one lane per channel (D = 32, L = 4, P = 4, head-major schedule) ------------
+// Measured on the kernel above (profiles/r2_msda_probe_v1.txt): even when every gather hits in L1 it needs ~125 clk per
+// (query, head) per SM, twice the 64 clk that 64 corner rows x 128 B cost at 128 B/clk.  Its LDG.128 instructions touch four
+// different 128-byte lines each (one per 8-lane group), and a multi-line request is replayed at ~2 clk per line
+// (B300_MICROARCH.md: 1.0 clk per wavefront across instructions, 2.07 within one).  Here every corner row is ONE fully
+// coalesced 128-byte LDG.32 -- a single line, a single wavefront -- issued by the whole warp:
+//   * lane e (and its mirror e + 16) owns sampling point e of the (query, head): softmax over 16 lanes by shuffles,
+//     location, corner index and the four weights are computed once per point and published in 320 bytes of shared memory
+//     per warp; every lane then reads a level's four indices with one uniform LDS.128 and each point's weights with one
+//     uniform LDS.128 (1 wavefront each: 20 per item instead of 80 shuffles);
+//   * 16 (one level) or 32 (two levels) independent corner loads in flight per lane, one FMA each; ~40 registers, so up
+//     to 48 warps per SM;
+//   * the 8 warps of a CTA walk consecutive queries of the tile order (same head), so co-resident gathers share lines.
+constexpr int kW32Warps = 8;
+
+template <bool FUSED, int LVB /* levels gathered per batch: 1 or 2 */, int MINB>
+__global__ void __launch_bounds__(kW32Warps * 32, MINB) msda_fwd_w32_kernel(const MsdaFwdParams p) {
+    constexpr int L = 4, P = 4, NP = 16, D = 32;
+    __shared__ __align__(16) float4 s_w[kW32Warps][NP];
+    __shared__ __align__(16) uint32_t s_pk[kW32Warps][NP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, e = lane & 15, lvl_e = e >> 2;
+    LevelGeom geo[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        geo[l].H = (int)__ldg(p.shapes + 2 * l);
+        geo[l].W = (int)__ldg(p.shapes + 2 * l + 1);
+        geo[l].Hf = (float)geo[l].H, geo[l].Wf = (float)geo[l].W;
+        geo[l].start = __ldg(p.lsi + l);
+    }
+    // geometry of the level this lane's point belongs to
+    int He = geo[0].H, We = geo[0].W;
+    float Hfe = geo[0].Hf, Wfe = geo[0].Wf;
+#pragma unroll
+    for (int l = 1; l < L; ++l)
+        if (lvl_e == l) He = geo[l].H, We = geo[l].W, Hfe = geo[l].Hf, Wfe = geo[l].Wf;
+    const int b = blockIdx.z, m = blockIdx.y;
+    const int q_end = min(p.nq, (int)(blockIdx.x + 1) * p.chunk);
+    const uint32_t tsb = (uint32_t)p.v_tstride * 4u;
+    const char *vhead = reinterpret_cast<const char *>(p.value + (int64_t)b * p.v_bstride + (int64_t)m * D + lane);
+    const char *lvl_base[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) lvl_base[l] = vhead + geo[l].start * (int64_t)tsb;
+
+    for (int qi = blockIdx.x * p.chunk + warp; qi < q_end; qi += kW32Warps) {  // warp-uniform trip count
+        const int q = p.order ? __ldg(p.order + (int64_t)b * p.nq + qi) : qi;
+        const int64_t row = (int64_t)b * p.nq + q;
+        const int64_t qm = row * p.heads + m;
+        float x, y, a;
+        if constexpr (FUSED) {
+            const float *prow = p.proj + row * p.proj_stride;
+            const float2 o = __ldg(reinterpret_cast<const float2 *>(prow + (int64_t)m * 2 * NP) + e);
+            const float lg = __ldg(prow + (int64_t)p.heads * 2 * NP + (int64_t)m * NP + e);
+            const float mx = group_max<16>(lg);  // softmax over the 16 logits (ms_deform_attn.py:326-329)
+            const float ex = __expf(lg - mx);
+            const float inv = __frcp_rn(group_sum<16>(ex));
+            fused_location<P>(p.ref + row * (p.ref_dim * L), lvl_e, p.ref_dim, o.x, o.y, Wfe, Hfe, x, y);
+            a = ex * inv;
+            if (lane < NP) {
+                if (p.loc_out) reinterpret_cast<float2 *>(p.loc_out + qm * (2 * NP))[e] = make_float2(x, y);
+                if (p.attn_out) p.attn_out[qm * NP + e] = a;
+            }
+        } else {
+            const float2 o = __ldg(reinterpret_cast<const float2 *>(p.loc + qm * (2 * NP)) + e);
+            x = o.x, y = o.y;
+            a = __ldg(p.attn + qm * NP + e);
+        }
+        const PointSetup st = make_setup(x, y, a, He, We, Hfe, Wfe);
+        if (lane < NP) {
+            s_w[warp][e] = make_float4(st.w00, st.w01, st.w10, st.w11);
+            s_pk[warp][e] = st.packed;
+        }
+        __syncwarp();
+        float acc = 0.f;
+#pragma unroll
+        for (int l0 = 0; l0 < L; l0 += LVB) {
+            float v[LVB][P][4];
+            float4 w[LVB][P];
+#pragma unroll
+            for (int dl = 0; dl < LVB; ++dl) {
+                const int l = l0 + dl;
+                const uint4 pk4 = *reinterpret_cast<const uint4 *>(&s_pk[warp][l * P]);
+                const uint32_t pks[4] = {pk4.x, pk4.y, pk4.z, pk4.w};
+                const uint32_t W = (uint32_t)geo[l].W;
+#pragma unroll
+                for (int pt = 0; pt < P; ++pt) {
+                    w[dl][pt] = s_w[warp][l * P + pt];
+                    const uint32_t pk = pks[pt];
+                    const uint32_t i00 = pk & 0x3fffffffu;
+                    const uint32_t i01 = i00 + ((pk >> 30) & 1u);
+                    const uint32_t i10 = i00 + (pk >> 31) * W;
+                    const uint32_t i11 = i10 + ((pk >> 30) & 1u);
+                    v[dl][pt][0] = __ldg(row_ptr(lvl_base[l], i00, tsb));
+                    v[dl][pt][1] = __ldg(row_ptr(lvl_base[l], i01, tsb));
+                    v[dl][pt][2] = __ldg(row_ptr(lvl_base[l], i10, tsb));
+                    v[dl][pt][3] = __ldg(row_ptr(lvl_base[l], i11, tsb));
+                }
+            }
+#pragma unroll
+            for (int dl = 0; dl < LVB; ++dl)
+#pragma unroll
+                for (int pt = 0; pt < P; ++pt) {
+                    acc = fmaf(w[dl][pt].x, v[dl][pt][0], acc);
+                    acc = fmaf(w[dl][pt].y, v[dl][pt][1], acc);
+                    acc = fmaf(w[dl][pt].z, v[dl][pt][2], acc);
+                    acc = fmaf(w[dl][pt].w, v[dl][pt][3], acc);
+                }
+        }
+        __syncwarp();  // all lanes have read this item's setups before the next item overwrites them
+        asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p.out + qm * D + lane), "f"(acc) : "memory");
+    }
+}
+
 // ---- generic fallback (any head_dim % 4 == 0, L <= kMaxLevels, any P) ------------------------------------
 __global__ void __launch_bounds__(kThreads) msda_fwd_generic_kernel(const MsdaFwdParams p, int D, int L, int P,
                                                                    int fused) {
@@ -367,8 +494,14 @@ __global__ void __launch_bounds__(kThreads) msda_fwd_generic_kernel(const MsdaFw
             float x, y, a;
             if (fused) {
                 const float *off = prow + (int64_t)m * 2 * NP + 2 * e;
-                x = __ldg(p.ref + row * (2 * L) + 2 * l) + __ldg(off) / g.Wf;
-                y = __ldg(p.ref + row * (2 * L) + 2 * l + 1) + __ldg(off + 1) / g.Hf;
+                const float *rr = p.ref + row * (p.ref_dim * L) + p.ref_dim * l;
+                if (p.ref_dim == 2) {
+                    x = __ldg(rr) + __ldg(off) / g.Wf;
+                    y = __ldg(rr + 1) + __ldg(off + 1) / g.Hf;
+                } else {
+                    x = __ldg(rr) + __fmul_rn(__fmul_rn(__fdiv_rn(__ldg(off), (float)P), __ldg(rr + 2)), 0.5f);
+                    y = __ldg(rr + 1) + __fmul_rn(__fmul_rn(__fdiv_rn(__ldg(off + 1), (float)P), __ldg(rr + 3)), 0.5f);
+                }
                 a = expf(__ldg(prow + (int64_t)p.heads * 2 * NP + (int64_t)m * NP + e) - mx) / sum;
                 if (lane == 0) {
                     if (p.loc_out) {
@@ -399,7 +532,8 @@ __global__ void __launch_bounds__(kThreads) msda_fwd_generic_kernel(const MsdaFw
 static std::atomic<int> g_bcast{1};  // 0 = shuffle broadcast, 1 = shared-memory broadcast (D=32, L=4, P=4 only)
 static std::atomic<int> g_minb{4};   // tuning knobs (sdetr_set_option)
 static std::atomic<int> g_chunk{64};
-static std::atomic<int> g_threads{256};  // head-major schedule: threads per CTA (256 x 4 CTAs/SM, 512 x 2, 1024 x 1)
+static std::atomic<int> g_threads{256};
+static std::atomic<int> g_w32{0};      // head-major schedule, D=32/L=4/P=4: 0 = 8-lane groups (above), 1 / 2 = warp per item, 1 / 2 levels per batch  // head-major schedule: threads per CTA (256 x 4 CTAs/SM, 512 x 2, 1024 x 1)
 
 template <int D, int L, int P, int MINB>
 static void launch_special(const MsdaFwdParams &p, bool fused, int schedule, cudaStream_t s) {
@@ -440,7 +574,17 @@ static int msda_forward_dispatch(MsdaFwdParams p, bool fused, int head_dim, int 
     bool special = true;
     if (fused) special = (p.proj_stride % 4 == 0) && aligned16(p.proj);
     else special = aligned16(p.loc) && aligned16(p.attn);
-    if (special && head_dim == 32 && levels == 4 && points == 4 && g_bcast == 1) {
+    if (special && head_dim == 32 && levels == 4 && points == 4 && schedule == 1 && g_w32.load() != 0) {
+        dim3 grid((p.nq + p.chunk - 1) / p.chunk, p.heads, p.batch);
+        const int k = g_w32.load();
+        if (k == 2) {
+            if (fused) msda_fwd_w32_kernel<true, 2, 4><<<grid, kW32Warps * 32, 0, s>>>(p);
+            else msda_fwd_w32_kernel<false, 2, 4><<<grid, kW32Warps * 32, 0, s>>>(p);
+        } else {
+            if (fused) msda_fwd_w32_kernel<true, 1, 6><<<grid, kW32Warps * 32, 0, s>>>(p);
+            else msda_fwd_w32_kernel<false, 1, 6><<<grid, kW32Warps * 32, 0, s>>>(p);
+        }
+    } else if (special && head_dim == 32 && levels == 4 && points == 4 && g_bcast == 1) {
         const int threads = schedule == 1 ? g_threads.load() : kThreads;
         const int groups = threads / 8;
         const size_t smem = (size_t)groups * (kWStride + kPkStride);
@@ -495,6 +639,9 @@ extern "C" int sdetr_set_option(const char *name, int value) {
     } else if (eq("msda_smem_broadcast")) {
         SDETR_REQUIRE(value == 0 || value == 1, SDETR_ERR_INVALID_ARG, "set_option: msda_smem_broadcast in {0,1}");
         g_bcast = value;
+    } else if (eq("msda_warp_per_item")) {
+        SDETR_REQUIRE(value >= 0 && value <= 2, SDETR_ERR_INVALID_ARG, "set_option: msda_warp_per_item in {0,1,2}");
+        g_w32 = value;
     } else if (eq("msda_threads")) {
         SDETR_REQUIRE(value == 256 || value == 512 || value == 1024, SDETR_ERR_INVALID_ARG, "set_option: msda_threads in {256,512,1024}");
         g_threads = value;
@@ -532,13 +679,15 @@ extern "C" int sdetr_msda_forward(const float *value, const int64_t *spatial_sha
                                  stream);
 }
 
-extern "C" int sdetr_msda_fused_forward(const float *value, int64_t value_batch_stride, int64_t value_token_stride,
-                                        const int64_t *spatial_shapes, const int64_t *level_start_index,
-                                        const float *ref_points, const float *proj, int64_t proj_stride,
-                                        float *output, float *loc_out, float *attn_out, int batch, int num_value,
-                                        int num_heads, int head_dim, int num_levels, int num_query, int num_points,
-                                        const int32_t *query_order, int schedule, sdetr_stream_t stream) {
+static int msda_fused_impl(const float *value, int64_t value_batch_stride, int64_t value_token_stride,
+                           const int64_t *spatial_shapes, const int64_t *level_start_index, const float *ref_points, int ref_dim,
+                           const float *proj, int64_t proj_stride, float *output, float *loc_out, float *attn_out, int batch,
+                           int num_value, int num_heads, int head_dim, int num_levels, int num_query, int num_points,
+                           const int32_t *query_order, int schedule, sdetr_stream_t stream) {
     MsdaFwdParams p{};
+    p.ref_dim = ref_dim;
+    SDETR_REQUIRE(ref_dim == 2 || (ref_dim == 4 && aligned16(ref_points)), SDETR_ERR_INVALID_ARG,
+                  "msda_fused_forward: reference points must be (..,2) or 16-byte aligned (..,4) boxes");
     p.value = value, p.v_bstride = value_batch_stride, p.v_tstride = value_token_stride;
     p.shapes = spatial_shapes, p.lsi = level_start_index;
     p.ref = ref_points, p.proj = proj, p.proj_stride = proj_stride, p.loc_out = loc_out, p.attn_out = attn_out;
@@ -547,4 +696,26 @@ extern "C" int sdetr_msda_fused_forward(const float *value, int64_t value_batch_
     SDETR_REQUIRE(proj_stride >= (int64_t)num_heads * num_levels * num_points * 3, SDETR_ERR_INVALID_ARG,
                   "msda_fused_forward: proj_stride too small");
     return msda_forward_dispatch(p, true, head_dim, num_levels, num_points, schedule, (cudaStream_t)stream);
+}
+
+extern "C" int sdetr_msda_fused_forward(const float *value, int64_t value_batch_stride, int64_t value_token_stride,
+                                        const int64_t *spatial_shapes, const int64_t *level_start_index,
+                                        const float *ref_points, const float *proj, int64_t proj_stride,
+                                        float *output, float *loc_out, float *attn_out, int batch, int num_value,
+                                        int num_heads, int head_dim, int num_levels, int num_query, int num_points,
+                                        const int32_t *query_order, int schedule, sdetr_stream_t stream) {
+    return msda_fused_impl(value, value_batch_stride, value_token_stride, spatial_shapes, level_start_index, ref_points, 2, proj,
+                           proj_stride, output, loc_out, attn_out, batch, num_value, num_heads, head_dim, num_levels, num_query,
+                           num_points, query_order, schedule, stream);
+}
+
+extern "C" int sdetr_msda_fused_forward_boxes(const float *value, int64_t value_batch_stride, int64_t value_token_stride,
+                                              const int64_t *spatial_shapes, const int64_t *level_start_index,
+                                              const float *ref_boxes, const float *proj, int64_t proj_stride,
+                                              float *output, float *loc_out, float *attn_out, int batch, int num_value,
+                                              int num_heads, int head_dim, int num_levels, int num_query, int num_points,
+                                              const int32_t *query_order, int schedule, sdetr_stream_t stream) {
+    return msda_fused_impl(value, value_batch_stride, value_token_stride, spatial_shapes, level_start_index, ref_boxes, 4, proj,
+                           proj_stride, output, loc_out, attn_out, batch, num_value, num_heads, head_dim, num_levels, num_query,
+                           num_points, query_order, schedule, stream);
 }

@@ -33,7 +33,8 @@ from . import cabi, gemm
 from .ms_deform_attn import MultiScaleDeformableAttention
 
 OVERLAP_VALUE_PROJ = True  # inside a graph capture: all-layer value projection as a parallel branch beside the salience filter
-VALUE_PROJ_PER_LAYER = True  # each layer's value_proj as its own GEMM on a side stream beside that layer's (latency-bound)
+VALUE_PROJ_PER_LAYER = False  # (measured, profiles/r2_msda_probe_v1.txt: L2-warm value buys the sampling kernel 2 %; one N=1536 GEMM is 1.5x cheaper than six N=256 ones)
+# each layer's value_proj as its own GEMM on a side stream beside that layer's (latency-bound)
 # pre-attention, joined right before the sampling kernel: the 45.7 MB it writes are still in the 126 MB L2 when the
 # sampling kernel gathers from them (one 6-layer GEMM up front writes 274 MB, which L2 cannot hold), and the value rows
 # are 1 KB apart instead of 6 KB

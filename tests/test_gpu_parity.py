@@ -34,6 +34,7 @@ def _restore_global_state(pkg):
     yield
     pkg.gemm.MODE = mode
     pkg.gemm.OWN_KERNEL = os.environ.get("SDETR_GEMM_KERNEL", "f16x3")
+    pkg.cabi.lib().sdetr_gemm_f16x3_set_as(0)
     pkg.cabi.set_option("msda_smem_broadcast", 1)
     pkg.cabi.lib().sdetr_gemm_set_variant(0)
     pkg.cabi.lib().sdetr_gemm_set_variant(3)
@@ -551,6 +552,22 @@ def test_gemm_f16x3_accuracy_and_range(pkg):
         e32 = (pkg.gemm.linear(x if act is None else (F.relu(x) if act == "relu" else F.gelu(x)), w, b).double() - ref).abs().max().item()
         assert err < 3e-4 and err < 32 * e32 + 1e-6, (rows, K, N, err, e32)
         assert torch.equal(pkg.cabi.gemm_f16x3_pre(x, w_hi, w_lo, sc, b, {None: 0, "relu": 1, "gelu": 2}[act]), y)
+    # activation-stationary variant (K <= 256, several output tiles per work unit): the same MMA sequence per tile as the
+    # streaming kernel, so the results are bit-identical
+    for rows, K, N, act in [(22726, 256, 2048, 0), (4544, 256, 2048, 1), (44646, 256, 1536, 0), (20000, 128, 640, 2),
+                            (19000, 64, 384, 0), (18180, 256, 384, 0), (40000, 192, 300, 0)]:
+        x = torch.randn(rows, K, generator=g).to(DEV)
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+        b = torch.randn(N, generator=g).to(DEV)
+        w_hi, w_lo, sc = pkg.cabi.split_f16_pair(w)
+        pkg.cabi.lib().sdetr_gemm_f16x3_set_as(0)
+        y0 = pkg.cabi.gemm_f16x3_pre(x, w_hi, w_lo, sc, b, act)
+        pkg.cabi.lib().sdetr_gemm_f16x3_set_as(1)
+        y1 = pkg.cabi.gemm_f16x3_pre(x, w_hi, w_lo, sc, b, act)
+        xa = x.double() if act == 0 else (F.relu(x.double()) if act == 1 else F.gelu(x.double()))
+        assert (y1.double() - F.linear(xa, w.double(), b.double())).abs().max() < 1e-4, (rows, K, N)
+        assert torch.equal(y0, y1), (rows, K, N)
+        assert torch.equal(pkg.cabi.gemm_f16x3_pre(x, w_hi, w_lo, sc, b, act), y1)
     # range: tiny, huge and mixed-magnitude activations; relative error of the result stays fp32-class
     K, N = 256, 256
     w = (torch.randn(N, K, generator=g) / 16).to(DEV)

@@ -28,13 +28,14 @@ for name, M, K, N, relu in shapes:
     x = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) / K ** 0.5; b = torch.randn(N, device=dev)
     ref = torch.nn.functional.linear((x.relu() if relu else x).double(), w.double(), b.double())
     r, e = {}, {}
-    for mode, own in (("auto", "f16x3"), ("auto", "tf32x3"), ("3xtf32", ""), ("fp32", "")):
-        pkg.gemm.MODE, pkg.gemm.OWN_KERNEL = mode, own or "f16x3"
+    for mode, own in (("auto", "f16x3"), ("auto", "f16x3-noas"), ("auto", "tf32x3"), ("3xtf32", ""), ("fp32", "")):
+        pkg.gemm.MODE, pkg.gemm.OWN_KERNEL = mode, (own or "f16x3").split("-")[0]
+        pkg.cabi.lib().sdetr_gemm_f16x3_set_as(0 if own.endswith("noas") else 1)
         key = own or mode
         fn = lambda: pkg.gemm.linear(x, w, b, relu_input=bool(relu))
         e[key] = (fn().double() - ref).abs().max().item()
         r[key] = timeit(fn)
         tot[key] = tot.get(key, 0) + r[key]
-    print(f"{name:14s} {M:6d} {K:5d} {N:5d} | {r['f16x3']:7.1f} ({e['f16x3']:.1e}) | {r['tf32x3']:7.1f} ({e['tf32x3']:.1e}) | {r['3xtf32']:8.1f} | "
+    print(f"{name:14s} {M:6d} {K:5d} {N:5d} | {r['f16x3']:7.1f} ({e['f16x3']:.1e}) [streaming only {r['f16x3-noas']:7.1f}] | {r['tf32x3']:7.1f} ({e['tf32x3']:.1e}) | {r['3xtf32']:8.1f} | "
           f"{r['fp32']:7.1f} ({e['fp32']:.1e}) | {2*M*N*K/r['f16x3']/1e6:7.1f} | {r['tf32x3']/r['f16x3']:.2f}x")
 print("sum us", {k: round(v, 1) for k, v in tot.items()})

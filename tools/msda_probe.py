@@ -19,9 +19,19 @@ model = build_model().to(dev)
 feats, masks, pos = make_inputs("resnet50_800_1333_bs2", seed=0, device=dev)
 cabi = pkg.cabi
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for kv in sys.argv[1:]:
-    k, v = kv.split("=")
-    cabi.set_option(k, int(v))
+# variants: "name:opt=val,opt=val" ... (first = reference for the error column)
+variants = [a for a in sys.argv[1:]] or ["default:"]
+DEFAULTS = {"msda_warp_per_item": 0, "msda_threads": 256, "msda_chunk": 64, "msda_smem_broadcast": 1, "msda_min_blocks": 4}
+
+
+def apply(spec):
+    for k, v in DEFAULTS.items():
+        cabi.set_option(k, v)
+    name, _, opts = spec.partition(":")
+    for kv in filter(None, opts.split(",")):
+        k, v = kv.split("=")
+        cabi.set_option(k, int(v))
+    return name
 
 calls = []
 orig = cabi.msda_fused_forward
@@ -62,10 +72,18 @@ def run(mode, reps=15):
     return [statistics.median(x) for x in per]
 
 
-print("options", sys.argv[1:], " value layout: token stride", calls[0][0][2], "floats")
-print("mode   | per-layer us | total us | GB/s algorithmic | cycles per (query,head) per SM @1.965 GHz")
+print("value layout: token stride", calls[0][0][2], "floats")
+print("variant            mode   | per-layer us | total us | GB/s algorithmic | clk per (query,head) per SM @1.965 GHz | max err vs first variant")
 items = [b * nq * 8 for nq in plan.layer_num_query]
-for mode in ("cold", "warm", "allhit"):
-    t = run(mode)
-    cyc = sum(t) * 1e-6 * 1.965e9 * 148 / sum(items)
-    print(f"{mode:6s} | " + " ".join(f"{x:6.1f}" for x in t) + f" | {sum(t):7.1f} | {sum(byts) / sum(t) / 1e3:7.1f} | {cyc:6.1f}")
+ref_out = None
+for spec in variants:
+    name = apply(spec)
+    outs = [orig(*a, **k) for a, k in calls]
+    torch.cuda.synchronize()
+    if ref_out is None:
+        ref_out = outs
+    err = max((o - r).abs().max().item() for o, r in zip(outs, ref_out))
+    for mode in ("cold", "warm", "allhit"):
+        t = run(mode)
+        cyc = sum(t) * 1e-6 * 1.965e9 * 148 / sum(items)
+        print(f"{name:18s} {mode:6s} | " + " ".join(f"{x:6.1f}" for x in t) + f" | {sum(t):7.1f} | {sum(byts) / sum(t) / 1e3:7.1f} | {cyc:6.1f} | {err:.1e}")
