@@ -96,6 +96,12 @@ int sdetr_msda_fused_forward_boxes(const float *value, int64_t value_batch_strid
                                    int num_levels, int num_query, int num_points, const int32_t *query_order, int schedule,
                                    sdetr_stream_t stream);
 
+/* Benchmarking variant "msda_tma" (sdetr_set_option("msda_tma", 1); D = 32, L = 4, P = 4, head-major schedule with a query
+ * order): the fused / plain forward stages per-level value windows in shared memory with TMA (csrc/msda_forward_tma.cu).
+ * TMA tensor maps are encoded on the host, which needs the level shapes as HOST integers: give them here once per
+ * geometry (process-global; the default path reads the shapes from the device tensors and needs none of this). */
+int sdetr_msda_set_host_shapes(int num_levels, const int32_t *level_h_host, const int32_t *level_w_host);
+
 /* Two-stage proposal selection, NMS on token indices (SalienceTransformer.nms_on_topk_index, salience_transformer.py:
  * 249-295 = torchvision.ops.batched_nms over boxes (x-1,y-1,x+1,y+1) on each (image, level) grid).  topk_index (b,k) int64:
  * candidate tokens in descending score order (the rank decides who suppresses whom).  kept_index (b,k) int64 receives the

@@ -19,6 +19,13 @@ from .ms_deform_attn import (  # noqa: F401
 )
 from . import gemm  # noqa: F401
 from .position_encoding import PositionEmbeddingSine  # noqa: F401
+from .decoder import (  # noqa: F401
+    MLP,
+    SalienceTransformerDecoder,
+    SalienceTransformerDecoderLayer,
+    get_sine_pos_embed,
+    inverse_sigmoid,
+)
 from .salience_transformer import (  # noqa: F401
     EncoderPlan,
     MaskPredictor,

@@ -32,6 +32,7 @@ SIGNATURES = {
     "sdetr_msda_forward_ex": (_i, [_vp, _i64, _i64] + [_vp] * 5 + [_i] * 7 + [_vp, _i, _vp]),
     "sdetr_msda_fused_forward": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp] + [_i] * 7 + [_vp, _i, _vp]),
     "sdetr_msda_fused_forward_boxes": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp] + [_i] * 7 + [_vp, _i, _vp]),
+    "sdetr_msda_set_host_shapes": (_i, [_i, _vp, _vp]),
     "sdetr_nms_topk_index": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
     "sdetr_msda_backward": (_i, [_vp] * 9 + [_i] * 7 + [_vp]),
     "sdetr_salience_select_workspace": (_sz, [_i, _i, _i]),
@@ -196,6 +197,12 @@ def msda_fused_forward(value_buf, value_batch_stride, value_token_stride, value_
     if t0 is not None:
         KERNEL_TIMERS.setdefault("msda", []).append((t0, _timer_event()))
     return (out, loc, attn) if want_loc_attn else out
+
+
+def msda_set_host_shapes(shapes):
+    """Level shapes as host integers for the TMA-staged variant's tensor maps (option "msda_tma")."""
+    _check(lib().sdetr_msda_set_host_shapes(len(shapes), _host_i32([h for h, _ in shapes]), _host_i32([w for _, w in shapes])),
+           "sdetr_msda_set_host_shapes")
 
 
 def nms_topk_index(topk_index, shapes, iou_threshold=0.3):

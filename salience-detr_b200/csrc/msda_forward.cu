@@ -17,39 +17,9 @@
 //     (all heads of 256/(8*M) consecutive queries per CTA) or head-major (one head of a chunk of
 //     consecutive queries per CTA) so that co-resident groups gather from the same value neighbourhood
 //     and hit in L1 instead of L2.  Output rows stay in the caller's order.
-#include "common.cuh"
+#include "msda.cuh"
 
 namespace sdetr {
-
-struct MsdaFwdParams {
-    const float *value;
-    int64_t v_bstride, v_tstride;  // floats
-    const int64_t *shapes, *lsi;
-    const float *loc, *attn;  // plain variant
-    const float *ref, *proj;  // fused variant
-    int64_t proj_stride;
-    float *loc_out, *attn_out;
-    float *out;
-    const int32_t *order;
-    int batch, nv, heads, nq, chunk;
-    int ref_dim;  // fused variant: 2 = reference points, 4 = reference boxes (cx, cy, w, h) (ms_deform_attn.py:345-349)
-};
-
-// fused variant: raw offset -> sampling location.  2-d: ref + off / (W_l, H_l) (ms_deform_attn.py:339-344);
-// 4-d: ref_xy + off / P * ref_wh * 0.5 (:345-349), same operation order as the reference
-template <int P>
-__device__ __forceinline__ void fused_location(const float *__restrict__ rrow, int l, int ref_dim, float ox, float oy, float Wf,
-                                               float Hf, float &x, float &y) {
-    if (ref_dim == 2) {
-        const float2 r = __ldg(reinterpret_cast<const float2 *>(rrow) + l);
-        x = r.x + __fdividef(ox, Wf);
-        y = r.y + __fdividef(oy, Hf);
-    } else {
-        const float4 r = __ldg(reinterpret_cast<const float4 *>(rrow) + l);
-        x = r.x + __fmul_rn(__fmul_rn(__fdiv_rn(ox, (float)P), r.z), 0.5f);
-        y = r.y + __fmul_rn(__fmul_rn(__fdiv_rn(oy, (float)P), r.w), 0.5f);
-    }
-}
 
 constexpr int kThreads = 256;
 
@@ -58,19 +28,6 @@ constexpr int kThreads = 256;
 // its sampling location into everything the gather needs -- top-left token index, two "has a neighbour" bits
 // and the four corner weights (already multiplied by the attention weight, zero for corners outside the map)
 // -- exactly once; the other lanes receive it with five shuffles instead of redoing ~50 instructions each.
-template <int LANES>
-__device__ __forceinline__ float group_max(float v) {
-#pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o, LANES));
-    return v;
-}
-template <int LANES>
-__device__ __forceinline__ float group_sum(float v) {
-#pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, LANES);
-    return v;
-}
-
 struct LevelGeom {
     int H, W;
     float Hf, Wf;
@@ -533,6 +490,8 @@ static std::atomic<int> g_bcast{1};  // 0 = shuffle broadcast, 1 = shared-memory
 static std::atomic<int> g_minb{4};   // tuning knobs (sdetr_set_option)
 static std::atomic<int> g_chunk{64};
 static std::atomic<int> g_threads{256};
+int g_msda_host_shapes[2 * kMaxLevels + 1] = {0};  // [L, H_0, W_0, H_1, W_1, ...] for the TMA variant's tensor maps
+static std::atomic<int> g_tma{0};      // head-major schedule, D=32/L=4/P=4: 1 = TMA-staged shared-memory windows (msda_forward_tma.cu)
 static std::atomic<int> g_w32{0};      // head-major schedule, D=32/L=4/P=4: 0 = 8-lane groups (above), 1 / 2 = warp per item, 1 / 2 levels per batch  // head-major schedule: threads per CTA (256 x 4 CTAs/SM, 512 x 2, 1024 x 1)
 
 template <int D, int L, int P, int MINB>
@@ -574,7 +533,9 @@ static int msda_forward_dispatch(MsdaFwdParams p, bool fused, int head_dim, int 
     bool special = true;
     if (fused) special = (p.proj_stride % 4 == 0) && aligned16(p.proj);
     else special = aligned16(p.loc) && aligned16(p.attn);
-    if (special && head_dim == 32 && levels == 4 && points == 4 && schedule == 1 && g_w32.load() != 0) {
+    if (special && head_dim == 32 && levels == 4 && points == 4 && schedule == 1 && g_tma.load() != 0 && p.order) {
+        return launch_msda_tma(p, fused, s);
+    } else if (special && head_dim == 32 && levels == 4 && points == 4 && schedule == 1 && g_w32.load() != 0) {
         dim3 grid((p.nq + p.chunk - 1) / p.chunk, p.heads, p.batch);
         const int k = g_w32.load();
         if (k == 2) {
@@ -630,6 +591,14 @@ static int msda_forward_dispatch(MsdaFwdParams p, bool fused, int head_dim, int 
 
 using namespace sdetr;
 
+extern "C" int sdetr_msda_set_host_shapes(int num_levels, const int32_t *level_h_host, const int32_t *level_w_host) {
+    SDETR_REQUIRE(num_levels >= 0 && num_levels <= kMaxLevels && (num_levels == 0 || (level_h_host && level_w_host)),
+                  SDETR_ERR_INVALID_ARG, "msda_set_host_shapes: bad arguments");
+    g_msda_host_shapes[0] = num_levels;
+    for (int l = 0; l < num_levels; ++l) g_msda_host_shapes[1 + 2 * l] = level_h_host[l], g_msda_host_shapes[2 + 2 * l] = level_w_host[l];
+    return SDETR_OK;
+}
+
 extern "C" int sdetr_set_option(const char *name, int value) {
     SDETR_REQUIRE(name, SDETR_ERR_INVALID_ARG, "set_option: null name");
     const auto eq = [&](const char *k) { int i = 0; while (k[i] && k[i] == name[i]) ++i; return k[i] == 0 && name[i] == 0; };
@@ -639,6 +608,9 @@ extern "C" int sdetr_set_option(const char *name, int value) {
     } else if (eq("msda_smem_broadcast")) {
         SDETR_REQUIRE(value == 0 || value == 1, SDETR_ERR_INVALID_ARG, "set_option: msda_smem_broadcast in {0,1}");
         g_bcast = value;
+    } else if (eq("msda_tma")) {
+        SDETR_REQUIRE(value == 0 || value == 1, SDETR_ERR_INVALID_ARG, "set_option: msda_tma in {0,1}");
+        g_tma = value;
     } else if (eq("msda_warp_per_item")) {
         SDETR_REQUIRE(value >= 0 && value <= 2, SDETR_ERR_INVALID_ARG, "set_option: msda_warp_per_item in {0,1,2}");
         g_w32 = value;

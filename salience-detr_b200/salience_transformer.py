@@ -416,6 +416,10 @@ class SalienceTransformer(nn.Module):
         self.encoder_class_head = nn.Linear(self.embed_dim, num_classes)
         self.encoder.enhance_mcsp = self.encoder_class_head
         self.enc_mask_predictor = MaskPredictor(self.embed_dim, self.embed_dim)
+        if decoder is not None:  # decoder half (reference :74-77): only then do these parameters exist in the state_dict
+            from .decoder import MLP
+            self.tgt_embed = nn.Embedding(two_stage_num_proposals, self.embed_dim)
+            self.encoder_bbox_head = MLP(self.embed_dim, self.embed_dim, 4, 3)
         # not a sub-module of the reference transformer (the detector owns it, salience_detr.py:150-176); attach one
         # (``position_encoding.PositionEmbeddingSine``) to let forward_encoder derive the embeddings from the masks
         self.__dict__["position_embedding"] = None
@@ -427,6 +431,10 @@ class SalienceTransformer(nn.Module):
         nn.init.xavier_uniform_(self.enc_output.weight)
         nn.init.constant_(self.enc_output.bias, 0.0)
         nn.init.constant_(self.encoder_class_head.bias, -math.log((1 - 0.01) / 0.01))
+        if self.decoder is not None:
+            nn.init.normal_(self.tgt_embed.weight)
+            nn.init.constant_(self.encoder_bbox_head.layers[-1].weight, 0.0)
+            nn.init.constant_(self.encoder_bbox_head.layers[-1].bias, 0.0)
         self.alpha.data.uniform_(-0.3, 0.3)
 
     def _side_stream(self, device):
@@ -603,15 +611,91 @@ class SalienceTransformer(nn.Module):
         aux = dict(raw_score=raw, selected_inds=inds, selected_score=score, foreground_score=fg, plan=plan)
         return memory, aux
 
+    # -- two-stage proposals (:194-212) ----------------------------------------------------------------------------
+    def gen_encoder_output_proposals(self, memory: Tensor, plan: EncoderPlan):
+        """base_transformer.py:74-112 on the encoder OUTPUT: (output_memory = LN(Linear(memory * keep)), output_proposals =
+        inverse-sigmoid of the (cx, cy, w, h) proposal of every token, +inf where padded / outside (0.01, 0.99))."""
+        b, nv, c = memory.shape
+        dev = memory.device
+        props = []
+        for lvl, (h, w) in enumerate(plan.shapes_list):
+            vr = plan.valid_ratios[:, lvl]                                  # (b,2) = (valid_w / w, valid_h / h)
+            valid_w, valid_h = (vr[:, 0] * w).round(), (vr[:, 1] * h).round()
+            gy, gx = torch.meshgrid(torch.linspace(0, h - 1, h, dtype=torch.float32, device=dev),
+                                    torch.linspace(0, w - 1, w, dtype=torch.float32, device=dev), indexing="ij")
+            grid = torch.stack([gx, gy], -1)
+            scale = torch.stack([valid_w, valid_h], -1).view(b, 1, 1, 2)
+            grid = (grid.expand(b, -1, -1, -1) + 0.5) / scale
+            wh = torch.ones_like(grid) * 0.05 * 2.0 ** lvl
+            props.append(torch.cat([grid, wh], -1).view(b, -1, 4))
+        output_proposals = torch.cat(props, 1)
+        valid = ((output_proposals > 0.01) & (output_proposals < 0.99)).all(-1, keepdim=True)
+        output_proposals = torch.log(output_proposals / (1 - output_proposals))
+        output_proposals.masked_fill_(plan.mask_flat.unsqueeze(-1) | ~valid, float("inf"))
+        grad = torch.is_grad_enabled() and (memory.requires_grad or any(p.requires_grad for p in self.parameters()))
+        x = memory * plan.keep  # plan.keep = ~padding & valid, as float (the same predicate, base_transformer.py:100-108)
+        if grad:
+            output_memory = self.enc_output_norm(self.enc_output(x))
+        else:
+            y = gemm.linear(x, self.enc_output.weight, self.enc_output.bias)
+            output_memory = cabi.add_layernorm(y, None, self.enc_output_norm.weight, self.enc_output_norm.bias,
+                                               self.enc_output_norm.eps, out=y)
+        return output_memory, output_proposals
+
+    @torch.no_grad()
+    def nms_on_topk_index(self, topk_scores, topk_index, spatial_shapes, level_start_index, iou_threshold=0.3,
+                          shapes_list=None):
+        """Reference :249-295 -> (b, min_num) token indices: NMS of the (x-1, y-1, x+1, y+1) boxes per (image, level) in
+        descending score order, first ``two_stage_num_proposals`` survivors, truncated to the batch minimum.  One kernel
+        (``sdetr_nms_topk_index``) + the one host read of the survivor counts the reference also needs."""
+        shapes = shapes_list if shapes_list is not None else [tuple(int(v) for v in r) for r in spatial_shapes.tolist()]
+        kept, count, _ = cabi.nms_topk_index(topk_index.contiguous(), shapes, iou_threshold)
+        min_num = min(int(count.min()), self.two_stage_num_proposals)
+        return kept[:, :min_num]
+
     def forward(self, multi_level_feats, multi_level_masks, multi_level_pos_embeds, noised_label_query=None,
                 noised_box_query=None, attn_mask=None):
-        """Reference call signature (:97-105).  Only the encoder half exists in this round: returns
-        (memory, salience_score maps) when no decoder is attached."""
+        """Reference call signature and outputs (:97-239): (outputs_classes, outputs_coords, enc_outputs_class,
+        enc_outputs_coord, salience_score) when a decoder is attached; (memory, salience maps) for the encoder half alone."""
         memory, aux = self.forward_encoder(multi_level_feats, multi_level_masks, multi_level_pos_embeds)
-        if self.decoder is not None or self.neck is not None:
-            raise NotImplementedError("neck / decoder half are outside this round's hot path (SURVEY.md 8(f))")
-        b = memory.shape[0]
         plan = aux["plan"]
-        salience = [aux["raw_score"][:, s:s + h * w].reshape(b, 1, h, w)
-                    for s, (h, w) in zip(plan.level_start, plan.shapes_list)]
-        return memory, salience
+        b = memory.shape[0]
+        salience = [aux["raw_score"][:, s:s + h * w].reshape(b, 1, h, w) for s, (h, w) in zip(plan.level_start, plan.shapes_list)]
+        if self.decoder is None and self.neck is None:
+            return memory, salience
+        if self.neck is not None:  # :185-192 (the RepVGG neck itself is outside the path: any nn.Module taking {i: NCHW})
+            feats = memory.split(plan.level_size, dim=1)
+            feats = {i: f.transpose(1, 2).contiguous().reshape(b, self.embed_dim, h, w)
+                     for i, (f, (h, w)) in enumerate(zip(feats, plan.shapes_list))}
+            feats = list(self.neck(feats).values())
+            memory = torch.cat([f.flatten(2).transpose(1, 2) for f in feats], dim=1).contiguous()
+            if self.decoder is None:
+                return memory, salience
+        output_memory, output_proposals = self.gen_encoder_output_proposals(memory, plan)
+        grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if grad:
+            enc_outputs_class = self.encoder_class_head(output_memory)
+        else:
+            enc_outputs_class = gemm.linear(output_memory, self.encoder_class_head.weight, self.encoder_class_head.bias)
+        enc_outputs_coord = (self.encoder_bbox_head(output_memory) + output_proposals).sigmoid()
+        topk = min(self.two_stage_num_proposals * 4, enc_outputs_class.shape[1])
+        cls_max = enc_outputs_class.max(-1)[0]
+        if cls_max.is_cuda:   # descending score, ties by smaller index (the canonical order of the selection kernels)
+            topk_index = cabi.topk_desc(cls_max.detach().float().contiguous(), topk)
+            topk_scores = torch.gather(cls_max, 1, topk_index)
+        else:
+            topk_scores, topk_index = torch.topk(cls_max, topk, dim=1)
+        topk_index = self.nms_on_topk_index(topk_scores, topk_index, plan.spatial_shapes, plan.level_start_index, 0.3,
+                                            shapes_list=plan.shapes_list).unsqueeze(-1)
+        enc_outputs_class = enc_outputs_class.gather(1, topk_index.expand(-1, -1, self.num_classes))
+        enc_outputs_coord = enc_outputs_coord.gather(1, topk_index.expand(-1, -1, 4))
+        reference_points = enc_outputs_coord.detach()
+        target = self.tgt_embed.weight.expand(b, -1, -1)
+        if noised_label_query is not None and noised_box_query is not None:
+            target = torch.cat([noised_label_query, target], 1)
+            reference_points = torch.cat([noised_box_query.sigmoid(), reference_points], 1)
+        outputs_classes, outputs_coords = self.decoder(
+            query=target, value=memory, key_padding_mask=plan.mask_flat, reference_points=reference_points,
+            spatial_shapes=plan.spatial_shapes, level_start_index=plan.level_start_index, valid_ratios=plan.valid_ratios,
+            attn_mask=attn_mask)
+        return outputs_classes, outputs_coords, enc_outputs_class, enc_outputs_coord, salience

@@ -122,6 +122,41 @@ def test_msda_smem_broadcast_variant(pkg):
     assert (outs[1][0].cpu() - orc.c_msda_forward(value, st, lsi, loc, attn)).abs().max() < 1e-4
 
 
+def test_msda_kernel_variants_agree(pkg):
+    """The measured-and-rejected variants stay correct: warp-per-item (option msda_warp_per_item) and TMA-staged
+    shared-memory windows (option msda_tma; csrc/msda_forward_tma.cu, incl. its out-of-window global fallback) reproduce
+    the default kernel on a tile-ordered head-major launch, fused and plain, 2-d points and 4-d boxes."""
+    shapes = [(40, 56), (20, 28), (10, 14), (5, 7)]
+    value, st, lsi, loc, attn = [t.to(DEV) for t in _msda_inputs(2, shapes, 8, 32, 777, 4, seed=9)]
+    b, nv = value.shape[:2]
+    g = torch.Generator().manual_seed(10)
+    order = torch.stack([torch.randperm(777, generator=g) for _ in range(b)]).to(torch.int32).to(DEV)
+    proj = torch.randn(b, 777, 384, generator=g).to(DEV)
+    proj[..., :256] *= 6.0  # offsets of several pixels: some samples leave the staged windows
+    ref2 = torch.rand(b, 777, 4, 2, generator=g).to(DEV)
+    ref4 = torch.cat([ref2, torch.rand(b, 777, 4, 2, generator=g).to(DEV) * 0.3], -1).contiguous()
+    pkg.cabi.msda_set_host_shapes(shapes)
+
+    def run():
+        outs = [pkg.cabi.msda_forward(value, st, lsi, loc, attn, query_order=order, schedule=1)]
+        for ref in (ref2, ref4):
+            outs.append(pkg.cabi.msda_fused_forward(value, nv * 256, 256, 0, st, lsi, ref, proj, 8, 32, 4, 4, nv, order, 1))
+        return outs
+
+    try:
+        want = run()
+        assert (want[0].cpu() - orc.c_msda_forward(value.cpu(), st.cpu(), lsi.cpu(), loc.cpu(), attn.cpu())).abs().max() < 1e-4
+        for opt, val in (("msda_warp_per_item", 1), ("msda_warp_per_item", 2), ("msda_tma", 1)):
+            pkg.cabi.set_option(opt, val)
+            got = run()
+            pkg.cabi.set_option(opt, 0)
+            for a, w in zip(got, want):
+                assert (a - w).abs().max() < 1e-5, (opt, val)
+    finally:
+        pkg.cabi.set_option("msda_warp_per_item", 0)
+        pkg.cabi.set_option("msda_tma", 0)
+
+
 def test_msda_autograd_function(pkg):
     value, st, lsi, loc, attn = _msda_inputs(1, [(6, 5), (3, 3)], 2, 32, 9, 2, seed=3)
     v, l, a = (t.to(DEV).requires_grad_(True) for t in (value, loc, attn))

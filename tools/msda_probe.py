@@ -21,7 +21,7 @@ cabi = pkg.cabi
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 # variants: "name:opt=val,opt=val" ... (first = reference for the error column)
 variants = [a for a in sys.argv[1:]] or ["default:"]
-DEFAULTS = {"msda_warp_per_item": 0, "msda_threads": 256, "msda_chunk": 64, "msda_smem_broadcast": 1, "msda_min_blocks": 4}
+DEFAULTS = {"msda_tma": 0, "msda_warp_per_item": 0, "msda_threads": 256, "msda_chunk": 64, "msda_smem_broadcast": 1, "msda_min_blocks": 4}
 
 
 def apply(spec):
@@ -48,6 +48,7 @@ with torch.no_grad():
     model.forward_encoder(feats, masks, pos, plan=plan, use_order=True)
 cabi.msda_fused_forward = orig
 torch.cuda.synchronize()
+cabi.msda_set_host_shapes(plan.shapes_list)  # the TMA variant encodes its tensor maps on the host
 b, nv = plan.mask_flat.shape
 byts = [b * (4 * nv * 256 + nq * (12 * 128 + 4 * 256)) for nq in plan.layer_num_query]
 
