@@ -220,6 +220,45 @@ def use_host_cores():
     return torch.get_num_threads()
 
 
+def numa_node_cpus():
+    """-> list of cpu sets, one per NUMA node that this process may run on."""
+    nodes = []
+    try:
+        allowed = set(os.sched_getaffinity(0))
+        base = "/sys/devices/system/node"
+        for d in sorted(os.listdir(base)):
+            if d.startswith("node") and d[4:].isdigit():
+                cpus = set()
+                for part in open(f"{base}/{d}/cpulist").read().strip().split(","):
+                    if part:
+                        lo, _, hi = part.partition("-")
+                        cpus.update(range(int(lo), int(hi or lo) + 1))
+                if cpus & allowed:
+                    nodes.append(cpus & allowed)
+    except Exception:
+        pass
+    return nodes
+
+
+def best_cpu_setting(step, feats, masks, pos):
+    """The CPU arm runs at the FASTEST of two settings (a fair baseline, not a strawman): every physical core of the host,
+    or the physical cores of one NUMA node (cross-socket traffic costs this workload more than the second socket's cores
+    bring: measured 0.56 images/s on 2 x 32 cores against 0.94 on 32 cores of one node).  One timed forward each."""
+    start = set(os.sched_getaffinity(0))
+    results = []
+    for name, cpus in [("all nodes", start)] + [(f"node {i}", c) for i, c in enumerate(numa_node_cpus()[:1]) if c != start]:
+        os.sched_setaffinity(0, cpus)
+        n = use_host_cores()
+        step(feats, masks, pos)
+        t0 = time.time()
+        step(feats, masks, pos)
+        results.append((time.time() - t0, name, cpus, n))
+    dt, name, cpus, n = min(results, key=lambda r: r[0])
+    os.sched_setaffinity(0, cpus)
+    use_host_cores()
+    return n, name, [(r[1], r[3], round(r[0], 3)) for r in results]
+
+
 def model_cfg(model):
     m = model.encoder.layers[0]
     return dict(heads=m.n_heads, points=m.self_attn.num_points, topk_sa=m.topk_sa, num_layers=model.encoder.num_layers,
@@ -261,10 +300,10 @@ def reference_step_fn(model, device="cpu"):
 def cpu_baseline(pkg, model, budget_s=20.0):
     """The reference's CPU path on this host's cores, bounded sample (full bs=2 forwards for about `budget_s`)."""
     from salience_detr_b200.synthetic import make_inputs
-    cores = use_host_cores()
     feats, masks, pos = make_inputs(WORKLOAD, seed=0)
     step, kind, desc = reference_step_fn(model, "cpu")
-    step(feats, masks, pos)  # warm-up
+    cores, where, tried = best_cpu_setting(step, feats, masks, pos)
+    desc += f"; threads: {cores} on {where} (tried {tried})"
     times = []
     t_end = time.time() + budget_s
     while len(times) < 2 or (time.time() < t_end and len(times) < 10):
@@ -309,10 +348,11 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from salience_detr_b200.synthetic import build_model, make_inputs
-    cores = use_host_cores()
     model = build_model()
     feats, masks, pos = make_inputs(WORKLOAD, seed=0)
     step, kind, desc = reference_step_fn(model, "cpu")
+    cores, where, tried = best_cpu_setting(step, feats, masks, pos)
+    desc += f"; threads: {cores} on {where} (tried {tried})"
     for _ in range(args.warmup):
         step(feats, masks, pos)
     t0 = time.time()
@@ -418,6 +458,7 @@ def main():
     ap.add_argument("--gemm", default="auto", choices=["auto", "tcgen05", "3xtf32", "fp32", "tf32"])
     ap.add_argument("--mode", default="forward", choices=["forward", "train"])
     ap.add_argument("--bucket-mb", type=int, default=32)
+    ap.add_argument("--pipeline-depth", type=int, default=2, help="lanes of the host-buffer pipeline (e2e)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -503,7 +544,7 @@ def main():
     stream_keep, stream = stream, host_runner.stream
     e2e_serial_ms = timed(host_runner.run_host, args.steps, 3)
     stream = stream_keep
-    pipe = HostPipeline(model, feats, masks, None, depth=2, use_graph=not args.no_graph, use_order=not args.no_order)
+    pipe = HostPipeline(model, feats, masks, None, depth=args.pipeline_depth, use_graph=not args.no_graph, use_order=not args.no_order)
     host_batch = ([t.pin_memory() for t in feats_h], None)
     pipe.run([host_batch] * 4)  # warm-up
     barrier()
@@ -555,11 +596,13 @@ def main():
             except Exception:
                 traffic = None
         gemm_ms, gemm_flops, gemm_calls = time_gemm_kernels(pkg, runner)
-        tf32_peak = None
+        f16 = pkg.gemm.MODE == "auto" and pkg.gemm.OWN_KERNEL == "f16x3"
         try:
-            tf32_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"] / 2.0
+            tf32_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"] / (1.0 if f16 else 2.0)
+            gemm_peak_src = "MEASURED_PEAKS.json bf16_tflops" + ("" if f16 else " / 2 (TF32 dense = half the bf16 rate)")
         except Exception:
-            tf32_peak = 2250.0 / 2.0  # nominal dense bf16 / 2 (B200_PROFILING.md fallback)
+            tf32_peak = 1590.0 / (1.0 if f16 else 2.0)  # B200_PROFILING.md fallback
+            gemm_peak_src = "fallback (B200_PROFILING.md)"
         passes = 1 if pkg.gemm.MODE in ("fp32", "tf32") else 3
         gemm_exec = passes * gemm_flops / (gemm_ms / 1000.0) / 1e12
         line = {
@@ -569,9 +612,11 @@ def main():
             "config": {"workload": WORKLOAD, "batch_per_gpu": bsz, "global_batch": bsz * world,
                        "parallelism": f"dp{world} (independent replicas, no forward collective)",
                        "weights": "random init (seed 0) + N(0,0.02) sampling-offset weights",
-                       "gemm": {"auto": "3xTF32 (fp32-class accuracy): hand-written persistent tcgen05.mma.kind::tf32 GEMM (TMA, pre-split weight, "
-                                        "activation split in the kernel into tensor memory, double-buffered TMEM accumulator, TMA-store epilogue) for "
-                                        "every projection; GEMMs of <= 2304 rows (latency-bound) on cuBLAS fp32",
+                       "gemm": {"auto": ("3xFP16 (fp32-class accuracy, 22-bit operands: hi/lo fp16 split with exact power-of-two range scaling): "
+                                         "hand-written persistent tcgen05.mma.kind::f16 GEMM" if pkg.gemm.OWN_KERNEL == "f16x3" else
+                                         "3xTF32 (fp32-class accuracy): hand-written persistent tcgen05.mma.kind::tf32 GEMM") +
+                                        " (TMA, pre-split weight, activation split in the kernel into tensor memory, double-buffered TMEM "
+                                        "accumulator, TMA-store epilogue) for every projection; GEMMs of <= 2304 rows (latency-bound) on cuBLAS fp32",
                                 "tcgen05": "hand-written tcgen05.mma.kind::tf32 GEMM (TMA, in-kernel 3xTF32 split, TMEM accumulator; fp32-class accuracy)",
                                 "3xtf32": "cuBLAS TF32 tensor cores on 3-way split operands (3xTF32, fp32-class accuracy)",
                                 "fp32": "cuBLAS fp32 SIMT", "tf32": "cuBLAS TF32 (reduced precision)"}[pkg.gemm.MODE], "cuda_graph": runner.graph is not None,
@@ -580,6 +625,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": round(e2e_val, 2), "unit": "images/s", "h2d_bytes_per_step": host_runner.h2d_bytes,
                     "d2h_bytes_per_step": host_runner.d2h_bytes, "ms_per_step": round(e2e_ms / e2e_steps, 4), "steps": e2e_steps,
+                    "pipeline_depth": args.pipeline_depth,
                     "api": "salience_detr_b200.runner.HostPipeline.run (pinned host feature maps in, memory out, double-buffered: "
                            "H2D, forward and D2H of consecutive batches overlap; the sine position embedding is derived from "
                            "the padding masks on the device, as in the detector, salience_detr.py:172-176)",
@@ -591,7 +637,9 @@ def main():
                     "numa": numa},
             "gpu_launches": runner.launches_per_step * args.steps,
             "gpu_launches_per_step": runner.launches_per_step,
-            "roofline": {"bound": "hbm", "kernel": "sdetr::msda_fwd_kernel<32,4,4,fused> (6 launches/step)",
+            "roofline": {"bound": "hbm (SURVEY.md 8(d) denominator; measured: the gather is bound by the L1 tag stage, ~2 clk per "
+                                  "128-byte line, DESIGN.md 3.1)",
+                         "kernel": "sdetr::msda_fwd_kernel<32,4,4,fused> (6 launches/step)",
                          "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic,
                          "algorithmic_bytes_per_step": int(sum(byts)), "kernel_ms_per_step": round(sum(med), 4),
@@ -601,9 +649,10 @@ def main():
                                            "per_layer_us": [round(1000 * x, 1) for x in cold],
                                            "how": "the same six launches replayed alone after an L2 flush (round-1 definition)"}},
             # secondary leg: the dense projections (tensor-bound; 3xTF32 issues 3 TF32 MMA passes per logical product)
-            "roofline_gemm": {"bound": "tensor", "kernels": "sdetr::gemm_3xtf32_p_kernel<presplit> (+ cuBLAS fp32 for <= 2304-row GEMMs)",
-                              "achieved": round(gemm_exec, 1), "peak": round(tf32_peak, 1),
-                              "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 dense = half the bf16 rate)",
+            "roofline_gemm": {"bound": "tensor (measured: the kernel is bound by L2<->SM operand/result traffic, DESIGN.md 3.4)",
+                              "kernels": ("sdetr::gemm_f16x3_kernel (3xFP16, tcgen05.mma.kind::f16)" if f16 else
+                                          "sdetr::gemm_3xtf32_p_kernel<presplit>") + " (+ cuBLAS fp32 for <= 2304-row GEMMs)",
+                              "achieved": round(gemm_exec, 1), "peak": round(tf32_peak, 1), "peak_source": gemm_peak_src,
                               "unit": "TFLOP/s", "frac": round(gemm_exec / tf32_peak, 4),
                               "logical_tflops": round(gemm_flops / (gemm_ms / 1000.0) / 1e12, 1),
                               "mma_passes": passes, "gemm_calls_per_step": gemm_calls,

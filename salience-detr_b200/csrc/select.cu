@@ -508,34 +508,49 @@ __global__ void __launch_bounds__(kSortThreads) topk_select_kernel(const float *
 // selected them (b*L CTAs in parallel, <= 8192 elements each) and merging by rank -- every candidate's final
 // position is its rank in its own list plus binary-search ranks in the other lists, one thread per candidate,
 // all SMs -- gives the same order ~5x faster.
-constexpr int kLevelSortMax = 8192;
+// A level's winners are further cut into SLICES of at most kSlice candidates (by position in index order), one CTA per
+// (image, slice): every CTA of a level redoes the (cheap, L2-resident) threshold search and prefix scan over the whole
+// level but compacts and sorts only its own slice -- a 2048-element bitonic sort (66 stages) instead of an 8192-element
+// one (91 stages on 4x the data) on the critical path, and 16 CTAs instead of 8 at config 2.  The rank merge below does
+// not care how the candidates were partitioned into sorted lists.
+constexpr int kSlice = 2048;
+constexpr int kMaxLists = 32;
+
+struct ListTable {
+    int n;
+    int level[kMaxLists], lo[kMaxLists], cnt[kMaxLists], off[kMaxLists + 1];  // winners [lo, lo+cnt) of `level` -> sorted[off ..]
+};
 
 __global__ void __launch_bounds__(kSortThreads) level_select_sort_kernel(const float *__restrict__ raw,
                                                                          const uint8_t *__restrict__ mask,
                                                                          const float *__restrict__ lmin, LevelTable tb,
-                                                                         int nv, int K,
+                                                                         ListTable lt, int nv, int K,
                                                                          unsigned long long *__restrict__ sorted) {
     __shared__ SelectSmem sm;
-    extern __shared__ unsigned long long comp[];
-    const int b = blockIdx.x / tb.L, l = blockIdx.x % tb.L;
-    const int k = tb.k[l];
-    if (k == 0) return;
+    static_assert(sizeof(sm.hist) >= kSlice * sizeof(unsigned long long), "slice buffer aliases the histograms");
+    unsigned long long *comp = reinterpret_cast<unsigned long long *>(sm.hist);  // free once radix_select returned
+    const int b = blockIdx.x / lt.n, li = blockIdx.x % lt.n;
+    const int l = lt.level[li], k = tb.k[l];
+    const uint32_t lo = (uint32_t)lt.lo[li], cnt = (uint32_t)lt.cnt[li];
     int N = 1;
-    while (N < k) N <<= 1;
+    while (N < (int)cnt) N <<= 1;
     const int64_t off = (int64_t)b * nv + tb.start[l];
     const float fill = __ldg(lmin + l);
     auto key = [=](int i) { return desc_key(__ldg(mask + off + i) ? fill : __ldg(raw + off + i)); };
     uint32_t T, need;
     radix_select(key, tb.size[l], k, T, need, sm);
-    for (int j = k + threadIdx.x; j < N; j += kSortThreads) comp[j] = ~0ull;
+    __syncthreads();
+    for (int j = cnt + threadIdx.x; j < N; j += kSortThreads) comp[j] = ~0ull;
     const uint32_t start = (uint32_t)tb.start[l];
     stable_compact(key, tb.size[l], T, need,
-                   [&](uint32_t pos, int i, uint32_t kv) { comp[pos] = ((unsigned long long)kv << 32) | (start + (uint32_t)i); },
+                   [&](uint32_t pos, int i, uint32_t kv) {
+                       if (pos - lo < cnt) comp[pos - lo] = ((unsigned long long)kv << 32) | (start + (uint32_t)i);
+                   },
                    sm);
     __syncthreads();
     bitonic_sort_smem(comp, N);
-    const int64_t dst = (int64_t)b * K + tb.koff[l];
-    for (int j = threadIdx.x; j < k; j += kSortThreads) sorted[dst + j] = comp[j];
+    const int64_t dst = (int64_t)b * K + lt.off[li];
+    for (int j = threadIdx.x; j < (int)cnt; j += kSortThreads) sorted[dst + j] = comp[j];
 }
 
 __device__ __forceinline__ int lower_bound_u64(const unsigned long long *a, int n, unsigned long long key) {
@@ -548,21 +563,20 @@ __device__ __forceinline__ int lower_bound_u64(const unsigned long long *a, int 
     return lo;
 }
 
-__global__ void __launch_bounds__(256) merge_rank_kernel(const unsigned long long *__restrict__ sorted, LevelTable tb, int K,
+__global__ void __launch_bounds__(256) merge_rank_kernel(const unsigned long long *__restrict__ sorted, ListTable lt, int K,
                                                          int batch, int64_t *__restrict__ sel_inds,
                                                          float *__restrict__ sel_score) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (int64_t)batch * K) return;
     const int b = (int)(g / K), j = (int)(g - (int64_t)b * K);
-    int l = 0;
-#pragma unroll
-    for (int t = 1; t < kMaxLevels; ++t)
-        if (t < tb.L && j >= tb.koff[t]) l = t;
+    int li = 0;
+    for (int t = 1; t < lt.n; ++t)
+        if (j >= lt.off[t]) li = t;
     const unsigned long long *base = sorted + (int64_t)b * K;
     const unsigned long long key = base[j];
-    int pos = j - tb.koff[l];
-    for (int t = 0; t < tb.L; ++t)
-        if (t != l) pos += lower_bound_u64(base + tb.koff[t], tb.k[t], key);
+    int pos = j - lt.off[li];
+    for (int t = 0; t < lt.n; ++t)
+        if (t != li) pos += lower_bound_u64(base + lt.off[t], lt.cnt[t], key);
     sel_inds[(int64_t)b * K + pos] = (int64_t)(key & 0xffffffffull);
     sel_score[(int64_t)b * K + pos] = desc_key_inv((uint32_t)(key >> 32));
 }
@@ -706,16 +720,23 @@ extern "C" int sdetr_salience_select(const float *raw_score, const uint8_t *mask
         }
         bins = (((max_h_px + cell_px - 1) / cell_px + 1) * cells_x) << 3;
     }
-    if (kmax <= kLevelSortMax && bins <= 12000) {
-        // fastest path: select + sort per (image, level), rank merge, counting-sort processing order
-        static PerDeviceOnce once_a;
-        SDETR_OPT_IN_SMEM(once_a, level_select_sort_kernel, kLevelSortMax * (int)sizeof(unsigned long long), "salience_select");
+    ListTable lt{};
+    for (int l = 0; l < num_levels; ++l)
+        for (int lo = 0; lo < tb.k[l]; lo += kSlice) {
+            if (lt.n < kMaxLists) {
+                lt.level[lt.n] = l, lt.lo[lt.n] = lo, lt.cnt[lt.n] = tb.k[l] - lo < kSlice ? tb.k[l] - lo : kSlice;
+                lt.off[lt.n] = tb.koff[l] + lo;
+            }
+            ++lt.n;
+        }
+    if (lt.n <= kMaxLists && bins <= 12000) {
+        // fastest path: select + sort per (image, slice of a level), rank merge, counting-sort processing order
+        lt.off[lt.n] = K;
         unsigned long long *sorted = reinterpret_cast<unsigned long long *>(buf[0]);  // b*K u64 <= two u32 buffers
-        level_select_sort_kernel<<<batch * num_levels, kSortThreads, (size_t)next_pow2(kmax) * sizeof(unsigned long long),
-                                   s>>>(raw_score, mask, lmin, tb, num_value, K, sorted);
+        level_select_sort_kernel<<<batch * lt.n, kSortThreads, 0, s>>>(raw_score, mask, lmin, tb, lt, num_value, K, sorted);
         if ((rc = check_launch("salience_select/level_select_sort"))) return rc;
         const int64_t cand = (int64_t)batch * K;
-        merge_rank_kernel<<<(unsigned)((cand + 255) / 256), 256, 0, s>>>(sorted, tb, K, batch, selected_inds, selected_score);
+        merge_rank_kernel<<<(unsigned)((cand + 255) / 256), 256, 0, s>>>(sorted, lt, K, batch, selected_inds, selected_score);
         if ((rc = check_launch("salience_select/merge_rank"))) return rc;
         if (tile_order) {
             tile_count_kernel<<<batch, kSortThreads, (size_t)(bins + 1) * sizeof(uint32_t), s>>>(selected_inds, tb, K, cell_px,
