@@ -458,7 +458,7 @@ def main():
     ap.add_argument("--gemm", default="auto", choices=["auto", "tcgen05", "3xtf32", "fp32", "tf32"])
     ap.add_argument("--mode", default="forward", choices=["forward", "train"])
     ap.add_argument("--bucket-mb", type=int, default=32)
-    ap.add_argument("--pipeline-depth", type=int, default=2, help="lanes of the host-buffer pipeline (e2e)")
+    ap.add_argument("--pipeline-depth", type=int, default=3, help="lanes of the host-buffer pipeline (e2e)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
