@@ -44,6 +44,8 @@ FUSED_PRE_ATTENTION = True  # C = 256 / head_dim 32: gather+in-proj, attention, 
 # only for geometries the fused pre-attention does not cover (C != 256 or head_dim != 32):
 SMALL_ATTENTION = False   # sdetr_attention_small instead of SDPA between the library projections
 MHA_GEMM_TENSOR_CORE = False  # projections of the 600 rows on the tensor-core GEMM instead of cuBLAS SGEMM (latency-bound: slower)
+OVERLAP_PROJ = True  # the offsets|logits GEMM of ALL rows runs on a side stream beside the (latency-bound, few-CTA) class-max /
+# top-300 / pre-attention chain, from the gather's q + pos; the 300 rows the pre-attention rewrites are recomputed afterwards
 TILE_CELL_PX = 64   # edge (image pixels) of the spatial cells that define the MSDA processing order
 MSDA_SCHEDULE = 1   # 0 = query-major, 1 = head-major chunks (see include/sdetr_b200.h)
 
@@ -210,7 +212,7 @@ class SalienceTransformerEncoderLayer(nn.Module):
             o = cabi.attention_qkv(qkv, self.n_heads)
             cabi.mha_out_proj_ln_scatter_(q, o, t, w_out_t, self.pre_attention.out_proj.bias, self.pre_norm.weight,
                                           self.pre_norm.bias, self.pre_norm.eps, top, qp if qs is not None else None, qs)
-            return q, qs
+            return q, qs, top
         t, x = cabi.rows_gather_add(q, qp, top)           # t = q[top], x = t + qp[top]
         wqk, bqk, wv, bv = self._mha_views()
         h, d = self.n_heads, c // self.n_heads
@@ -225,15 +227,31 @@ class SalienceTransformerEncoderLayer(nn.Module):
         o = lin(o, self.pre_attention.out_proj.weight, self.pre_attention.out_proj.bias)
         t = cabi.add_layernorm(t, o, self.pre_norm.weight, self.pre_norm.bias, self.pre_norm.eps)
         cabi.rows_scatter_(q, top, t)  # q is this layer's private gather buffer
-        return q, None
+        return q, None, top
+
+    def overlaps_projection(self, nq: int) -> bool:
+        """True when the fused pre-attention runs (it keeps `q + pos` current), i.e. when the stale-row patch is exact."""
+        return (OVERLAP_PROJ and FUSED_PRE_ATTENTION and FUSED_QUERY_SUM and self.embed_dim == 256 and
+                self.embed_dim // self.n_heads == 32 and min(self.topk_sa, nq) <= 448)
 
     def forward_fast(self, q, qp, mc, ref_q, vbuf, v_bstride, v_tstride, v_off, num_value, spatial_shapes,
-                     level_start_index, order=None, schedule=MSDA_SCHEDULE, qs=None, value_ready=None):
+                     level_start_index, order=None, schedule=MSDA_SCHEDULE, qs=None, value_ready=None, proj_future=None):
         """``qs``: optional q + qp buffer (from the gather); the fused pre-attention keeps its rewritten rows current.
-        ``value_ready``: optional callable returning the value buffer, run right before the sampling launch."""
-        q, qs = self._pre_attention_fast(q, qp, mc, qs)
+        ``value_ready``: optional callable returning the value buffer, run right before the sampling launch.
+        ``proj_future``: optional (proj, side_stream): the offsets|logits projection of the PRE-attention ``qs``, in flight on
+        a side stream; joined here and the top-k rows the pre-attention rewrote are recomputed."""
+        q, qs, top = self._pre_attention_fast(q, qp, mc, qs)
+        proj = None
+        if proj_future is not None:
+            proj, side = proj_future
+            cur = torch.cuda.current_stream(q.device)
+            cur.wait_stream(side)
+            proj.record_stream(cur)
+            # the side-stream GEMM may have read the rewritten rows mid-update: exactly those rows are replaced here
+            w, bias = self.self_attn.fused_projection()
+            cabi.rows_scatter_(proj, top, F.linear(cabi.rows_gather(qs, top), w, bias).contiguous())
         a = self.self_attn.forward_projected(qs if qs is not None else q + qp, ref_q, vbuf, v_bstride, v_tstride, v_off, num_value, spatial_shapes,
-                                             level_start_index, order, schedule, value_ready=value_ready)
+                                             level_start_index, order, schedule, value_ready=value_ready, proj=proj)
         q = cabi.add_layernorm(q, a, self.norm1.weight, self.norm1.bias, self.norm1.eps, out=q)
         h = gemm.linear(q, self.linear1.weight, self.linear1.bias)
         f = gemm.linear(h, self.linear2.weight, self.linear2.bias, relu_input=True)  # ReLU fused into the operand split
@@ -346,10 +364,17 @@ class SalienceTransformerEncoder(nn.Module):
                     cur.wait_stream(side)
                     vj.record_stream(cur)
                     return vj
+            fut = None
+            if qs is not None and layer.overlaps_projection(nq):
+                cur_s, side_s = torch.cuda.current_stream(query.device), self._side_stream(query.device)
+                side_s.wait_stream(cur_s)
+                with torch.cuda.stream(side_s):
+                    wf, bf = layer.self_attn.fused_projection()
+                    fut = (gemm.linear(qs, wf, bf), side_s)
             mc = cabi.class_max_times_fg(gemm.linear(q, self.enhance_mcsp.weight, self.enhance_mcsp.bias), fq)
             q = layer.forward_fast(q, qp, mc, rq, vbuf, nv * wide, wide, 0 if per_layer else j * c, nv, spatial_shapes,
                                    level_start_index, None if query_orders is None else query_orders[j], qs=qs,
-                                   value_ready=ready)
+                                   value_ready=ready, proj_future=fut)
             cabi.token_scatter_(out, q, inds, focus)
         if multi_level_masks is not None:
             cabi.background_embed_(out, mask_u8, inds, self.background_embedding.row_embed.weight,
