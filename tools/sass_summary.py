@@ -23,7 +23,7 @@ def main():
         if m:
             cur = names[i] if i < len(names) else m.group(1)
             i += 1
-            cur = re.sub(r"\(.*$", "", cur)
+            cur = re.sub(r"\(.*$", "", cur.replace("(anonymous namespace)", "{anon}"))
             counts[cur] = collections.Counter()
             continue
         if cur is None:
