@@ -237,6 +237,12 @@ int sdetr_flatten_tokens_pos(const float *const *feats_host, const float *pos_to
                              const float *keep, const int32_t *level_size_host, int batch, int channels, int num_levels,
                              float *feat_tok, float *lpos_tok, float *x_tok, sdetr_stream_t stream);
 
+/* Layout hand-off to / from a convolutional neck (salience_transformer.py:185-192): tokens (b,Nv,C) <-> per-level NCHW
+ * maps; maps_host = HOST array of num_levels device pointers to (b,C,H_l*W_l) fp32.  to_maps != 0: tokens -> maps (the
+ * reference's split + transpose + contiguous + reshape); to_maps == 0: maps -> tokens (flatten(2).transpose(1,2) + cat). */
+int sdetr_token_map_transpose(float *tokens, float *const *maps_host, const int32_t *level_size_host, int batch, int channels,
+                              int num_levels, int to_maps, sdetr_stream_t stream);
+
 /* Everything the path derives from the padding masks, in two launches (replaces ~60 ATen launches and makes a fresh-mask
  * batch cheap).  mask (b,Nv) uint8 (1 = padding), levels given by host (H_l, W_l).
  *   valid_token_nums[b,l] = #valid tokens;  focus_token_nums[b,l] = int(float(valid) * level_filter_ratio[l])

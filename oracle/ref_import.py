@@ -20,6 +20,8 @@ _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BASELINE_REF = os.path.join(_REPO, "baseline", "_ref")  # git-ignored install of the reference's hot-path modules
 # the Python modules of the path; everything else of the reference stays where it is
 PATH_MODULES = ("base_transformer.py", "basic.py", "ms_deform_attn.py", "position_encoding.py", "salience_transformer.py")
+# consumer right after the path: the RepVGG neck the encoder memory is handed to, for the hand-off test
+NECK_MODULES = (("models/necks", "repnet.py"), ("models/bricks", "misc.py"))
 
 
 def _has(root: str) -> bool:
@@ -61,6 +63,11 @@ def install(src: str = "/root/reference", dst: str = BASELINE_REF) -> bool:
         a, b = os.path.join(src, "models", "bricks", name), os.path.join(out, name)
         if not (os.path.exists(b) and filecmp.cmp(a, b, shallow=False)):
             shutil.copyfile(a, b)
+    for sub, name in NECK_MODULES:
+        a, b = os.path.join(src, sub, name), os.path.join(dst, sub, name)
+        os.makedirs(os.path.dirname(b), exist_ok=True)
+        if os.path.exists(a) and not (os.path.exists(b) and filecmp.cmp(a, b, shallow=False)):
+            shutil.copyfile(a, b)
     with open(os.path.join(dst, "README"), "w") as f:
         f.write("Unmodified copies of xiuqhou/Salience-DETR models/bricks/{%s} (reference arm of bench.py and the\n"
                 "drop-in tests; written by oracle/ref_import.install(), git-ignored, never imported by the product).\n"
@@ -100,7 +107,15 @@ def load():
         import models.bricks.salience_transformer as st  # noqa
         import models.bricks.position_encoding as pe  # noqa
         import models.bricks.base_transformer as bt  # noqa
-    return types.SimpleNamespace(msda=msda, st=st, pe=pe, bt=bt)
+    ns = types.SimpleNamespace(msda=msda, st=st, pe=pe, bt=bt, repnet=None)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            import models.necks.repnet as repnet  # noqa
+        ns.repnet = repnet
+    except Exception:  # older installs without the neck modules
+        pass
+    return ns
 
 
 class _Stop(Exception):

@@ -57,6 +57,7 @@ SIGNATURES = {
     "sdetr_gemm_3xtf32": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
     "sdetr_gemm_3xtf32_pre": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
     "sdetr_flatten_tokens_pos": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "sdetr_token_map_transpose": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sdetr_mask_plan": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sdetr_sine_pos_tokens": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
     "sdetr_split_f16_pair": (_i, [_vp, _i64, _f, _vp, _vp, _vp]),
@@ -495,6 +496,28 @@ def flatten_tokens_pos(feats, pos_tokens, level_embeds, keep):
                                         _host_i32(sizes), b, c, L, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), _stream())
     _check(rc, "sdetr_flatten_tokens_pos")
     return out
+
+
+def tokens_to_maps(tokens, shapes):
+    """(b,Nv,C) tokens -> list of per-level (b,C,H,W) maps (one launch; salience_transformer.py:186-190)."""
+    b, nv, c = tokens.shape
+    maps = [torch.empty(b, c, h, w, device=tokens.device, dtype=torch.float32) for h, w in shapes]
+    ptrs = (ctypes.c_void_p * len(shapes))(*[m.data_ptr() for m in maps])
+    rc = lib().sdetr_token_map_transpose(_req(tokens, "tokens", torch.float32), ptrs, _host_i32([h * w for h, w in shapes]), b, c,
+                                         len(shapes), 1, _stream())
+    _check(rc, "sdetr_token_map_transpose")
+    return maps
+
+
+def maps_to_tokens(maps):
+    """list of per-level (b,C,H,W) maps -> (b,Nv,C) tokens (one launch; salience_transformer.py:192)."""
+    b, c = maps[0].shape[:2]
+    sizes = [m.shape[2] * m.shape[3] for m in maps]
+    tokens = torch.empty(b, sum(sizes), c, device=maps[0].device, dtype=torch.float32)
+    ptrs = (ctypes.c_void_p * len(maps))(*[_req(m, "map", torch.float32) for m in maps])
+    rc = lib().sdetr_token_map_transpose(tokens.data_ptr(), ptrs, _host_i32(sizes), b, c, len(maps), 0, _stream())
+    _check(rc, "sdetr_token_map_transpose")
+    return tokens
 
 
 def mask_plan(mask_u8, shapes, level_filter_ratio, pos_offset=-0.5, pos_eps=1e-6, pos_scale=2 * 3.141592653589793):

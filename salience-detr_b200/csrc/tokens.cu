@@ -685,6 +685,71 @@ extern "C" int sdetr_flatten_tokens_pos(const float *const *feats_host, const fl
                                feat_tok, lpos_tok, x_tok, stream);
 }
 
+// ---- layout hand-off to / from a convolutional neck (salience_transformer.py:185-192) -----------------------------------------
+// tokens (b,Nv,C) <-> per-level NCHW maps (b,C,H_l*W_l): 32x32 tiles transposed through shared memory, both directions
+// coalesced.  to_maps != 0: tokens -> maps (the reference's split + transpose + contiguous + reshape); else maps -> tokens
+// (its flatten(2).transpose(1,2) + cat).
+namespace sdetr {
+__global__ void __launch_bounds__(256) token_map_transpose_kernel(FlattenArgs a, int nv, int C, float *__restrict__ tokens,
+                                                                  int to_maps) {
+    __shared__ float tile[32][33];
+    int l = 0;
+#pragma unroll
+    for (int u = 1; u < kMaxLevels; ++u)
+        if (u < a.L && (int)blockIdx.x >= a.tile0[u]) l = u;
+    const int t0 = ((int)blockIdx.x - a.tile0[l]) * 32, c0 = blockIdx.y * 32, b = blockIdx.z;
+    const int hw = a.size[l];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    float *map = const_cast<float *>(a.feat[l]) + ((int64_t)b * C + c0) * hw;
+    float *tok = tokens + ((int64_t)b * nv + a.start[l]) * C;
+    if (to_maps) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // read tokens: consecutive channels of one token are contiguous
+            const int t = t0 + ty + 8 * i, c = c0 + tx;
+            tile[ty + 8 * i][tx] = (t < hw && c < C) ? tok[(int64_t)t * C + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // write maps: consecutive tokens of one channel are contiguous
+            const int c = ty + 8 * i, t = t0 + tx;
+            if (t < hw && c0 + c < C) map[(int64_t)c * hw + t] = tile[tx][c];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = ty + 8 * i, t = t0 + tx;
+            tile[c][tx] = (t < hw && c0 + c < C) ? map[(int64_t)c * hw + t] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int t = t0 + ty + 8 * i, c = c0 + tx;
+            if (t < hw && c < C) tok[(int64_t)t * C + c] = tile[tx][ty + 8 * i];
+        }
+    }
+}
+}  // namespace sdetr
+
+extern "C" int sdetr_token_map_transpose(float *tokens, float *const *maps_host, const int32_t *level_size_host, int batch,
+                                         int channels, int num_levels, int to_maps, sdetr_stream_t stream) {
+    SDETR_REQUIRE(tokens && maps_host && level_size_host, SDETR_ERR_INVALID_ARG, "token_map_transpose: null pointer");
+    SDETR_REQUIRE(batch > 0 && batch <= 65535 && channels > 0 && num_levels > 0 && num_levels <= kMaxLevels, SDETR_ERR_INVALID_ARG,
+                  "token_map_transpose: bad sizes");
+    FlattenArgs a{};
+    a.L = num_levels;
+    int nv = 0, tiles = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        SDETR_REQUIRE(maps_host[l] && level_size_host[l] > 0, SDETR_ERR_INVALID_ARG, "token_map_transpose: level %d", l);
+        a.feat[l] = maps_host[l], a.size[l] = level_size_host[l], a.start[l] = nv, a.tile0[l] = tiles;
+        nv += level_size_host[l];
+        tiles += (level_size_host[l] + 31) / 32;
+    }
+    a.tile0[num_levels] = tiles;
+    dim3 grid(tiles, (channels + 31) / 32, batch);
+    token_map_transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, nv, channels, tokens, to_maps);
+    return check_launch("token_map_transpose");
+}
+
 // ---- pre-attention gather: t = q[top], x = t + pos[top] (salience_transformer.py:368-371) -----------------------------
 namespace sdetr {
 __global__ void __launch_bounds__(kRowThreads) rows_gather_add_kernel(const float *__restrict__ src, const float *__restrict__ pos,

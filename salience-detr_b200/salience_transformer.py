@@ -689,11 +689,16 @@ class SalienceTransformer(nn.Module):
         if self.decoder is None and self.neck is None:
             return memory, salience
         if self.neck is not None:  # :185-192 (the RepVGG neck itself is outside the path: any nn.Module taking {i: NCHW})
-            feats = memory.split(plan.level_size, dim=1)
-            feats = {i: f.transpose(1, 2).contiguous().reshape(b, self.embed_dim, h, w)
-                     for i, (f, (h, w)) in enumerate(zip(feats, plan.shapes_list))}
-            feats = list(self.neck(feats).values())
-            memory = torch.cat([f.flatten(2).transpose(1, 2) for f in feats], dim=1).contiguous()
+            if memory.is_cuda and not (torch.is_grad_enabled() and memory.requires_grad):
+                feats = dict(enumerate(cabi.tokens_to_maps(memory.contiguous(), plan.shapes_list)))   # one launch each way
+                feats = list(self.neck(feats).values())
+                memory = cabi.maps_to_tokens([f.float().contiguous() for f in feats])
+            else:
+                feats = memory.split(plan.level_size, dim=1)
+                feats = {i: f.transpose(1, 2).contiguous().reshape(b, self.embed_dim, h, w)
+                         for i, (f, (h, w)) in enumerate(zip(feats, plan.shapes_list))}
+                feats = list(self.neck(feats).values())
+                memory = torch.cat([f.flatten(2).transpose(1, 2) for f in feats], dim=1).contiguous()
             if self.decoder is None:
                 return memory, salience
         output_memory, output_proposals = self.gen_encoder_output_proposals(memory, plan)

@@ -167,3 +167,50 @@ def test_full_transformer_forward_vs_reference(pkg, ref, ragged):
     assert (got[2] - want[2]).abs().amax(-1)[same].max() < 1e-3   # their class logits
     if bool(same.all()):  # identical proposal lists: the decoder outputs must agree everywhere
         assert (got[0] - want[0]).abs().max() < 2e-3 and (got[1] - want[1]).abs().max() < 2e-4
+
+
+def test_neck_handoff_with_reference_repvgg(pkg, ref):
+    """the encoder memory is handed to the RepVGG neck in per-level NCHW maps and comes back as tokens
+    (salience_transformer.py:185-192).  Layout kernels: exact round trip; then the reference's own RepVGGPluXNetwork
+    (models/necks/repnet.py:125-245, eval mode) plugged into OUR transformer against the reference transformer with the same
+    neck and weights: the memory that leaves the neck (captured at the decoder's `value` input) within 2e-3."""
+    if ref.repnet is None:
+        pytest.skip("baseline/_ref has no models/necks/repnet.py (re-run __graft_entry__.build())")
+    shapes = [(60, 80), (30, 40), (15, 20), (8, 10)]
+    g = torch.Generator().manual_seed(1)
+    tok = torch.randn(2, sum(h * w for h, w in shapes), 96, generator=g).to(DEV)
+    maps = pkg.cabi.tokens_to_maps(tok, shapes)
+    want = [t.transpose(1, 2).reshape(2, 96, h, w) for t, (h, w) in zip(tok.split([h * w for h, w in shapes], 1), shapes)]
+    assert all(torch.equal(a, b) for a, b in zip(maps, want))
+    assert torch.equal(pkg.cabi.maps_to_tokens(maps), tok)
+
+    tr = _reference(ref)
+    torch.manual_seed(3)
+    neck = ref.repnet.RepVGGPluXNetwork([GEO["embed_dim"]] * 4, [GEO["embed_dim"]] * 4, norm_layer=torch.nn.BatchNorm2d,
+                                       activation=torch.nn.SiLU, groups=4).to(DEV).eval()
+    tr.neck = neck
+    ours = _ours(pkg, _reference(ref))      # same seed -> same weights as `tr` (the state_dict now also has neck.* keys)
+    ours.neck = neck
+    feats, masks, pos = _inputs(False)
+    cap = {}
+
+    def grab(store):
+        def spy(**kw):
+            store["value"] = kw["value"]
+            raise ref_import._Stop()
+        return spy
+
+    for model, key in ((tr, "ref"), (ours, "ours")):
+        cap[key] = {}
+        model.decoder.forward = grab(cap[key])
+        try:
+            with torch.no_grad():
+                if key == "ours":
+                    pkg.gemm.MODE = "fp32"
+                model(feats, masks, pos, None, None, None)
+        except ref_import._Stop:
+            pass
+        finally:
+            del model.decoder.forward
+    a, w = cap["ours"]["value"], cap["ref"]["value"]
+    assert a.shape == w.shape and (a - w).abs().max() < 2e-3 * max(1.0, w.abs().max().item())
