@@ -237,6 +237,15 @@ int sdetr_flatten_tokens_pos(const float *const *feats_host, const float *pos_to
                              const float *keep, const int32_t *level_size_host, int batch, int channels, int num_levels,
                              float *feat_tok, float *lpos_tok, float *x_tok, sdetr_stream_t stream);
 
+/* Salience supervision targets (training side of the filter; SalienceCriterion.get_mask_single_level with noise_scale 0,
+ * models/detectors/salience_detr.py:64-114): target[b,t] = max over the boxes that contain the token's pixel centre
+ * ((x+.5) stride_x, (y+.5) stride_y) of 1 - sqrt(dx^2 + dy^2) / 2, and 0 unless one containing box has its largest border
+ * distance in (limit_lo[l], limit_hi[l]].  boxes (b,max_boxes,4) xyxy in pixels, 16-byte aligned; num_boxes (b,) int32. */
+int sdetr_salience_targets(const float *boxes_xyxy, const int32_t *num_boxes, int max_boxes, int batch, int num_value,
+                           int num_levels, const int32_t *level_h_host, const int32_t *level_w_host, const float *stride_y_host,
+                           const float *stride_x_host, const float *limit_lo_host, const float *limit_hi_host, float *target,
+                           sdetr_stream_t stream);
+
 /* Layout hand-off to / from a convolutional neck (salience_transformer.py:185-192): tokens (b,Nv,C) <-> per-level NCHW
  * maps; maps_host = HOST array of num_levels device pointers to (b,C,H_l*W_l) fp32.  to_maps != 0: tokens -> maps (the
  * reference's split + transpose + contiguous + reshape); to_maps == 0: maps -> tokens (flatten(2).transpose(1,2) + cat). */

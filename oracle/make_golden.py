@@ -217,6 +217,46 @@ def make_encoder_c256(name="encoder_c256.npz"):
         layer_num_query=np.array([x.shape[1] for x in captured["foreground_inds"]]))
 
 
+def make_salience_criterion(name="salience_criterion.npz"):
+    """SalienceCriterion (models/detectors/salience_detr.py:13-116) + sigmoid_focal_loss (models/bricks/losses.py:4-12).
+    The detector module cannot be imported here (pycocotools / accelerate are missing), so the two definitions are compiled
+    from the reference's own source files, unmodified, without the modules' import lines; loss, its gradient w.r.t. the
+    score maps, and the target maps on seeded boxes."""
+    import ast
+    from typing import Tuple  # noqa: F401
+    from torch import nn
+    from torch.nn import functional as F
+    from torchvision.ops import boxes as box_ops
+    ns = {"torch": torch, "nn": nn, "F": F, "box_ops": box_ops, "Tuple": Tuple}
+    for path, kind, ident in ((os.path.join(ref_import.REFERENCE_ROOT, "models/bricks/losses.py"), ast.FunctionDef, "sigmoid_focal_loss"),
+                              (os.path.join(ref_import.REFERENCE_ROOT, "models/detectors/salience_detr.py"), ast.ClassDef, "SalienceCriterion")):
+        node = [n for n in ast.parse(open(path).read()).body if isinstance(n, kind) and n.name == ident][0]
+        exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    crit = ns["SalienceCriterion"]()
+    g = torch.Generator().manual_seed(0)
+    shapes = [(50, 84), (25, 42), (13, 21), (7, 11)]
+    fg = [torch.randn(2, 1, h, w, generator=g).requires_grad_(True) for h, w in shapes]
+
+    def boxes(n):
+        return torch.cat([torch.rand(n, 2, generator=g) * 0.6 + 0.2, torch.rand(n, 2, generator=g) * 0.5 + 0.02], -1)
+
+    targets = [{"boxes": boxes(7)}, {"boxes": boxes(3)}]
+    image_sizes = [(400, 672), (380, 600)]
+    strides = [(400 / h, 672 / w) for h, w in shapes]
+    loss = crit(fg, targets, strides, image_sizes)["loss_salience"]
+    loss.backward()
+    mt = []
+    for lvl, (shape, st) in enumerate(zip(shapes, strides)):
+        cx, cy = crit.get_pixel_coordinate(shape, st, "cpu")
+        mt.append(torch.stack([crit.get_mask_single_level(cx, cy, box_ops._box_cxcywh_to_xyxy(t["boxes"]) *
+                                                          torch.tensor([iw, ih, iw, ih]), lvl)
+                               for t, (ih, iw) in zip(targets, image_sizes)]))
+    np.savez_compressed(os.path.join(OUT, name), loss=np_(loss), boxes0=np_(targets[0]["boxes"]), boxes1=np_(targets[1]["boxes"]),
+                        image_sizes=np.array(image_sizes), shapes=np.array(shapes), strides=np.array(strides, dtype=np.float64),
+                        mask_targets=np_(torch.cat(mt, 1)), **{f"fg{i}": np_(f) for i, f in enumerate(fg)},
+                        **{f"grad{i}": np_(f.grad) for i, f in enumerate(fg)})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     make_msda_core("msda_core_a.npz", b=2, shapes=[(10, 12), (5, 6), (3, 3), (2, 2)], m=4, d=32, nq=40, p=4, seed=1)
@@ -226,6 +266,7 @@ def main():
     make_encoder_tiny("encoder_tiny_ragged.npz", [(96, 128), (72, 90)], (96, 128), seed=6)
     make_encoder_c256()
     make_encoder_tiny_grads("encoder_tiny_even_grads.npz", [(96, 128), (96, 128)], (96, 128), seed=5)
+    make_salience_criterion()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
     print("torch", torch.__version__)

@@ -57,6 +57,7 @@ SIGNATURES = {
     "sdetr_gemm_3xtf32": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
     "sdetr_gemm_3xtf32_pre": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
     "sdetr_flatten_tokens_pos": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "sdetr_salience_targets": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sdetr_token_map_transpose": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sdetr_mask_plan": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sdetr_sine_pos_tokens": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
@@ -495,6 +496,20 @@ def flatten_tokens_pos(feats, pos_tokens, level_embeds, keep):
                                         _req(level_embeds, "level_embeds", torch.float32), _req(keep, "keep", torch.float32),
                                         _host_i32(sizes), b, c, L, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), _stream())
     _check(rc, "sdetr_flatten_tokens_pos")
+    return out
+
+
+def salience_targets(boxes_xyxy, num_boxes, shapes, strides, limit_range):
+    """boxes (b,max_boxes,4) xyxy pixels (padded), num_boxes (b,) int32 -> (b,Nv) salience targets (noise-free)."""
+    b, mb = boxes_xyxy.shape[:2]
+    nv = sum(h * w for h, w in shapes)
+    out = torch.empty(b, nv, device=num_boxes.device, dtype=torch.float32)
+    f = lambda xs: (ctypes.c_float * len(xs))(*[float(x) for x in xs])  # noqa: E731
+    rc = lib().sdetr_salience_targets(_req(boxes_xyxy, "boxes", torch.float32) if mb else None, _req(num_boxes, "num_boxes", torch.int32),
+                                      mb, b, nv, len(shapes), _host_i32([h for h, _ in shapes]), _host_i32([w for _, w in shapes]),
+                                      f([s[0] for s in strides]), f([s[1] for s in strides]), f([r[0] for r in limit_range]),
+                                      f([r[1] for r in limit_range]), out.data_ptr(), _stream())
+    _check(rc, "sdetr_salience_targets")
     return out
 
 

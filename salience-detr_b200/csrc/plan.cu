@@ -151,3 +151,75 @@ extern "C" int sdetr_sine_pos_tokens(const float *ynorm, const float *xnorm, con
                                                                                         num_pos_feats, pos_tokens);
     return check_launch("sine_pos_tokens");
 }
+
+// ---- salience supervision targets (training side of the filter) -- sdetr_salience_targets -------------------------------------
+// Reference semantics: SalienceCriterion.get_pixel_coordinate / get_mask_single_level with noise_scale = 0
+// (models/detectors/salience_detr.py:64-114): for every token (pixel centre ((x+.5) s_x, (y+.5) s_y) of its level) and every
+// ground-truth box, the four border distances decide (a) inside the box: min > 0, (b) the box belongs to this level:
+// lo < max <= hi; the target is max over the boxes the pixel is inside of  1 - sqrt(dx^2 + dy^2) / 2  with
+// dx = (l - r) / (l + r), dy = (t - b) / (t + b), and 0 unless some box satisfies (a) and (b).  The reference materialises
+// (HW, boxes, 4) tensors per image and level (~15 ATen launches each); here it is one thread per token, one launch.
+namespace sdetr {
+struct TargetLevels {
+    int H[kMaxLevels], W[kMaxLevels], start[kMaxLevels];
+    float sy[kMaxLevels], sx[kMaxLevels], lo[kMaxLevels], hi[kMaxLevels];
+    int L;
+};
+
+__global__ void __launch_bounds__(256) salience_targets_kernel(const float *__restrict__ boxes /* (b, max_boxes, 4) xyxy px */,
+                                                               const int32_t *__restrict__ num_boxes, int max_boxes, int batch,
+                                                               int nv, TargetLevels lv, float *__restrict__ target) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)batch * nv) return;
+    const int b = (int)(i / nv), t = (int)(i - (int64_t)b * nv);
+    int l = 0;
+#pragma unroll
+    for (int u = 1; u < kMaxLevels; ++u)
+        if (u < lv.L && t >= lv.start[u]) l = u;
+    const int r = t - lv.start[l], y = r / lv.W[l], x = r - y * lv.W[l];
+    const float cx = __fmul_rn((float)x + 0.5f, lv.sx[l]), cy = __fmul_rn((float)y + 0.5f, lv.sy[l]);
+    const float lo = lv.lo[l], hi = lv.hi[l];
+    float best = 0.f;
+    bool pos = false;
+    const float *bx = boxes + (int64_t)b * max_boxes * 4;
+    const int m = __ldg(num_boxes + b);
+    for (int j = 0; j < m; ++j) {
+        const float4 g = __ldg(reinterpret_cast<const float4 *>(bx) + j);
+        const float dl = __fsub_rn(cx, g.x), dt = __fsub_rn(cy, g.y), dr = __fsub_rn(g.z, cx), db = __fsub_rn(g.w, cy);
+        const float mn = fminf(fminf(dl, dt), fminf(dr, db)), mx = fmaxf(fmaxf(dl, dt), fmaxf(dr, db));
+        const bool inside = mn > 0.f;
+        pos |= inside && mx > lo && mx <= hi;
+        if (inside) {
+            const float ddx = __fdiv_rn(__fsub_rn(dl, dr), __fadd_rn(dl, dr)), ddy = __fdiv_rn(__fsub_rn(dt, db), __fadd_rn(dt, db));
+            const float conf = __fsub_rn(1.f, __fdiv_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy))), 2.f));
+            best = fmaxf(best, conf);
+        }
+    }
+    target[i] = pos ? best : 0.f;
+}
+}  // namespace sdetr
+
+extern "C" int sdetr_salience_targets(const float *boxes_xyxy, const int32_t *num_boxes, int max_boxes, int batch, int num_value,
+                                      int num_levels, const int32_t *level_h_host, const int32_t *level_w_host,
+                                      const float *stride_y_host, const float *stride_x_host, const float *limit_lo_host,
+                                      const float *limit_hi_host, float *target, sdetr_stream_t stream) {
+    SDETR_REQUIRE(num_boxes && level_h_host && level_w_host && stride_y_host && stride_x_host && limit_lo_host && limit_hi_host && target,
+                  SDETR_ERR_INVALID_ARG, "salience_targets: null pointer");
+    SDETR_REQUIRE(batch > 0 && max_boxes >= 0 && (max_boxes == 0 || (boxes_xyxy && aligned16(boxes_xyxy))) && num_levels > 0 &&
+                      num_levels <= kMaxLevels,
+                  SDETR_ERR_INVALID_ARG, "salience_targets: bad sizes / alignment");
+    TargetLevels lv{};
+    lv.L = num_levels;
+    int nv = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        lv.H[l] = level_h_host[l], lv.W[l] = level_w_host[l], lv.start[l] = nv;
+        lv.sy[l] = stride_y_host[l], lv.sx[l] = stride_x_host[l], lv.lo[l] = limit_lo_host[l], lv.hi[l] = limit_hi_host[l];
+        SDETR_REQUIRE(lv.H[l] > 0 && lv.W[l] > 0, SDETR_ERR_INVALID_ARG, "salience_targets: level %d is empty", l);
+        nv += lv.H[l] * lv.W[l];
+    }
+    SDETR_REQUIRE(nv == num_value, SDETR_ERR_INVALID_ARG, "salience_targets: levels hold %d tokens, num_value is %d", nv, num_value);
+    const int64_t n = (int64_t)batch * nv;
+    salience_targets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(boxes_xyxy, num_boxes, max_boxes, batch, nv,
+                                                                                         lv, target);
+    return check_launch("salience_targets");
+}

@@ -1083,3 +1083,30 @@ def test_config2_whole_path_benched_callable(pkg, config):
                                     foreground_inds=[oinds[:, :n] for n in plan.layer_num_query], multi_level_masks=masks)
         err = (mem_inj.cpu() - omem).abs().max().item()
         assert err < 1e-3, (mode, err)
+
+
+def test_salience_targets_kernel_vs_reference_golden(pkg):
+    """sdetr_salience_targets (one launch) against the reference SalienceCriterion's target maps, loss and gradient
+    (tests/golden/salience_criterion.npz); an image without boxes; many boxes."""
+    g, _ = load_golden("salience_criterion")
+    shapes = [tuple(int(v) for v in r) for r in g["shapes"]]
+    fg = [g[f"fg{i}"].to(DEV).requires_grad_(True) for i in range(4)]
+    targets = [{"boxes": g["boxes0"].to(DEV)}, {"boxes": g["boxes1"].to(DEV)}]
+    sizes = [tuple(int(v) for v in r) for r in g["image_sizes"]]
+    strides = [tuple(float(v) for v in r) for r in g["strides"]]
+    crit = pkg.SalienceCriterion()
+    n0 = pkg.cabi.launch_count()
+    mt = crit.mask_targets(shapes, targets, strides, sizes, torch.device(DEV))
+    assert pkg.cabi.launch_count() == n0 + 1
+    assert (mt.cpu() - g["mask_targets"]).abs().max() < 1e-6 and torch.equal(mt.cpu() > 0, g["mask_targets"] > 0)
+    loss = crit(fg, targets, strides, sizes)["loss_salience"]
+    assert abs(loss.item() - g["loss"].item()) < 1e-5
+    loss.backward()
+    for i in range(4):
+        assert (fg[i].grad.cpu() - g[f"grad{i}"]).abs().max() < 1e-6
+    gen = torch.Generator().manual_seed(5)
+    many = torch.cat([torch.rand(150, 2, generator=gen) * 0.8 + 0.1, torch.rand(150, 2, generator=gen) * 0.4 + 0.01], -1)
+    t2 = [{"boxes": torch.zeros(0, 4, device=DEV)}, {"boxes": many.to(DEV)}]
+    a = crit.mask_targets(shapes, t2, strides, sizes, torch.device(DEV)).cpu()
+    w = crit.mask_targets(shapes, [{"boxes": torch.zeros(0, 4)}, {"boxes": many}], strides, sizes, torch.device("cpu"))
+    assert a[0].abs().max() == 0 and (a - w).abs().max() < 1e-6

@@ -84,3 +84,49 @@ def test_mha_transposed_weight_cache_follows_parameter_updates():
     w_in_t2, w_out_t2 = layer._mha_transposed()
     assert w_in_t2 is not w_in_t and torch.equal(w_in_t2, layer.pre_attention.in_proj_weight.detach().t())
     assert torch.equal(w_out_t2, layer.pre_attention.out_proj.weight.detach().t())
+
+
+def test_salience_criterion_matches_reference_golden():
+    """SalienceCriterion mirror (host restatement of the target maps + focal loss) against the reference class's loss,
+    gradient and target maps (tests/golden/salience_criterion.npz, oracle/make_golden.py::make_salience_criterion)."""
+    import salience_detr_b200 as pkg
+    g, _ = load_golden("salience_criterion")
+    shapes = [tuple(int(v) for v in r) for r in g["shapes"]]
+    fg = [g[f"fg{i}"].clone().requires_grad_(True) for i in range(4)]
+    targets = [{"boxes": g["boxes0"]}, {"boxes": g["boxes1"]}]
+    sizes = [tuple(int(v) for v in r) for r in g["image_sizes"]]
+    strides = [tuple(float(v) for v in r) for r in g["strides"]]
+    crit = pkg.SalienceCriterion()
+    assert torch.equal(crit.mask_targets(shapes, targets, strides, sizes, torch.device("cpu")), g["mask_targets"])
+    loss = crit(fg, targets, strides, sizes)["loss_salience"]
+    assert abs(loss.item() - g["loss"].item()) < 1e-6
+    loss.backward()
+    for i in range(4):
+        assert (fg[i].grad - g[f"grad{i}"]).abs().max() < 1e-7
+    # an image without boxes contributes zero targets
+    assert crit.mask_targets(shapes, [{"boxes": torch.zeros(0, 4)}, targets[1]], strides, sizes, torch.device("cpu"))[0].abs().max() == 0
+
+
+def test_load_reference_checkpoint_layouts():
+    """Checkpoints as the reference writes them: bare state_dict, {"model": ...}, DDP `module.` prefix, whole-detector
+    `transformer.` prefix, shape-mismatched entries skipped (util/utils.py:358-422)."""
+    import salience_detr_b200 as pkg
+    g, sd = load_golden("encoder_tiny_even")
+    ref_sum = sum(float(v.double().sum()) for v in sd.values())
+
+    def fresh():
+        return _model(pkg)
+
+    def total(m):
+        return sum(float(v.double().sum()) for k, v in m.state_dict().items() if k in sd)
+
+    for ckpt in (sd, {"model": sd, "epoch": 3}, {"model": {"module." + k: v for k, v in sd.items()}},
+                 {"model": {**{"transformer." + k: v for k, v in sd.items()}, "backbone.conv1.weight": torch.zeros(3)}}):
+        m = fresh()
+        rep = pkg.load_reference_checkpoint(m, ckpt)
+        assert not rep["missing"] and not rep["mismatched"] and abs(total(m) - ref_sum) < 1e-6
+    bad = dict(sd)
+    bad["alpha"] = torch.zeros(7)
+    m = fresh()
+    rep = pkg.load_reference_checkpoint(m, bad)
+    assert rep["mismatched"] == ["alpha"] and m.alpha.shape == (3,)
