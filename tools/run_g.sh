@@ -1,5 +1,5 @@
 cd $GRAFT_REPO_ROOT
-(timeout 900 python -m pytest tests/test_gpu_parity.py -q -x -k "config2 or runner or golden_even or c256" 2>&1 | tail -6) > gpurun_out/r2_g_tests.log
+(timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -30) > gpurun_out/r2_g_tests.log
 (timeout 600 python bench.py --skip-cpu-baseline > gpurun_out/r2_g_bench.json) 2> gpurun_out/r2_g_bench.err
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_f16x3_kernel -s 2 -c 1 -o gpurun_out/r2_gemm_f16x3_ffn1 python tools/one_gemm.py 22726 256 2048 4 > gpurun_out/r2_g_ncu1.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_f16x3_kernel -s 2 -c 1 -o gpurun_out/r2_gemm_f16x3_ffn2 python tools/one_gemm.py 22726 2048 256 4 > gpurun_out/r2_g_ncu2.log 2>&1
