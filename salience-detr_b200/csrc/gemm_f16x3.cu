@@ -84,6 +84,13 @@ struct HGemmParams {
     float out_scale;  // 1 / (kActScale * weight scale), a power of two
 };
 
+// CL = true: clusters of TWO CTAs along M.  Both CTAs of a pair work on the same 128-column tile of the output for two
+// adjacent 128-row panels, so they need the same weight k-blocks: rank 0 fetches W_hi, rank 1 fetches W_lo, and each TMA
+// load is MULTICAST into both CTAs' rings -- an SM ingests half the weight bytes per tile (the kernel is bound by the
+// L2 -> SM fabric: ncu shows ~750 MB through the crossbar at 7.4-8.8 TB/s for both FFN GEMMs,
+// profiles/r2_gemm_f16x3_ffn{1,2}_ncu_full.txt).  A ring stage is refilled only when the MMAs of BOTH CTAs have released it
+// (tcgen05.commit multicast onto both `empty` barriers, count 2).
+template <bool CL>
 __global__ void __launch_bounds__(kHThreads, 1)
 gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_whi,
                   const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_c,
@@ -99,13 +106,19 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nk = p.K / kHK;
     const int n_tiles = (p.N + kHN - 1) / kHN, m_tiles = (p.M + kHM - 1) / kHM;
-    const int tiles = n_tiles * m_tiles;
+    // tile walk: CL = false: tile t = blockIdx.x + i * gridDim.x over (m, n) row-major;
+    //            CL = true : pair p = cluster + i * #clusters over (m-pair, n); this CTA's panel = 2 * m-pair + rank
+    const uint32_t rank = CL ? cluster_ctarank() : 0u;
+    const int first = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, step = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int tiles = CL ? ((m_tiles + 1) / 2) * n_tiles : n_tiles * m_tiles;
+    auto tile_m0 = [&](int t) { return (CL ? 2 * (t / n_tiles) + (int)rank : t / n_tiles) * kHM; };
+    auto tile_n0 = [&](int t) { return (t % n_tiles) * kHN; };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kHStages; ++s) {
             mbar_init(tma_full + s, 1);
             mbar_init(conv_full + s, 32 * kHConvWarps);
-            mbar_init(empty + s, 1);
+            mbar_init(empty + s, CL ? 2 : 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(acc_full + b, 1);
@@ -119,6 +132,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL) cluster_sync_all();  // the peer's barriers are initialised before any multicast / remote arrive can reach them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
@@ -126,17 +140,23 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles) * kHM, n0 = (tile % n_tiles) * kHN;
+            for (int tile = first; tile < tiles; tile += step) {
+                const int m0 = tile_m0(tile), n0 = tile_n0(tile);
                 for (int kb = 0; kb < nk; ++kb, ++it) {
                     const int s = it % kHStages;
-                    mbar_wait(empty + s, ((it / kHStages) & 1) ^ 1);
+                    mbar_wait(empty + s, ((it / kHStages) & 1) ^ 1);  // CL: released by the MMA warps of BOTH CTAs
                     uint8_t *st = smem + s * kHStageBytes;
-                    mbar_expect_tx(tma_full + s, 4 * kHBox);
+                    mbar_expect_tx(tma_full + s, 4 * kHBox);          // own A boxes + W_hi + W_lo (CL: one of them from the peer)
                     tma_load_2d(&map_a, tma_full + s, st, kb * kHK, m0);
                     tma_load_2d(&map_a, tma_full + s, st + kHBox, kb * kHK + 32, m0);
-                    tma_load_2d(&map_whi, tma_full + s, st + 2 * kHBox, kb * kHK, n0);
-                    tma_load_2d(&map_wlo, tma_full + s, st + 3 * kHBox, kb * kHK, n0);
+                    if (!CL) {
+                        tma_load_2d(&map_whi, tma_full + s, st + 2 * kHBox, kb * kHK, n0);
+                        tma_load_2d(&map_wlo, tma_full + s, st + 3 * kHBox, kb * kHK, n0);
+                    } else if (rank == 0) {
+                        tma_load_2d_mc(&map_whi, tma_full + s, st + 2 * kHBox, kb * kHK, n0, 0b11);
+                    } else {
+                        tma_load_2d_mc(&map_wlo, tma_full + s, st + 3 * kHBox, kb * kHK, n0, 0b11);
+                    }
                 }
             }
         }
@@ -144,7 +164,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ===== MMA issuer =====
         if (lane == 0) {
             uint32_t it = 0, tc = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tc) {
+            for (int tile = first; tile < tiles; tile += step, ++tc) {
                 const uint32_t buf = tc & 1;
                 mbar_wait(acc_empty + buf, ((tc >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -162,7 +182,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         umma_f16_ts(acc, a_hi + 8u * k, d_lo + 2 * k, kIdescF16, 1);
                         umma_f16_ts(acc, a_lo + 8u * k, d_hi + 2 * k, kIdescF16, 1);
                     }
-                    umma_commit(empty + s);
+                    if (CL) umma_commit_mc(empty + s, 0b11);  // stage reusable (in both CTAs) once these MMAs have read it
+                    else umma_commit(empty + s);
                 }
                 umma_commit(acc_full + buf);
             }
@@ -171,7 +192,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ===== converters: landed fp32 A boxes -> scaled, split, packed f16x2 -> TMEM slot =====
         const int q = warp & 3, half = (warp - 4) >> 2, r_in = q * 32 + lane;
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int tile = first; tile < tiles; tile += step) {
             for (int kb = 0; kb < nk; ++kb, ++it) {
                 const int s = it % kHStages;
                 mbar_wait(tma_full + s, (it / kHStages) & 1);
@@ -202,8 +223,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const bool elected = threadIdx.x == 12 * 32;
         const float sc = p.out_scale;
         uint32_t tc = 0, box_it = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tc) {
-            const int m0 = (tile / n_tiles) * kHM, n0 = (tile % n_tiles) * kHN;
+        for (int tile = first; tile < tiles; tile += step, ++tc) {
+            const int m0 = tile_m0(tile), n0 = tile_n0(tile);
             const uint32_t buf = tc & 1;
             mbar_wait(acc_full + buf, (tc >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -255,6 +276,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL) cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's shared memory until it is done too
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
     }
@@ -493,7 +515,13 @@ __global__ void split_f16_pair_kernel(const float *__restrict__ w, int64_t n, fl
 
 using namespace sdetr;
 
+static std::atomic<int> g_f16_cluster{1};  // 1: clusters of two CTAs share the weight k-blocks by TMA multicast (M >= 2 panels)
 static std::atomic<int> g_f16_as{0};  // 1: K <= 256 goes to the activation-stationary kernel (measured: +4 % on FFN-1, -3 % on the 6-layer value projection -- profiles/r2_gemm_shapes_f16x3_as.txt -- so off by default)
+
+extern "C" int sdetr_gemm_f16x3_set_cluster(int enable) {
+    g_f16_cluster = enable ? 1 : 0;
+    return SDETR_OK;
+}
 
 extern "C" int sdetr_gemm_f16x3_set_as(int enable) {
     g_f16_as = enable ? 1 : 0;
@@ -543,7 +571,9 @@ extern "C" int sdetr_gemm_f16x3_pre(const float *A, int64_t lda, const void *W_h
                               make_map_2d(&mc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C, M, N, ldc, 32, kHM);
     if (!use_tma_store) mc = ma;
     static PerDeviceOnce once, once_as;
-    SDETR_OPT_IN_SMEM(once, gemm_f16x3_kernel, kHSmem, "gemm_f16x3_pre");
+    static PerDeviceOnce once_cl;
+    SDETR_OPT_IN_SMEM(once, gemm_f16x3_kernel<false>, kHSmem, "gemm_f16x3_pre");
+    SDETR_OPT_IN_SMEM(once_cl, gemm_f16x3_kernel<true>, kHSmem, "gemm_f16x3_pre");
     SDETR_OPT_IN_SMEM(once_as, gemm_f16x3_as_kernel, kAsSmem, "gemm_f16x3_pre");
     const int sms = sm_count();
     HGemmParams p{bias, C, ldc, M, N, K, act, use_tma_store, 1.f / (kActScale * w_scale)};
@@ -554,7 +584,22 @@ extern "C" int sdetr_gemm_f16x3_pre(const float *A, int64_t lda, const void *W_h
         gemm_f16x3_as_kernel<<<(int)(units < sms ? units : sms), kHThreads, kAsSmem, (cudaStream_t)stream>>>(ma, mh, ml, mc, p, group);
         return check_launch("gemm_f16x3_pre/as");
     }
+    if (g_f16_cluster.load() && m_tiles >= 2) {
+        const int pairs = ((m_tiles + 1) / 2) * n_tiles, max_clusters = sms / 2;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * (pairs < max_clusters ? pairs : max_clusters));
+        cfg.blockDim = dim3(kHThreads);
+        cfg.dynamicSmemBytes = kHSmem;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+        cfg.attrs = at, cfg.numAttrs = 1;
+        const cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_f16x3_kernel<true>, ma, mh, ml, mc, p);
+        SDETR_REQUIRE(le == cudaSuccess, SDETR_ERR_CUDA, "gemm_f16x3_pre: cluster launch: %s", cudaGetErrorString(le));
+        return check_launch("gemm_f16x3_pre/cluster");
+    }
     const int tiles = n_tiles * m_tiles;
-    gemm_f16x3_kernel<<<tiles < sms ? tiles : sms, kHThreads, kHSmem, (cudaStream_t)stream>>>(ma, mh, ml, mc, p);
+    gemm_f16x3_kernel<false><<<tiles < sms ? tiles : sms, kHThreads, kHSmem, (cudaStream_t)stream>>>(ma, mh, ml, mc, p);
     return check_launch("gemm_f16x3_pre");
 }

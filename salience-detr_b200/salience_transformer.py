@@ -44,7 +44,8 @@ FUSED_PRE_ATTENTION = True  # C = 256 / head_dim 32: gather+in-proj, attention, 
 # only for geometries the fused pre-attention does not cover (C != 256 or head_dim != 32):
 SMALL_ATTENTION = False   # sdetr_attention_small instead of SDPA between the library projections
 MHA_GEMM_TENSOR_CORE = False  # projections of the 600 rows on the tensor-core GEMM instead of cuBLAS SGEMM (latency-bound: slower)
-OVERLAP_PROJ = True  # the offsets|logits GEMM of ALL rows runs on a side stream beside the (latency-bound, few-CTA) class-max /
+OVERLAP_PROJ = False  # (measured: 763 vs 773 images/s, e2e 918 vs 942 -- the extra launches and stream joins cost more than the overlap buys)
+# the offsets|logits GEMM of ALL rows runs on a side stream beside the (latency-bound, few-CTA) class-max /
 # top-300 / pre-attention chain, from the gather's q + pos; the 300 rows the pre-attention rewrites are recomputed afterwards
 TILE_CELL_PX = 64   # edge (image pixels) of the spatial cells that define the MSDA processing order
 MSDA_SCHEDULE = 1   # 0 = query-major, 1 = head-major chunks (see include/sdetr_b200.h)

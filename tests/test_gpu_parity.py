@@ -35,6 +35,7 @@ def _restore_global_state(pkg):
     pkg.gemm.MODE = mode
     pkg.gemm.OWN_KERNEL = os.environ.get("SDETR_GEMM_KERNEL", "f16x3")
     pkg.cabi.lib().sdetr_gemm_f16x3_set_as(0)
+    pkg.cabi.lib().sdetr_gemm_f16x3_set_cluster(1)
     pkg.cabi.set_option("msda_smem_broadcast", 1)
     pkg.cabi.lib().sdetr_gemm_set_variant(0)
     pkg.cabi.lib().sdetr_gemm_set_variant(3)
@@ -603,6 +604,21 @@ def test_gemm_f16x3_accuracy_and_range(pkg):
         assert (y1.double() - F.linear(xa, w.double(), b.double())).abs().max() < 1e-4, (rows, K, N)
         assert torch.equal(y0, y1), (rows, K, N)
         assert torch.equal(pkg.cabi.gemm_f16x3_pre(x, w_hi, w_lo, sc, b, act), y1)
+    # cluster-of-two variant (weight k-blocks multicast to two adjacent panels): same MMA sequence per tile -> bit-identical;
+    # odd panel counts (a dummy out-of-range panel), one-panel problems (plain launch), ragged N, long K, many tiles per CTA
+    for rows, K, N, act in [(22726, 256, 2048, 0), (22726, 2048, 256, 1), (44646, 256, 1536, 0), (129, 64, 128, 0), (385, 256, 91, 0),
+                            (100, 128, 256, 0), (36264, 256, 91, 2), (19000, 64, 384, 0), (4544, 256, 384, 0)]:
+        x = torch.randn(rows, K, generator=g).to(DEV)
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+        b = torch.randn(N, generator=g).to(DEV)
+        w_hi, w_lo, sc = pkg.cabi.split_f16_pair(w)
+        pkg.cabi.lib().sdetr_gemm_f16x3_set_cluster(0)
+        y0 = pkg.cabi.gemm_f16x3_pre(x, w_hi, w_lo, sc, b, act)
+        pkg.cabi.lib().sdetr_gemm_f16x3_set_cluster(1)
+        y1 = pkg.cabi.gemm_f16x3_pre(x, w_hi, w_lo, sc, b, act)
+        assert torch.equal(y0, y1), (rows, K, N)
+        for _ in range(3):
+            assert torch.equal(pkg.cabi.gemm_f16x3_pre(x, w_hi, w_lo, sc, b, act), y1)
     # range: tiny, huge and mixed-magnitude activations; relative error of the result stays fp32-class
     K, N = 256, 256
     w = (torch.randn(N, K, generator=g) / 16).to(DEV)
