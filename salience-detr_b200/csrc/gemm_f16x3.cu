@@ -515,7 +515,9 @@ __global__ void split_f16_pair_kernel(const float *__restrict__ w, int64_t n, fl
 
 using namespace sdetr;
 
-static std::atomic<int> g_f16_cluster{1};  // 1: clusters of two CTAs share the weight k-blocks by TMA multicast (M >= 2 panels)
+static std::atomic<int> g_f16_cluster{0};  // 1: clusters of two CTAs share the weight k-blocks by TMA multicast (M >= 2 panels).
+// Measured (profiles/r2_gemm_shapes_f16x3_cluster.txt): bit-identical, but 3-12 % SLOWER on every shape -- the stage-by-stage
+// lockstep of the two CTAs costs more than the halved weight ingest saves -- so off by default.
 static std::atomic<int> g_f16_as{0};  // 1: K <= 256 goes to the activation-stationary kernel (measured: +4 % on FFN-1, -3 % on the 6-layer value projection -- profiles/r2_gemm_shapes_f16x3_as.txt -- so off by default)
 
 extern "C" int sdetr_gemm_f16x3_set_cluster(int enable) {

@@ -35,7 +35,7 @@ def _restore_global_state(pkg):
     pkg.gemm.MODE = mode
     pkg.gemm.OWN_KERNEL = os.environ.get("SDETR_GEMM_KERNEL", "f16x3")
     pkg.cabi.lib().sdetr_gemm_f16x3_set_as(0)
-    pkg.cabi.lib().sdetr_gemm_f16x3_set_cluster(1)
+    pkg.cabi.lib().sdetr_gemm_f16x3_set_cluster(0)
     pkg.cabi.set_option("msda_smem_broadcast", 1)
     pkg.cabi.lib().sdetr_gemm_set_variant(0)
     pkg.cabi.lib().sdetr_gemm_set_variant(3)
