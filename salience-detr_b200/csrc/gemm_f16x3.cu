@@ -82,7 +82,12 @@ struct HGemmParams {
     int64_t ldc;
     int M, N, K, act, use_tma_store;
     float out_scale;  // 1 / (kActScale * weight scale), a power of two
+    long long *dbg;   // optional clock64() trace of CTA 0: [event][index < 256] (sdetr_gemm_f16x3_set_trace, tools/gemm_trace2.py)
 };
+#define HTRACE(ev, idx)                                                                              \
+    do {                                                                                             \
+        if (p.dbg && blockIdx.x == 0 && (idx) < 256) p.dbg[(ev) * 256 + (idx)] = clock64();          \
+    } while (0)
 
 // CL = true: clusters of TWO CTAs along M.  Both CTAs of a pair work on the same 128-column tile of the output for two
 // adjacent 128-row panels, so they need the same weight k-blocks: rank 0 fetches W_hi, rank 1 fetches W_lo, and each TMA
@@ -145,6 +150,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 for (int kb = 0; kb < nk; ++kb, ++it) {
                     const int s = it % kHStages;
                     mbar_wait(empty + s, ((it / kHStages) & 1) ^ 1);  // CL: released by the MMA warps of BOTH CTAs
+                    HTRACE(0, it);  // producer: stage free, issuing TMA
                     uint8_t *st = smem + s * kHStageBytes;
                     mbar_expect_tx(tma_full + s, 4 * kHBox);          // own A boxes + W_hi + W_lo (CL: one of them from the peer)
                     tma_load_2d(&map_a, tma_full + s, st, kb * kHK, m0);
@@ -172,6 +178,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 for (int kb = 0; kb < nk; ++kb, ++it) {
                     const int s = it % kHStages;
                     mbar_wait(conv_full + s, (it / kHStages) & 1);
+                    HTRACE(3, it);  // MMA: operands ready, issuing
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t base = smem_u32(smem + s * kHStageBytes);
                     const uint32_t a_hi = tmem_base + 256u + 64u * (uint32_t)s, a_lo = a_hi + 32u;
@@ -196,6 +203,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             for (int kb = 0; kb < nk; ++kb, ++it) {
                 const int s = it % kHStages;
                 mbar_wait(tma_full + s, (it / kHStages) & 1);
+                if (threadIdx.x == 128) HTRACE(1, it);  // converter: TMA landed
                 const uint8_t *arow = smem + s * kHStageBytes + half * kHBox + r_in * 128;
                 uint32_t hi[16], lo[16];
 #pragma unroll
@@ -215,18 +223,27 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 mbar_arrive(conv_full + s);
+                if (threadIdx.x == 128) HTRACE(2, it);  // converter: done
             }
         }
     } else if (warp >= 12) {
-        // ===== epilogue: TMEM -> registers -> * 2^-(4+s) + bias -> swizzled box -> TMA store (or direct stores) =====
+        // ===== epilogue: TMEM -> registers -> * 2^-(4+s) + bias -> WARP-PRIVATE transpose box -> coalesced 128-bit global stores =====
+        // Round-2 trace (tools/gemm_trace2.py, profiles/r2_gemm_f16x3_trace.txt): with the TMA-store epilogue of the 3xTF32
+        // kernel (two shared 16 KB boxes, two named barriers and a bulk-group wait per 32-column block) a tile's epilogue took
+        // ~6800 clk against ~4800 clk of main loop at K = 256, so the MMA warp waited for a free accumulator at every tile
+        // boundary.  Here each of the four epilogue warps owns its 32 rows end to end: a thread stages its row segment
+        // (32 floats) into a private, XOR-swizzled 4 KB box, __syncwarp, and the warp writes the box out as 8 instructions of
+        // four full 128-byte row segments each -- no CTA-level barrier, no store-engine drain on the critical path.
         const int q = warp & 3, r_in = q * 32 + lane;
         const bool elected = threadIdx.x == 12 * 32;
         const float sc = p.out_scale;
-        uint32_t tc = 0, box_it = 0;
+        uint8_t *wbox = boxes + (warp - 12) * 4096;
+        uint32_t tc = 0;
         for (int tile = first; tile < tiles; tile += step, ++tc) {
             const int m0 = tile_m0(tile), n0 = tile_n0(tile);
             const uint32_t buf = tc & 1;
             mbar_wait(acc_full + buf, (tc >> 1) & 1);
+            if (elected) HTRACE(5, tc);  // epilogue: accumulator complete
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = m0 + r_in;
 #pragma unroll 1
@@ -239,11 +256,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
                 const int col0 = n0 + c * 32;
                 if (col0 >= p.N) continue;  // uniform across the CTA
-                if (p.use_tma_store) {
-                    // the two staging boxes alternate per ISSUED store (a skipped column block must not advance the counter)
-                    uint8_t *box = boxes + (box_it++ & 1) * kHBox;
-                    if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // box free again
-                    named_bar_sync(1, 128);
+                if (p.use_tma_store) {      // (name kept: "C rows are 16-byte aligned" -> vector path)
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         float4 o = make_float4(__uint_as_float(r[j]) * sc, __uint_as_float(r[j + 1]) * sc,
@@ -256,14 +269,26 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             if (col0 + j + 1 < p.N) o.y += __ldg(p.bias + col0 + j + 1);
                             if (col0 + j + 2 < p.N) o.z += __ldg(p.bias + col0 + j + 2);
                         }
-                        *reinterpret_cast<float4 *>(box + r_in * 128 + (((j >> 2) ^ (r_in & 7)) << 4)) = o;
+                        *reinterpret_cast<float4 *>(wbox + lane * 128 + (((j >> 2) ^ (lane & 7)) << 4)) = o;
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    named_bar_sync(1, 128);
-                    if (elected) {
-                        tma_store_2d(&map_c, box, col0, m0);  // clips rows >= M and columns >= N
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    __syncwarp();
+                    const int ch = lane & 7, gcol = col0 + 4 * ch;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = 4 * i + (lane >> 3), grow = m0 + q * 32 + rr;
+                        const float4 v = *reinterpret_cast<const float4 *>(wbox + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                        if (grow < p.M) {
+                            float *dst = p.C + (int64_t)grow * p.ldc + gcol;
+                            if (gcol + 3 < p.N) {
+                                st_stream_f4(dst, v);
+                            } else {
+                                if (gcol < p.N) dst[0] = v.x;
+                                if (gcol + 1 < p.N) dst[1] = v.y;
+                                if (gcol + 2 < p.N) dst[2] = v.z;
+                            }
+                        }
                     }
+                    __syncwarp();  // the box is rewritten by the next column block
                 } else if (row < p.M) {
                     float *crow = p.C + (int64_t)row * p.ldc;
 #pragma unroll
@@ -271,8 +296,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         if (col0 + j < p.N) crow[col0 + j] = __uint_as_float(r[j]) * sc + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
                 }
             }
+            if (elected) HTRACE(6, tc);  // epilogue: tile written
         }
-        if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -518,10 +543,16 @@ using namespace sdetr;
 static std::atomic<int> g_f16_cluster{0};  // 1: clusters of two CTAs share the weight k-blocks by TMA multicast (M >= 2 panels).
 // Measured (profiles/r2_gemm_shapes_f16x3_cluster.txt): bit-identical, but 3-12 % SLOWER on every shape -- the stage-by-stage
 // lockstep of the two CTAs costs more than the halved weight ingest saves -- so off by default.
+static std::atomic<long long *> g_f16_dbg{nullptr};
 static std::atomic<int> g_f16_as{0};  // 1: K <= 256 goes to the activation-stationary kernel (measured: +4 % on FFN-1, -3 % on the 6-layer value projection -- profiles/r2_gemm_shapes_f16x3_as.txt -- so off by default)
 
 extern "C" int sdetr_gemm_f16x3_set_cluster(int enable) {
     g_f16_cluster = enable ? 1 : 0;
+    return SDETR_OK;
+}
+
+extern "C" int sdetr_gemm_f16x3_set_trace(long long *device_buffer /* 7 * 256 int64, or NULL */) {
+    g_f16_dbg = device_buffer;
     return SDETR_OK;
 }
 
@@ -578,7 +609,7 @@ extern "C" int sdetr_gemm_f16x3_pre(const float *A, int64_t lda, const void *W_h
     SDETR_OPT_IN_SMEM(once_cl, gemm_f16x3_kernel<true>, kHSmem, "gemm_f16x3_pre");
     SDETR_OPT_IN_SMEM(once_as, gemm_f16x3_as_kernel, kAsSmem, "gemm_f16x3_pre");
     const int sms = sm_count();
-    HGemmParams p{bias, C, ldc, M, N, K, act, use_tma_store, 1.f / (kActScale * w_scale)};
+    HGemmParams p{bias, C, ldc, M, N, K, act, use_tma_store, 1.f / (kActScale * w_scale), g_f16_dbg.load()};
     const int n_tiles = (N + kHN - 1) / kHN, m_tiles = (M + kHM - 1) / kHM;
     const int group = (g_f16_as.load() && K <= kMaxKb * kHK) ? pick_group(m_tiles, n_tiles, sms) : 1;
     if (group >= 2) {  // a one-tile unit re-uses nothing: the streaming kernel pipelines it better
