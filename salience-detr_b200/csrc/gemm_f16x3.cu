@@ -227,18 +227,13 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
         }
     } else if (warp >= 12) {
-        // ===== epilogue: TMEM -> registers -> * 2^-(4+s) + bias -> WARP-PRIVATE transpose box -> coalesced 128-bit global stores =====
-        // Round-2 trace (tools/gemm_trace2.py, profiles/r2_gemm_f16x3_trace.txt): with the TMA-store epilogue of the 3xTF32
-        // kernel (two shared 16 KB boxes, two named barriers and a bulk-group wait per 32-column block) a tile's epilogue took
-        // ~6800 clk against ~4800 clk of main loop at K = 256, so the MMA warp waited for a free accumulator at every tile
-        // boundary.  Here each of the four epilogue warps owns its 32 rows end to end: a thread stages its row segment
-        // (32 floats) into a private, XOR-swizzled 4 KB box, __syncwarp, and the warp writes the box out as 8 instructions of
-        // four full 128-byte row segments each -- no CTA-level barrier, no store-engine drain on the critical path.
+        // ===== epilogue: TMEM -> registers -> * 2^-(4+s) + bias -> swizzled box -> TMA store (or direct stores) =====
+        // (a warp-private transpose box + coalesced 128-bit global stores instead of the shared boxes / TMA stores was measured
+        //  13 % slower over the projection shapes, profiles/r2_gemm_shapes_f16x3_warp_epilogue.txt: kept out)
         const int q = warp & 3, r_in = q * 32 + lane;
         const bool elected = threadIdx.x == 12 * 32;
         const float sc = p.out_scale;
-        uint8_t *wbox = boxes + (warp - 12) * 4096;
-        uint32_t tc = 0;
+        uint32_t tc = 0, box_it = 0;
         for (int tile = first; tile < tiles; tile += step, ++tc) {
             const int m0 = tile_m0(tile), n0 = tile_n0(tile);
             const uint32_t buf = tc & 1;
@@ -256,7 +251,11 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
                 const int col0 = n0 + c * 32;
                 if (col0 >= p.N) continue;  // uniform across the CTA
-                if (p.use_tma_store) {      // (name kept: "C rows are 16-byte aligned" -> vector path)
+                if (p.use_tma_store) {
+                    // the two staging boxes alternate per ISSUED store (a skipped column block must not advance the counter)
+                    uint8_t *box = boxes + (box_it++ & 1) * kHBox;
+                    if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // box free again
+                    named_bar_sync(1, 128);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         float4 o = make_float4(__uint_as_float(r[j]) * sc, __uint_as_float(r[j + 1]) * sc,
@@ -269,26 +268,14 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             if (col0 + j + 1 < p.N) o.y += __ldg(p.bias + col0 + j + 1);
                             if (col0 + j + 2 < p.N) o.z += __ldg(p.bias + col0 + j + 2);
                         }
-                        *reinterpret_cast<float4 *>(wbox + lane * 128 + (((j >> 2) ^ (lane & 7)) << 4)) = o;
+                        *reinterpret_cast<float4 *>(box + r_in * 128 + (((j >> 2) ^ (r_in & 7)) << 4)) = o;
                     }
-                    __syncwarp();
-                    const int ch = lane & 7, gcol = col0 + 4 * ch;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int rr = 4 * i + (lane >> 3), grow = m0 + q * 32 + rr;
-                        const float4 v = *reinterpret_cast<const float4 *>(wbox + rr * 128 + ((ch ^ (rr & 7)) << 4));
-                        if (grow < p.M) {
-                            float *dst = p.C + (int64_t)grow * p.ldc + gcol;
-                            if (gcol + 3 < p.N) {
-                                st_stream_f4(dst, v);
-                            } else {
-                                if (gcol < p.N) dst[0] = v.x;
-                                if (gcol + 1 < p.N) dst[1] = v.y;
-                                if (gcol + 2 < p.N) dst[2] = v.z;
-                            }
-                        }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    named_bar_sync(1, 128);
+                    if (elected) {
+                        tma_store_2d(&map_c, box, col0, m0);  // clips rows >= M and columns >= N
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
-                    __syncwarp();  // the box is rewritten by the next column block
                 } else if (row < p.M) {
                     float *crow = p.C + (int64_t)row * p.ldc;
 #pragma unroll
@@ -296,8 +283,9 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         if (col0 + j < p.N) crow[col0 + j] = __uint_as_float(r[j]) * sc + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
                 }
             }
-            if (elected) HTRACE(6, tc);  // epilogue: tile written
+            if (elected) HTRACE(6, tc);  // epilogue: tile handed to the store engine
         }
+        if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
