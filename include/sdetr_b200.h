@@ -363,7 +363,8 @@ int sdetr_gemm_f16x3_pre(const float *A, int64_t lda, const void *W_hi, const vo
 /* benchmarking knob: 0 (default) = always the streaming kernel, 1 = K <= 256 and >= 2 output tiles per work unit use the
  * activation-stationary kernel (the split activation panel stays in tensor memory across the unit's output tiles) */
 int sdetr_gemm_f16x3_set_as(int enable);
-/* debugging aid: when set, CTA 0 of every streaming sdetr_gemm_f16x3_pre launch records clock64() per pipeline event */
+/* debugging aid: when set, CTA 0 of every streaming sdetr_gemm_f16x3_pre launch records clock64() per pipeline event
+ * (device_buffer: 10 x 256 int64) */
 int sdetr_gemm_f16x3_set_trace(long long *device_buffer);
 /* benchmarking knob: 1 = clusters of two CTAs (adjacent 128-row panels, same output columns) share the weight k-blocks by
  * TMA multicast (measured slower, off by default); 0 (default) = independent CTAs */

@@ -41,7 +41,7 @@ constexpr int kHBox = 128 * 32 * 4;               // 16 KB: one A box (128 rows 
 constexpr int kHStageBytes = 4 * kHBox;           // A box 0, A box 1, W_hi, W_lo
 constexpr int kHRingBytes = kHStages * kHStageBytes;  // 192 KB
 constexpr int kHOutBoxes = 2 * kHBox;             // two 128x32 fp32 staging boxes for the TMA stores
-constexpr int kHSmem = kHRingBytes + kHOutBoxes + 1024 + 256;
+constexpr int kHSmem = kHRingBytes + kHOutBoxes + 1024 /* alignment */ + 256 /* barriers */ + 1024 /* bias slices */;
 constexpr int kHThreads = 512;
 constexpr int kHConvWarps = 8;
 constexpr float kActScale = 16.f;                 // activation pre-scale (exact), see header comment
@@ -82,7 +82,7 @@ struct HGemmParams {
     int64_t ldc;
     int M, N, K, act, use_tma_store;
     float out_scale;  // 1 / (kActScale * weight scale), a power of two
-    long long *dbg;   // optional clock64() trace of CTA 0: [event][index < 256] (sdetr_gemm_f16x3_set_trace, tools/gemm_trace2.py)
+    long long *dbg;   // optional clock64() trace of CTA 0: [event][index < 256] (sdetr_gemm_f16x3_set_trace, tools/gemm_trace2.py; 10 events)
 };
 #define HTRACE(ev, idx)                                                                              \
     do {                                                                                             \
@@ -107,6 +107,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint64_t *tma_full = bars, *conv_full = bars + kHStages, *empty = bars + 2 * kHStages;
     uint64_t *acc_full = bars + 3 * kHStages, *acc_empty = acc_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    float *sbias = reinterpret_cast<float *>(smem + kHRingBytes + kHOutBoxes + 256);  // 2 x 128 floats: this tile's bias slice
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nk = p.K / kHK;
@@ -234,17 +235,26 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const bool elected = threadIdx.x == 12 * 32;
         const float sc = p.out_scale;
         uint32_t tc = 0, box_it = 0;
+        const int et = threadIdx.x - 12 * 32;  // 0..127 within the epilogue group
         for (int tile = first; tile < tiles; tile += step, ++tc) {
             const int m0 = tile_m0(tile), n0 = tile_n0(tile);
             const uint32_t buf = tc & 1;
+            // The tile's bias slice goes through shared memory: fetched while the accumulator is still being computed.  (Trace,
+            // profiles/r2_gemm_f16x3_trace_epilogue_detail.txt: eight dependent global bias loads per 32-column block made the
+            // "write box" phase 1000-2400 clk and the whole epilogue ~7000 clk per tile against ~4800 clk of main loop at K = 256.)
+            const float bval = (p.bias && n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.f;
             mbar_wait(acc_full + buf, (tc >> 1) & 1);
             if (elected) HTRACE(5, tc);  // epilogue: accumulator complete
+            float *tb = sbias + buf * 128;
+            tb[et] = bval;
+            named_bar_sync(1, 128);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = m0 + r_in;
 #pragma unroll 1
             for (int c = 0; c < kHN / 32; ++c) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128u + (uint32_t)(c * 32), r);
+                if (elected) HTRACE(7, tc * 4 + c);  // epilogue detail: TMEM load done
                 if (c == kHN / 32 - 1) {  // last read of this accumulator: hand it back to the MMA warp
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive(acc_empty + buf);
@@ -256,22 +266,17 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     uint8_t *box = boxes + (box_it++ & 1) * kHBox;
                     if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // box free again
                     named_bar_sync(1, 128);
+                    if (elected) HTRACE(8, tc * 4 + c);  // box free + barrier
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        float4 o = make_float4(__uint_as_float(r[j]) * sc, __uint_as_float(r[j + 1]) * sc,
-                                               __uint_as_float(r[j + 2]) * sc, __uint_as_float(r[j + 3]) * sc);
-                        if (p.bias && col0 + j + 3 < p.N) {
-                            const float4 bv = ldg_f4(p.bias + col0 + j);
-                            o.x += bv.x, o.y += bv.y, o.z += bv.z, o.w += bv.w;
-                        } else if (p.bias) {
-                            if (col0 + j < p.N) o.x += __ldg(p.bias + col0 + j);
-                            if (col0 + j + 1 < p.N) o.y += __ldg(p.bias + col0 + j + 1);
-                            if (col0 + j + 2 < p.N) o.z += __ldg(p.bias + col0 + j + 2);
-                        }
+                        const float4 bv = *reinterpret_cast<const float4 *>(tb + c * 32 + j);  // zero beyond N / without bias
+                        const float4 o = make_float4(fmaf(__uint_as_float(r[j]), sc, bv.x), fmaf(__uint_as_float(r[j + 1]), sc, bv.y),
+                                                     fmaf(__uint_as_float(r[j + 2]), sc, bv.z), fmaf(__uint_as_float(r[j + 3]), sc, bv.w));
                         *reinterpret_cast<float4 *>(box + r_in * 128 + (((j >> 2) ^ (r_in & 7)) << 4)) = o;
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     named_bar_sync(1, 128);
+                    if (elected) HTRACE(9, tc * 4 + c);  // box written + barrier
                     if (elected) {
                         tma_store_2d(&map_c, box, col0, m0);  // clips rows >= M and columns >= N
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -280,7 +285,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     float *crow = p.C + (int64_t)row * p.ldc;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (col0 + j < p.N) crow[col0 + j] = __uint_as_float(r[j]) * sc + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
+                        if (col0 + j < p.N) crow[col0 + j] = fmaf(__uint_as_float(r[j]), sc, tb[c * 32 + j]);
                 }
             }
             if (elected) HTRACE(6, tc);  // epilogue: tile handed to the store engine
@@ -539,7 +544,7 @@ extern "C" int sdetr_gemm_f16x3_set_cluster(int enable) {
     return SDETR_OK;
 }
 
-extern "C" int sdetr_gemm_f16x3_set_trace(long long *device_buffer /* 7 * 256 int64, or NULL */) {
+extern "C" int sdetr_gemm_f16x3_set_trace(long long *device_buffer /* 10 * 256 int64, or NULL */) {
     g_f16_dbg = device_buffer;
     return SDETR_OK;
 }

@@ -11,12 +11,12 @@ x = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) / K ** 0.5;
 hi, lo, sc = pkg.cabi.split_f16_pair(w)
 for _ in range(3):
     pkg.cabi.gemm_f16x3_pre(x, hi, lo, sc, b)
-buf = torch.zeros(7 * 256, dtype=torch.int64, device=dev)
+buf = torch.zeros(10 * 256, dtype=torch.int64, device=dev)
 pkg.cabi.lib().sdetr_gemm_f16x3_set_trace(buf.data_ptr())
 pkg.cabi.gemm_f16x3_pre(x, hi, lo, sc, b)
 torch.cuda.synchronize()
 pkg.cabi.lib().sdetr_gemm_f16x3_set_trace(None)
-t = buf.view(7, 256).cpu()
+t = buf.view(10, 256).cpu()
 nk = K // 64
 t0 = int(t[0, 0])
 names = ["tma_issue", "landed", "conv_done", "mma_issue"]
@@ -32,3 +32,7 @@ print("tile  acc_complete  epilogue_done  (duration)")
 for i in range(nt):
     a, e = int(t[5, i]) - t0, int(t[6, i]) - t0
     print(f"{i:3d}  {a:10d} {e:10d}  {e - a:8d}")
+print("epilogue detail per 32-column block: after TMEM load | after box-free wait + barrier | after box write + barrier   (clk since accumulator complete)")
+for i in range(min(nt, 8)):
+    base = int(t[5, i])
+    print(f"tile {i}: " + "  ".join(f"[{int(t[7, 4*i+c]) - base:6d} {int(t[8, 4*i+c]) - base:6d} {int(t[9, 4*i+c]) - base:6d}]" for c in range(4)))
