@@ -363,6 +363,9 @@ int sdetr_gemm_f16x3_pre(const float *A, int64_t lda, const void *W_hi, const vo
 /* benchmarking knob: 0 (default) = always the streaming kernel, 1 = K <= 256 and >= 2 output tiles per work unit use the
  * activation-stationary kernel (the split activation panel stays in tensor memory across the unit's output tiles) */
 int sdetr_gemm_f16x3_set_as(int enable);
+/* benchmarking knob, streaming kernel epilogue: 0 (default) = two shared 16 KB boxes + TMA bulk stores, 1 = warp-private
+ * transpose boxes + coalesced 128-bit global stores (no CTA-level barrier in the epilogue) */
+int sdetr_gemm_f16x3_set_epilogue(int variant);
 /* debugging aid: when set, CTA 0 of every streaming sdetr_gemm_f16x3_pre launch records clock64() per pipeline event
  * (device_buffer: 10 x 256 int64) */
 int sdetr_gemm_f16x3_set_trace(long long *device_buffer);

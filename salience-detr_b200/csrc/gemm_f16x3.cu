@@ -82,6 +82,7 @@ struct HGemmParams {
     int64_t ldc;
     int M, N, K, act, use_tma_store;
     float out_scale;  // 1 / (kActScale * weight scale), a power of two
+    int epilogue;     // streaming kernel: 0 = shared boxes + TMA stores, 1 = warp-private boxes + coalesced 128-bit global stores
     long long *dbg;   // optional clock64() trace of CTA 0: [event][index < 256] (sdetr_gemm_f16x3_set_trace, tools/gemm_trace2.py; 10 events)
 };
 #define HTRACE(ev, idx)                                                                              \
@@ -235,6 +236,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const bool elected = threadIdx.x == 12 * 32;
         const float sc = p.out_scale;
         uint32_t tc = 0, box_it = 0;
+        uint8_t *wbox = boxes + (warp - 12) * 4096;  // epilogue variant 1: this warp's private 32-row x 128-byte box
         const int et = threadIdx.x - 12 * 32;  // 0..127 within the epilogue group
         for (int tile = first; tile < tiles; tile += step, ++tc) {
             const int m0 = tile_m0(tile), n0 = tile_n0(tile);
@@ -261,7 +263,33 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
                 const int col0 = n0 + c * 32;
                 if (col0 >= p.N) continue;  // uniform across the CTA
-                if (p.use_tma_store) {
+                if (p.use_tma_store && p.epilogue == 1) {  // warp-private transpose box + coalesced 128-bit global stores
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 bv = *reinterpret_cast<const float4 *>(tb + c * 32 + j);
+                        const float4 o = make_float4(fmaf(__uint_as_float(r[j]), sc, bv.x), fmaf(__uint_as_float(r[j + 1]), sc, bv.y),
+                                                     fmaf(__uint_as_float(r[j + 2]), sc, bv.z), fmaf(__uint_as_float(r[j + 3]), sc, bv.w));
+                        *reinterpret_cast<float4 *>(wbox + lane * 128 + (((j >> 2) ^ (lane & 7)) << 4)) = o;
+                    }
+                    __syncwarp();
+                    const int ch = lane & 7, gcol = col0 + 4 * ch;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = 4 * i + (lane >> 3), grow = m0 + q * 32 + rr;
+                        const float4 v = *reinterpret_cast<const float4 *>(wbox + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                        if (grow < p.M) {
+                            float *dst = p.C + (int64_t)grow * p.ldc + gcol;
+                            if (gcol + 3 < p.N) {
+                                st_stream_f4(dst, v);
+                            } else {
+                                if (gcol < p.N) dst[0] = v.x;
+                                if (gcol + 1 < p.N) dst[1] = v.y;
+                                if (gcol + 2 < p.N) dst[2] = v.z;
+                            }
+                        }
+                    }
+                    __syncwarp();  // the box is rewritten by the next column block
+                } else if (p.use_tma_store) {
                     // the two staging boxes alternate per ISSUED store (a skipped column block must not advance the counter)
                     uint8_t *box = boxes + (box_it++ & 1) * kHBox;
                     if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // box free again
@@ -537,6 +565,7 @@ static std::atomic<int> g_f16_cluster{0};  // 1: clusters of two CTAs share the 
 // Measured (profiles/r2_gemm_shapes_f16x3_cluster.txt): bit-identical, but 3-12 % SLOWER on every shape -- the stage-by-stage
 // lockstep of the two CTAs costs more than the halved weight ingest saves -- so off by default.
 static std::atomic<long long *> g_f16_dbg{nullptr};
+static std::atomic<int> g_f16_epi{0};
 static std::atomic<int> g_f16_as{0};  // 1: K <= 256 goes to the activation-stationary kernel (measured: +4 % on FFN-1, -3 % on the 6-layer value projection -- profiles/r2_gemm_shapes_f16x3_as.txt -- so off by default)
 
 extern "C" int sdetr_gemm_f16x3_set_cluster(int enable) {
@@ -546,6 +575,12 @@ extern "C" int sdetr_gemm_f16x3_set_cluster(int enable) {
 
 extern "C" int sdetr_gemm_f16x3_set_trace(long long *device_buffer /* 10 * 256 int64, or NULL */) {
     g_f16_dbg = device_buffer;
+    return SDETR_OK;
+}
+
+extern "C" int sdetr_gemm_f16x3_set_epilogue(int variant) {
+    SDETR_REQUIRE(variant == 0 || variant == 1, SDETR_ERR_INVALID_ARG, "gemm_f16x3_set_epilogue: 0 or 1");
+    g_f16_epi = variant;
     return SDETR_OK;
 }
 
@@ -602,7 +637,7 @@ extern "C" int sdetr_gemm_f16x3_pre(const float *A, int64_t lda, const void *W_h
     SDETR_OPT_IN_SMEM(once_cl, gemm_f16x3_kernel<true>, kHSmem, "gemm_f16x3_pre");
     SDETR_OPT_IN_SMEM(once_as, gemm_f16x3_as_kernel, kAsSmem, "gemm_f16x3_pre");
     const int sms = sm_count();
-    HGemmParams p{bias, C, ldc, M, N, K, act, use_tma_store, 1.f / (kActScale * w_scale), g_f16_dbg.load()};
+    HGemmParams p{bias, C, ldc, M, N, K, act, use_tma_store, 1.f / (kActScale * w_scale), g_f16_epi.load(), g_f16_dbg.load()};
     const int n_tiles = (N + kHN - 1) / kHN, m_tiles = (M + kHM - 1) / kHM;
     const int group = (g_f16_as.load() && K <= kMaxKb * kHK) ? pick_group(m_tiles, n_tiles, sms) : 1;
     if (group >= 2) {  // a one-tile unit re-uses nothing: the streaming kernel pipelines it better

@@ -36,6 +36,7 @@ def _restore_global_state(pkg):
     pkg.gemm.OWN_KERNEL = os.environ.get("SDETR_GEMM_KERNEL", "f16x3")
     pkg.cabi.lib().sdetr_gemm_f16x3_set_as(0)
     pkg.cabi.lib().sdetr_gemm_f16x3_set_cluster(0)
+    pkg.cabi.lib().sdetr_gemm_f16x3_set_epilogue(0)
     pkg.cabi.set_option("msda_smem_broadcast", 1)
     pkg.cabi.lib().sdetr_gemm_set_variant(0)
     pkg.cabi.lib().sdetr_gemm_set_variant(3)
@@ -617,6 +618,12 @@ def test_gemm_f16x3_accuracy_and_range(pkg):
         pkg.cabi.lib().sdetr_gemm_f16x3_set_cluster(1)
         y1 = pkg.cabi.gemm_f16x3_pre(x, w_hi, w_lo, sc, b, act)
         assert torch.equal(y0, y1), (rows, K, N)
+        pkg.cabi.lib().sdetr_gemm_f16x3_set_cluster(0)
+        pkg.cabi.lib().sdetr_gemm_f16x3_set_epilogue(1)   # warp-private store epilogue: same values, different store path
+        y2 = pkg.cabi.gemm_f16x3_pre(x, w_hi, w_lo, sc, b, act)
+        pkg.cabi.lib().sdetr_gemm_f16x3_set_epilogue(0)
+        assert torch.equal(y0, y2), (rows, K, N)
+        pkg.cabi.lib().sdetr_gemm_f16x3_set_cluster(1)
         for _ in range(3):
             assert torch.equal(pkg.cabi.gemm_f16x3_pre(x, w_hi, w_lo, sc, b, act), y1)
     # range: tiny, huge and mixed-magnitude activations; relative error of the result stays fp32-class
