@@ -65,6 +65,7 @@ SIGNATURES = {
     "sdetr_gemm_f16x3_set_as": (_i, [_i]),
     "sdetr_gemm_f16x3_set_cluster": (_i, [_i]),
     "sdetr_gemm_f16x3_set_epilogue": (_i, [_i]),
+    "sdetr_gemm_f16x3_set_epilogue_warps": (_i, [_i]),
     "sdetr_gemm_f16x3_set_trace": (_i, [_vp]),
     "sdetr_gemm_f16x3_pre": (_i, [_vp, _i64, _vp, _vp, _f, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
     "sdetr_flatten_tokens": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),

@@ -96,8 +96,12 @@ struct HGemmParams {
 // L2 -> SM fabric: ncu shows ~750 MB through the crossbar at 7.4-8.8 TB/s for both FFN GEMMs,
 // profiles/r2_gemm_f16x3_ffn{1,2}_ncu_full.txt).  A ring stage is refilled only when the MMAs of BOTH CTAs have released it
 // (tcgen05.commit multicast onto both `empty` barriers, count 2).
-template <bool CL>
-__global__ void __launch_bounds__(kHThreads, 1)
+// EW = epilogue warps: 4 (warps 12..15, all four 32-column blocks of a tile, two alternating store boxes) or 8 (warps 12..19:
+// group 0 = column blocks 0,1, group 1 = column blocks 2,3, one store box per group).  The trace of the EW = 4 kernel at K = 256
+// (profiles/r2_gemm_f16x3_trace_epilogue_detail2.txt) shows ~6500 clk of epilogue per tile against ~4600 clk of main loop: the
+// MMA warp waits for a drained accumulator at every tile boundary; two groups halve the epilogue's critical path.
+template <bool CL, int EW>
+__global__ void __launch_bounds__(384 + 32 * EW, 1)
 gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_whi,
                   const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_c,
                   const HGemmParams p) {
@@ -129,7 +133,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(acc_full + b, 1);
-            mbar_init(acc_empty + b, 128);
+            mbar_init(acc_empty + b, 32 * EW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -233,31 +237,35 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // (a warp-private transpose box + coalesced 128-bit global stores instead of the shared boxes / TMA stores was measured
         //  13 % slower over the projection shapes, profiles/r2_gemm_shapes_f16x3_warp_epilogue.txt: kept out)
         const int q = warp & 3, r_in = q * 32 + lane;
-        const bool elected = threadIdx.x == 12 * 32;
+        const int grp = (warp - 12) >> 2;                                  // 0 (EW = 4) or 0 / 1 (EW = 8)
+        const bool elected = threadIdx.x == (12 + 4 * grp) * 32;           // one store-issuing thread per group
+        const bool tracer = threadIdx.x == 12 * 32;
+        constexpr int kBlocksPerGroup = (kHN / 32) / (EW / 4);
+        const int c_begin = grp * kBlocksPerGroup, c_end = c_begin + kBlocksPerGroup;
         const float sc = p.out_scale;
         uint32_t tc = 0, box_it = 0;
         uint8_t *wbox = boxes + (warp - 12) * 4096;  // epilogue variant 1: this warp's private 32-row x 128-byte box
-        const int et = threadIdx.x - 12 * 32;  // 0..127 within the epilogue group
+        const int et = threadIdx.x - 12 * 32;        // 0 .. 32 * EW - 1 within the epilogue warps
         for (int tile = first; tile < tiles; tile += step, ++tc) {
             const int m0 = tile_m0(tile), n0 = tile_n0(tile);
             const uint32_t buf = tc & 1;
             // The tile's bias slice goes through shared memory: fetched while the accumulator is still being computed.  (Trace,
             // profiles/r2_gemm_f16x3_trace_epilogue_detail.txt: eight dependent global bias loads per 32-column block made the
             // "write box" phase 1000-2400 clk and the whole epilogue ~7000 clk per tile against ~4800 clk of main loop at K = 256.)
-            const float bval = (p.bias && n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.f;
+            const float bval = (et < 128 && p.bias && n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.f;
             mbar_wait(acc_full + buf, (tc >> 1) & 1);
-            if (elected) HTRACE(5, tc);  // epilogue: accumulator complete
+            if (tracer) HTRACE(5, tc);  // epilogue: accumulator complete
             float *tb = sbias + buf * 128;
-            tb[et] = bval;
-            named_bar_sync(1, 128);
+            if (et < 128) tb[et] = bval;
+            named_bar_sync(3, 32 * EW);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = m0 + r_in;
 #pragma unroll 1
-            for (int c = 0; c < kHN / 32; ++c) {
+            for (int c = c_begin; c < c_end; ++c) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128u + (uint32_t)(c * 32), r);
-                if (elected) HTRACE(7, tc * 4 + c);  // epilogue detail: TMEM load done
-                if (c == kHN / 32 - 1) {  // last read of this accumulator: hand it back to the MMA warp
+                if (tracer) HTRACE(7, tc * 4 + c);  // epilogue detail: TMEM load done
+                if (c == c_end - 1) {  // this warp's last read of the accumulator: hand it back to the MMA warp
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive(acc_empty + buf);
                 }
@@ -291,10 +299,13 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     __syncwarp();  // the box is rewritten by the next column block
                 } else if (p.use_tma_store) {
                     // the two staging boxes alternate per ISSUED store (a skipped column block must not advance the counter)
-                    uint8_t *box = boxes + (box_it++ & 1) * kHBox;
-                    if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // box free again
-                    named_bar_sync(1, 128);
-                    if (elected) HTRACE(8, tc * 4 + c);  // box free + barrier
+                    uint8_t *box = boxes + (EW == 8 ? grp : (int)(box_it++ & 1)) * kHBox;
+                    if (elected) {  // box free again (EW = 8: one box per group, so its previous store must have been read out)
+                        if (EW == 8) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    }
+                    named_bar_sync(1 + grp, 128);
+                    if (tracer) HTRACE(8, tc * 4 + c);  // box free + barrier
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 bv = *reinterpret_cast<const float4 *>(tb + c * 32 + j);  // zero beyond N / without bias
@@ -303,8 +314,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         *reinterpret_cast<float4 *>(box + r_in * 128 + (((j >> 2) ^ (r_in & 7)) << 4)) = o;
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    named_bar_sync(1, 128);
-                    if (elected) HTRACE(9, tc * 4 + c);  // box written + barrier
+                    named_bar_sync(1 + grp, 128);
+                    if (tracer) HTRACE(9, tc * 4 + c);  // box written + barrier
                     if (elected) {
                         tma_store_2d(&map_c, box, col0, m0);  // clips rows >= M and columns >= N
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -316,7 +327,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         if (col0 + j < p.N) crow[col0 + j] = fmaf(__uint_as_float(r[j]), sc, tb[c * 32 + j]);
                 }
             }
-            if (elected) HTRACE(6, tc);  // epilogue: tile handed to the store engine
+            if (tracer) HTRACE(6, tc);  // epilogue: tile handed to the store engine
         }
         if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
@@ -566,6 +577,7 @@ static std::atomic<int> g_f16_cluster{0};  // 1: clusters of two CTAs share the 
 // lockstep of the two CTAs costs more than the halved weight ingest saves -- so off by default.
 static std::atomic<long long *> g_f16_dbg{nullptr};
 static std::atomic<int> g_f16_epi{0};
+static std::atomic<int> g_f16_ew{8};  // epilogue warps of the streaming kernel: 4 or 8
 static std::atomic<int> g_f16_as{0};  // 1: K <= 256 goes to the activation-stationary kernel (measured: +4 % on FFN-1, -3 % on the 6-layer value projection -- profiles/r2_gemm_shapes_f16x3_as.txt -- so off by default)
 
 extern "C" int sdetr_gemm_f16x3_set_cluster(int enable) {
@@ -581,6 +593,12 @@ extern "C" int sdetr_gemm_f16x3_set_trace(long long *device_buffer /* 10 * 256 i
 extern "C" int sdetr_gemm_f16x3_set_epilogue(int variant) {
     SDETR_REQUIRE(variant == 0 || variant == 1, SDETR_ERR_INVALID_ARG, "gemm_f16x3_set_epilogue: 0 or 1");
     g_f16_epi = variant;
+    return SDETR_OK;
+}
+
+extern "C" int sdetr_gemm_f16x3_set_epilogue_warps(int warps) {
+    SDETR_REQUIRE(warps == 4 || warps == 8, SDETR_ERR_INVALID_ARG, "gemm_f16x3_set_epilogue_warps: 4 or 8");
+    g_f16_ew = warps;
     return SDETR_OK;
 }
 
@@ -632,9 +650,10 @@ extern "C" int sdetr_gemm_f16x3_pre(const float *A, int64_t lda, const void *W_h
                               make_map_2d(&mc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C, M, N, ldc, 32, kHM);
     if (!use_tma_store) mc = ma;
     static PerDeviceOnce once, once_as;
-    static PerDeviceOnce once_cl;
-    SDETR_OPT_IN_SMEM(once, gemm_f16x3_kernel<false>, kHSmem, "gemm_f16x3_pre");
-    SDETR_OPT_IN_SMEM(once_cl, gemm_f16x3_kernel<true>, kHSmem, "gemm_f16x3_pre");
+    static PerDeviceOnce once_cl, once_8;
+    SDETR_OPT_IN_SMEM(once, (gemm_f16x3_kernel<false, 4>), kHSmem, "gemm_f16x3_pre");
+    SDETR_OPT_IN_SMEM(once_8, (gemm_f16x3_kernel<false, 8>), kHSmem, "gemm_f16x3_pre");
+    SDETR_OPT_IN_SMEM(once_cl, (gemm_f16x3_kernel<true, 4>), kHSmem, "gemm_f16x3_pre");
     SDETR_OPT_IN_SMEM(once_as, gemm_f16x3_as_kernel, kAsSmem, "gemm_f16x3_pre");
     const int sms = sm_count();
     HGemmParams p{bias, C, ldc, M, N, K, act, use_tma_store, 1.f / (kActScale * w_scale), g_f16_epi.load(), g_f16_dbg.load()};
@@ -656,11 +675,14 @@ extern "C" int sdetr_gemm_f16x3_pre(const float *A, int64_t lda, const void *W_h
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
         cfg.attrs = at, cfg.numAttrs = 1;
-        const cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_f16x3_kernel<true>, ma, mh, ml, mc, p);
+        const cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_f16x3_kernel<true, 4>, ma, mh, ml, mc, p);
         SDETR_REQUIRE(le == cudaSuccess, SDETR_ERR_CUDA, "gemm_f16x3_pre: cluster launch: %s", cudaGetErrorString(le));
         return check_launch("gemm_f16x3_pre/cluster");
     }
     const int tiles = n_tiles * m_tiles;
-    gemm_f16x3_kernel<false><<<tiles < sms ? tiles : sms, kHThreads, kHSmem, (cudaStream_t)stream>>>(ma, mh, ml, mc, p);
+    if (g_f16_ew.load() == 8 && p.epilogue == 0)
+        gemm_f16x3_kernel<false, 8><<<tiles < sms ? tiles : sms, 384 + 32 * 8, kHSmem, (cudaStream_t)stream>>>(ma, mh, ml, mc, p);
+    else
+        gemm_f16x3_kernel<false, 4><<<tiles < sms ? tiles : sms, kHThreads, kHSmem, (cudaStream_t)stream>>>(ma, mh, ml, mc, p);
     return check_launch("gemm_f16x3_pre");
 }
