@@ -366,7 +366,7 @@ int sdetr_gemm_f16x3_set_as(int enable);
 /* benchmarking knob, streaming kernel epilogue: 0 (default) = two shared 16 KB boxes + TMA bulk stores, 1 = warp-private
  * transpose boxes + coalesced 128-bit global stores (no CTA-level barrier in the epilogue) */
 int sdetr_gemm_f16x3_set_epilogue(int variant);
-/* benchmarking knob, streaming kernel: 4 or 8 (default) epilogue warps (8: two groups of four, each draining half of a tile's
+/* benchmarking knob, streaming kernel: 4 (default) or 8 epilogue warps (8: two groups of four, each draining half of a tile's
  * columns through its own store box) */
 int sdetr_gemm_f16x3_set_epilogue_warps(int warps);
 /* debugging aid: when set, CTA 0 of every streaming sdetr_gemm_f16x3_pre launch records clock64() per pipeline event

@@ -577,7 +577,7 @@ static std::atomic<int> g_f16_cluster{0};  // 1: clusters of two CTAs share the 
 // lockstep of the two CTAs costs more than the halved weight ingest saves -- so off by default.
 static std::atomic<long long *> g_f16_dbg{nullptr};
 static std::atomic<int> g_f16_epi{0};
-static std::atomic<int> g_f16_ew{8};  // epilogue warps of the streaming kernel: 4 or 8
+static std::atomic<int> g_f16_ew{4};  // epilogue warps of the streaming kernel: 4 or 8 (measured equal: one store box per group waits ~1200 clk for its TMA store to drain)
 static std::atomic<int> g_f16_as{0};  // 1: K <= 256 goes to the activation-stationary kernel (measured: +4 % on FFN-1, -3 % on the 6-layer value projection -- profiles/r2_gemm_shapes_f16x3_as.txt -- so off by default)
 
 extern "C" int sdetr_gemm_f16x3_set_cluster(int enable) {

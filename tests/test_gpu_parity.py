@@ -37,7 +37,7 @@ def _restore_global_state(pkg):
     pkg.cabi.lib().sdetr_gemm_f16x3_set_as(0)
     pkg.cabi.lib().sdetr_gemm_f16x3_set_cluster(0)
     pkg.cabi.lib().sdetr_gemm_f16x3_set_epilogue(0)
-    pkg.cabi.lib().sdetr_gemm_f16x3_set_epilogue_warps(8)
+    pkg.cabi.lib().sdetr_gemm_f16x3_set_epilogue_warps(4)
     pkg.cabi.set_option("msda_smem_broadcast", 1)
     pkg.cabi.lib().sdetr_gemm_set_variant(0)
     pkg.cabi.lib().sdetr_gemm_set_variant(3)
@@ -624,9 +624,9 @@ def test_gemm_f16x3_accuracy_and_range(pkg):
         y2 = pkg.cabi.gemm_f16x3_pre(x, w_hi, w_lo, sc, b, act)
         pkg.cabi.lib().sdetr_gemm_f16x3_set_epilogue(0)
         assert torch.equal(y0, y2), (rows, K, N)
-        pkg.cabi.lib().sdetr_gemm_f16x3_set_epilogue_warps(4)  # four epilogue warps instead of two groups of four
+        pkg.cabi.lib().sdetr_gemm_f16x3_set_epilogue_warps(8)  # two groups of four epilogue warps instead of one
         y3 = pkg.cabi.gemm_f16x3_pre(x, w_hi, w_lo, sc, b, act)
-        pkg.cabi.lib().sdetr_gemm_f16x3_set_epilogue_warps(8)
+        pkg.cabi.lib().sdetr_gemm_f16x3_set_epilogue_warps(4)
         assert torch.equal(y0, y3), (rows, K, N)
         pkg.cabi.lib().sdetr_gemm_f16x3_set_cluster(1)
         for _ in range(3):

@@ -31,12 +31,12 @@ for name, M, K, N, relu in shapes:
     for mode, own in (("auto", "f16x3"), ("auto", "f16x3-noas"), ("auto", "tf32x3"), ("3xtf32", ""), ("fp32", "")):
         pkg.gemm.MODE, pkg.gemm.OWN_KERNEL = mode, (own or "f16x3").split("-")[0]
         pkg.cabi.lib().sdetr_gemm_f16x3_set_as(0)
-        pkg.cabi.lib().sdetr_gemm_f16x3_set_epilogue_warps(4 if own.endswith("noas") else 8)
+        pkg.cabi.lib().sdetr_gemm_f16x3_set_epilogue_warps(8 if own.endswith("noas") else 4)
         key = own or mode
         fn = lambda: pkg.gemm.linear(x, w, b, relu_input=bool(relu))
         e[key] = (fn().double() - ref).abs().max().item()
         r[key] = timeit(fn)
         tot[key] = tot.get(key, 0) + r[key]
-    print(f"{name:14s} {M:6d} {K:5d} {N:5d} | {r['f16x3']:7.1f} ({e['f16x3']:.1e}) [4 epilogue warps {r['f16x3-noas']:7.1f}] | {r['tf32x3']:7.1f} ({e['tf32x3']:.1e}) | {r['3xtf32']:8.1f} | "
+    print(f"{name:14s} {M:6d} {K:5d} {N:5d} | {r['f16x3']:7.1f} ({e['f16x3']:.1e}) [8 epilogue warps {r['f16x3-noas']:7.1f}] | {r['tf32x3']:7.1f} ({e['tf32x3']:.1e}) | {r['3xtf32']:8.1f} | "
           f"{r['fp32']:7.1f} ({e['fp32']:.1e}) | {2*M*N*K/r['f16x3']/1e6:7.1f} | {r['tf32x3']/r['f16x3']:.2f}x")
 print("sum us", {k: round(v, 1) for k, v in tot.items()})
