@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(kSortThreads) merge_bitonic_kernel(const uint3
 }
 
 // segment: top-k (k <= 2048) by radix select + compaction + bitonic sort of the winners
-constexpr int kTopkFast = 2048;
+constexpr int kTopkFast = 4096;  // winners alias the 32 KB histogram buffer (the decoder's two-stage top-3600 takes this path)
 __global__ void __launch_bounds__(kSortThreads) topk_select_kernel(const float *__restrict__ score, int n, int k, int N,
                                                                    int64_t *__restrict__ out) {
     __shared__ SelectSmem sm;

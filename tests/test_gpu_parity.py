@@ -256,7 +256,7 @@ def test_salience_select_bit_exact(pkg, cfg):
 
 def test_topk_desc(pkg):
     g = torch.Generator().manual_seed(0)
-    for seg, n, k in [(2, 11363, 300), (3, 700, 300), (1, 37, 37), (4, 5000, 1)]:
+    for seg, n, k in [(2, 11363, 300), (3, 700, 300), (1, 37, 37), (4, 5000, 1), (2, 22323, 3600), (2, 22323, 4096), (1, 9000, 4097)]:
         s = torch.randn(seg, n, generator=g)
         s[:, ::7] = 0.25  # ties
         want = torch.sort(s, dim=1, descending=True, stable=True)[1][:, :k]
