@@ -47,11 +47,12 @@ __device__ __forceinline__ PointSetup make_setup(float x, float y, float a, int 
     const int y0 = (int)hf, x0 = (int)wf;
     const float ly = h_im - hf, lx = w_im - wf, hy = 1.f - ly, hx = 1.f - lx;
     const bool top = y0 >= 0, bot = y0 + 1 <= H - 1, lef = x0 >= 0, rig = x0 + 1 <= W - 1;
-    const float at = in ? a : 0.f;
-    s.w00 = (top && lef) ? at * hy * hx : 0.f;
-    s.w01 = (top && rig) ? at * hy * lx : 0.f;
-    s.w10 = (bot && lef) ? at * ly * hx : 0.f;
-    s.w11 = (bot && rig) ? at * ly * lx : 0.f;
+    // selected, not multiplied: a non-finite location (in == false, NaN fractions) contributes exactly 0 like the reference's
+    // branch (.cuh:277) and like msda_backward.cu, instead of 0 * NaN
+    s.w00 = (in && top && lef) ? a * hy * hx : 0.f;
+    s.w01 = (in && top && rig) ? a * hy * lx : 0.f;
+    s.w10 = (in && bot && lef) ? a * ly * hx : 0.f;
+    s.w11 = (in && bot && rig) ? a * ly * lx : 0.f;
     // clamped corner rows/cols: every address is inside the level, invalid corners carry weight 0
     const int rt = max(y0, 0), rb = min(y0 + 1, H - 1), cl = max(x0, 0), cr = min(x0 + 1, W - 1);
     const uint32_t idx = (uint32_t)(rt * W + cl), dx = (uint32_t)(cr - cl), dy = (uint32_t)(rb - rt);

@@ -160,6 +160,20 @@ def test_msda_kernel_variants_agree(pkg):
         pkg.cabi.set_option("msda_tma", 0)
 
 
+def test_msda_non_finite_locations_contribute_zero(pkg):
+    """A NaN / Inf sampling location is skipped (contributes exactly 0) in the forward as in the reference kernel's branch
+    (ms_deform_im2col_cuda.cuh:277) and in the backward -- not 0 * NaN."""
+    value, st, lsi, loc, attn = [t.to(DEV) for t in _msda_inputs(2, [(16, 20), (8, 10), (4, 5), (2, 3)], 8, 32, 50, 4, seed=3)]
+    bad = loc.clone()
+    bad[0, 3, 2, 1, 0, 0] = float("nan")
+    bad[1, 7, 5, 3, 2, 1] = float("inf")
+    bad[1, 9, 0, 0, 1, :] = -float("inf")
+    want = orc.c_msda_forward(value.cpu(), st.cpu(), lsi.cpu(), torch.nan_to_num(bad.cpu(), nan=-9.0, posinf=9.0, neginf=-9.0), attn.cpu())
+    for sched in (0, 1):
+        out = pkg.cabi.msda_forward(value, st, lsi, bad, attn, schedule=sched)
+        assert torch.isfinite(out).all() and (out.cpu() - want).abs().max() < 1e-4
+
+
 def test_msda_autograd_function(pkg):
     value, st, lsi, loc, attn = _msda_inputs(1, [(6, 5), (3, 3)], 2, 32, 9, 2, seed=3)
     v, l, a = (t.to(DEV).requires_grad_(True) for t in (value, loc, attn))
