@@ -622,14 +622,24 @@ def split_f16_pair(w):
     return hi, lo, scale
 
 
-def gemm_f16x3_pre(x, w_hi, w_lo, w_scale, bias=None, act=0):
-    """y = act(x) @ W.T + bias on the persistent tcgen05.mma.kind::f16 kernel (3xFP16, fp32-class accuracy)."""
+def gemm_f16x3_pre(x, w_hi, w_lo, w_scale, bias=None, act=0, out=None):
+    """y = act(x) @ W.T + bias on the persistent tcgen05.mma.kind::f16 kernel (3xFP16, fp32-class accuracy).
+    ``out``: optional (M, N) fp32 destination with unit column stride (e.g. a row slice of a larger buffer)."""
     K = x.shape[-1]
     N = w_hi.shape[0]
     if not (x.is_cuda and x.dtype == torch.float32 and x.stride(-1) == 1):
         raise RuntimeError("gemm_f16x3_pre needs a CUDA float32 input with unit last stride")
     x2 = x if x.dim() == 2 else x.reshape(-1, K)
     M = x2.shape[0]
+    if out is not None:
+        if not (out.is_cuda and out.dtype == torch.float32 and out.dim() == 2 and tuple(out.shape) == (M, N) and out.stride(1) == 1):
+            raise RuntimeError(f"gemm_f16x3_pre: out must be a CUDA float32 ({M}, {N}) tensor with unit column stride")
+        rc = lib().sdetr_gemm_f16x3_pre(x2.data_ptr(), x2.stride(0) if M > 1 else K, _req(w_hi, "w_hi", torch.float16),
+                                        _req(w_lo, "w_lo", torch.float16), float(w_scale),
+                                        _req(bias, "bias", torch.float32) if bias is not None else None, out.data_ptr(),
+                                        out.stride(0) if M > 1 else N, M, N, K, int(act), _stream())
+        _check(rc, "sdetr_gemm_f16x3_pre")
+        return out
     ldc = (N + 3) // 4 * 4
     y = torch.empty(M, ldc, device=x.device, dtype=torch.float32)
     rc = lib().sdetr_gemm_f16x3_pre(x2.data_ptr(), x2.stride(0) if M > 1 else K, _req(w_hi, "w_hi", torch.float16),

@@ -47,6 +47,10 @@ MHA_GEMM_TENSOR_CORE = False  # projections of the 600 rows on the tensor-core G
 OVERLAP_PROJ = False  # (measured: 763 vs 773 images/s, e2e 918 vs 942 -- the extra launches and stream joins cost more than the overlap buys)
 # the offsets|logits GEMM of ALL rows runs on a side stream beside the (latency-bound, few-CTA) class-max /
 # top-300 / pre-attention chain, from the gather's q + pos; the 300 rows the pre-attention rewrites are recomputed afterwards
+FFN_CHUNK_ROWS = int(__import__("os").environ.get("SDETR_FFN_CHUNK", "6144"))  # FFN in row chunks: the hidden activations of a chunk (6144 x 2048 fp32 = 50 MB) are produced and consumed
+# inside the 126 MB L2 and their buffer is reused by the next chunk, so most of the hidden tensor (186 MB at layer 0) is never
+# written to / read back from HBM -- the K = 256 GEMMs with outputs larger than L2 are bound by the HBM write stream.
+# 0 = one GEMM pair over all rows.
 TILE_CELL_PX = 64   # edge (image pixels) of the spatial cells that define the MSDA processing order
 MSDA_SCHEDULE = 1   # 0 = query-major, 1 = head-major chunks (see include/sdetr_b200.h)
 
@@ -254,8 +258,20 @@ class SalienceTransformerEncoderLayer(nn.Module):
         a = self.self_attn.forward_projected(qs if qs is not None else q + qp, ref_q, vbuf, v_bstride, v_tstride, v_off, num_value, spatial_shapes,
                                              level_start_index, order, schedule, value_ready=value_ready, proj=proj)
         q = cabi.add_layernorm(q, a, self.norm1.weight, self.norm1.bias, self.norm1.eps, out=q)
-        h = gemm.linear(q, self.linear1.weight, self.linear1.bias)
-        f = gemm.linear(h, self.linear2.weight, self.linear2.bias, relu_input=True)  # ReLU fused into the operand split
+        rows = q.shape[0] * q.shape[1]
+        if FFN_CHUNK_ROWS and rows > FFN_CHUNK_ROWS + FFN_CHUNK_ROWS // 2:
+            q2 = q.view(rows, q.shape[-1])
+            f = torch.empty_like(q2)
+            n_chunks = -(-rows // FFN_CHUNK_ROWS)
+            step = -(-rows // n_chunks // 128) * 128  # equal chunks, whole 128-row panels
+            for r0 in range(0, rows, step):
+                h = gemm.linear(q2[r0:r0 + step], self.linear1.weight, self.linear1.bias)
+                gemm.linear(h, self.linear2.weight, self.linear2.bias, relu_input=True, out=f[r0:r0 + step])
+                del h  # the caching allocator hands the same block to the next chunk: the hidden buffer stays in L2
+            f = f.view_as(q)
+        else:
+            h = gemm.linear(q, self.linear1.weight, self.linear1.bias)
+            f = gemm.linear(h, self.linear2.weight, self.linear2.bias, relu_input=True)  # ReLU fused into the operand split
         return cabi.add_layernorm(q, f, self.norm2.weight, self.norm2.bias, self.norm2.eps, out=q)
 
 
