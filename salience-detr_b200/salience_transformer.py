@@ -47,10 +47,11 @@ MHA_GEMM_TENSOR_CORE = False  # projections of the 600 rows on the tensor-core G
 OVERLAP_PROJ = False  # (measured: 763 vs 773 images/s, e2e 918 vs 942 -- the extra launches and stream joins cost more than the overlap buys)
 # the offsets|logits GEMM of ALL rows runs on a side stream beside the (latency-bound, few-CTA) class-max /
 # top-300 / pre-attention chain, from the gather's q + pos; the 300 rows the pre-attention rewrites are recomputed afterwards
-FFN_CHUNK_ROWS = int(__import__("os").environ.get("SDETR_FFN_CHUNK", "6144"))  # FFN in row chunks: the hidden activations of a chunk (6144 x 2048 fp32 = 50 MB) are produced and consumed
+FFN_CHUNK_ROWS = int(__import__("os").environ.get("SDETR_FFN_CHUNK", "0"))  # FFN in row chunks: the hidden activations of a chunk (6144 x 2048 fp32 = 50 MB) are produced and consumed
 # inside the 126 MB L2 and their buffer is reused by the next chunk, so most of the hidden tensor (186 MB at layer 0) is never
 # written to / read back from HBM -- the K = 256 GEMMs with outputs larger than L2 are bound by the HBM write stream.
-# 0 = one GEMM pair over all rows.
+# 0 (default) = one GEMM pair over all rows.  MEASURED (profiles/r2_ffn_chunk_sweep.txt): 811 images/s unchunked vs 798 / 772 / 680
+# with chunks of 9216 / 6144 / 4096 rows -- the per-launch prologue and tail of the smaller GEMMs cost more than the HBM traffic saves.
 TILE_CELL_PX = 64   # edge (image pixels) of the spatial cells that define the MSDA processing order
 MSDA_SCHEDULE = 1   # 0 = query-major, 1 = head-major chunks (see include/sdetr_b200.h)
 
