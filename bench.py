@@ -176,13 +176,25 @@ def time_gemm_kernels(pkg, runner, reps=10):
         calls.append((x, w, b, a, k))
         return orig(x, w, b, *a, **k)
 
+    # the fused FFN (linear1 -> ReLU -> linear2 -> +residual -> LayerNorm in one tensor-core kernel) counts as its two GEMMs
+    ffn_calls = []
+    orig_ffn = pkg.cabi.ffn_fused_layernorm
+
+    def spy_ffn(x, *a, **k):
+        k2 = dict(k)
+        k2.pop("out", None)
+        ffn_calls.append((x.clone(), a, k2))
+        return orig_ffn(x, *a, **k)
+
     gemm.linear = spy
+    pkg.cabi.ffn_fused_layernorm = spy_ffn
     try:
         with torch.no_grad():
             runner.model.forward_encoder(runner.feats, runner.masks, runner.pos, plan=runner.plan,
                                          use_order=runner.use_order)
     finally:
         gemm.linear = orig
+        pkg.cabi.ffn_fused_layernorm = orig_ffn
     torch.cuda.synchronize()
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=runner.dev)
     totals = []
@@ -192,11 +204,14 @@ def time_gemm_kernels(pkg, runner, reps=10):
         e0.record()
         for x, w, b, a, k in calls:
             orig(x, w, b, *a, **k)
+        for x, a, k in ffn_calls:
+            orig_ffn(x, *a, out=x, **k)
         e1.record()
         torch.cuda.synchronize()
         totals.append(e0.elapsed_time(e1))
     flops = sum(2 * (x.numel() // x.shape[-1]) * w.shape[0] * w.shape[1] for x, w, _, _, _ in calls)
-    return statistics.median(totals), flops, len(calls)
+    flops += sum(2 * 2 * (x.numel() // 256) * 256 * a[0][0].shape[0] for x, a, _ in ffn_calls)  # a[0] = (W1_hi, W1_lo, scale)
+    return statistics.median(totals), flops, len(calls) + 2 * len(ffn_calls)
 
 
 def use_host_cores():
@@ -650,7 +665,7 @@ def main():
                                            "how": "the same six launches replayed alone after an L2 flush (round-1 definition)"}},
             # secondary leg: the dense projections (tensor-bound; 3xTF32 issues 3 TF32 MMA passes per logical product)
             "roofline_gemm": {"bound": "tensor (measured: the kernel is bound by L2<->SM operand/result traffic, DESIGN.md 3.4)",
-                              "kernels": ("sdetr::gemm_f16x3_kernel (3xFP16, tcgen05.mma.kind::f16)" if f16 else
+                              "kernels": ("sdetr::gemm_f16x3_kernel + sdetr::ffn_fused_kernel (3xFP16, tcgen05.mma.kind::f16; the FFN keeps its hidden activations in tensor memory)" if f16 else
                                           "sdetr::gemm_3xtf32_p_kernel<presplit>") + " (+ cuBLAS fp32 for <= 2304-row GEMMs)",
                               "achieved": round(gemm_exec, 1), "peak": round(tf32_peak, 1), "peak_source": gemm_peak_src,
                               "unit": "TFLOP/s", "frac": round(gemm_exec / tf32_peak, 4),

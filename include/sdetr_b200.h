@@ -376,6 +376,29 @@ int sdetr_gemm_f16x3_set_trace(long long *device_buffer);
  * TMA multicast (measured slower, off by default); 0 (default) = independent CTAs */
 int sdetr_gemm_f16x3_set_cluster(int enable);
 
+/* ---- fused encoder FFN: y = LayerNorm(x + linear2(ReLU(linear1(x)))) ------------------------------------------------------
+ * Replaces `forward_ffn` + `norm2` of the encoder layer (models/bricks/salience_transformer.py:347-351, :391) for embed_dim 256:
+ * one persistent tcgen05 kernel keeps a 128-row panel on chip from x to the output accumulator (the hidden activations never
+ * reach HBM; only the weights stream), then a row kernel adds the partial sums, b2 and the residual and normalises.
+ * Same 3xFP16 arithmetic and value domain as sdetr_gemm_f16x3_pre (both weights given as sdetr_split_f16_pair pairs with
+ * their scales; W1 (hidden,256), W2 (256,hidden); hidden % 128 == 0).
+ * x (M,256) fp32 with row pitch ldx (floats); y (M,256) contiguous, may alias x when ldx == 256;
+ * gamma == beta == NULL: y = linear2(ReLU(linear1(x))) without residual / LayerNorm.
+ * workspace: sdetr_ffn_fused_workspace_floats(M, hidden) floats (partial sums of panels shared by two CTAs: the persistent
+ * CTAs take equal numbers of 128-hidden-unit chunks of the (panel, chunk) sequence, whatever the panel count). */
+int64_t sdetr_ffn_fused_workspace_floats(int M, int hidden);
+int sdetr_ffn_fused_layernorm(const float *x, int64_t ldx, const void *W1_hi, const void *W1_lo, float w1_scale, const float *b1,
+                              const void *W2_hi, const void *W2_lo, float w2_scale, const float *b2, const float *gamma,
+                              const float *beta, float eps, int M, int hidden, float *workspace, int64_t workspace_floats, float *y,
+                              sdetr_stream_t stream);
+/* benchmarking knob: 1 (default) = equal chunk counts per CTA, 0 = whole panels per CTA (idle SMs when the panel count is not
+ * near a multiple of the SM count).  Changes the workspace size: query it after setting. */
+int sdetr_ffn_fused_set_balance(int enable);
+/* debugging aid: CTA 0 of every sdetr_ffn_fused_layernorm launch records clock64() per pipeline event (8 x 256 int64) */
+int sdetr_ffn_fused_set_trace(long long *device_buffer);
+/* debugging / benchmarking knob: at most n persistent CTAs (0 = one per SM) */
+int sdetr_ffn_fused_set_max_ctas(int n);
+
 #ifdef __cplusplus
 }
 #endif

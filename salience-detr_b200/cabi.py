@@ -68,6 +68,11 @@ SIGNATURES = {
     "sdetr_gemm_f16x3_set_epilogue_warps": (_i, [_i]),
     "sdetr_gemm_f16x3_set_trace": (_i, [_vp]),
     "sdetr_gemm_f16x3_pre": (_i, [_vp, _i64, _vp, _vp, _f, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "sdetr_ffn_fused_workspace_floats": (_i64, [_i, _i]),
+    "sdetr_ffn_fused_set_balance": (_i, [_i]),
+    "sdetr_ffn_fused_layernorm": (_i, [_vp, _i64, _vp, _vp, _f, _vp, _vp, _vp, _f, _vp, _vp, _vp, _f, _i, _i, _vp, _i64, _vp, _vp]),
+    "sdetr_ffn_fused_set_trace": (_i, [_vp]),
+    "sdetr_ffn_fused_set_max_ctas": (_i, [_i]),
     "sdetr_flatten_tokens": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "sdetr_attention_small": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sdetr_attention_qkv": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
@@ -649,6 +654,31 @@ def gemm_f16x3_pre(x, w_hi, w_lo, w_scale, bias=None, act=0, out=None):
     _check(rc, "sdetr_gemm_f16x3_pre")
     y = y if ldc == N else y[:, :N]
     return y.reshape(*x.shape[:-1], N) if ldc == N else y.unflatten(0, x.shape[:-1])
+
+
+def ffn_fused_layernorm(x, w1, b1, w2, b2, gamma=None, beta=None, eps: float = 1e-5, out=None):
+    """y = LayerNorm(x + linear2(ReLU(linear1(x)))) by the fused tcgen05 kernel (gamma None: the bare FFN, no residual / norm).
+    ``w1`` / ``w2``: (W_hi, W_lo, scale) triples of ``split_f16_pair``; x (..., 256) fp32 with unit last stride."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.shape[-1] == 256 and x.stride(-1) == 1):
+        raise RuntimeError("ffn_fused_layernorm needs a CUDA float32 (..., 256) input with unit last stride")
+    x2 = x if x.dim() == 2 else x.reshape(-1, 256)
+    M = x2.shape[0]
+    hidden = w1[0].shape[0]
+    if tuple(w1[0].shape) != (hidden, 256) or tuple(w2[0].shape) != (256, hidden):
+        raise RuntimeError("ffn_fused_layernorm: W1 must be (hidden, 256) and W2 (256, hidden)")
+    y = out if out is not None else torch.empty(M, 256, device=x.device, dtype=torch.float32)
+    if not (y.is_cuda and y.dtype == torch.float32 and y.is_contiguous() and y.numel() == M * 256):
+        raise RuntimeError("ffn_fused_layernorm: out must be a contiguous CUDA float32 tensor of the input's size")
+    ws = torch.empty(max(int(lib().sdetr_ffn_fused_workspace_floats(M, hidden)), 4), device=x.device, dtype=torch.float32)
+    rc = lib().sdetr_ffn_fused_layernorm(
+        x2.data_ptr(), x2.stride(0) if M > 1 else 256, _req(w1[0], "w1_hi", torch.float16), _req(w1[1], "w1_lo", torch.float16),
+        float(w1[2]), _req(b1, "b1", torch.float32), _req(w2[0], "w2_hi", torch.float16), _req(w2[1], "w2_lo", torch.float16),
+        float(w2[2]), _req(b2, "b2", torch.float32) if b2 is not None else None,
+        _req(gamma, "gamma", torch.float32) if gamma is not None else None,
+        _req(beta, "beta", torch.float32) if beta is not None else None, float(eps), M, hidden, ws.data_ptr(), ws.numel(),
+        y.data_ptr(), _stream())
+    _check(rc, "sdetr_ffn_fused_layernorm")
+    return y if out is not None else y.reshape(x.shape)
 
 
 def rows_gather_add(src, pos, index):

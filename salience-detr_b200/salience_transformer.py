@@ -47,6 +47,9 @@ MHA_GEMM_TENSOR_CORE = False  # projections of the 600 rows on the tensor-core G
 OVERLAP_PROJ = False  # (measured: 763 vs 773 images/s, e2e 918 vs 942 -- the extra launches and stream joins cost more than the overlap buys)
 # the offsets|logits GEMM of ALL rows runs on a side stream beside the (latency-bound, few-CTA) class-max /
 # top-300 / pre-attention chain, from the gather's q + pos; the 300 rows the pre-attention rewrites are recomputed afterwards
+FUSED_FFN = __import__("os").environ.get("SDETR_FUSED_FFN", "1") != "0"  # C = 256: linear1 -> ReLU -> linear2 -> +residual -> norm2 as ONE
+# tensor-core kernel that keeps the hidden activations in tensor memory (csrc/ffn_fused.cu) + a row kernel, instead of two GEMMs
+# writing / reading the (rows x d_ffn) hidden tensor and an add+LayerNorm launch
 FFN_CHUNK_ROWS = int(__import__("os").environ.get("SDETR_FFN_CHUNK", "0"))  # FFN in row chunks: the hidden activations of a chunk (6144 x 2048 fp32 = 50 MB) are produced and consumed
 # inside the 126 MB L2 and their buffer is reused by the next chunk, so most of the hidden tensor (186 MB at layer 0) is never
 # written to / read back from HBM -- the K = 256 GEMMs with outputs larger than L2 are bound by the HBM write stream.
@@ -260,7 +263,13 @@ class SalienceTransformerEncoderLayer(nn.Module):
                                              level_start_index, order, schedule, value_ready=value_ready, proj=proj)
         q = cabi.add_layernorm(q, a, self.norm1.weight, self.norm1.bias, self.norm1.eps, out=q)
         rows = q.shape[0] * q.shape[1]
-        if FFN_CHUNK_ROWS and rows > FFN_CHUNK_ROWS + FFN_CHUNK_ROWS // 2:
+        relu = isinstance(self.activation, nn.ReLU)
+        if (FUSED_FFN and relu and self.embed_dim == 256 and self.linear1.out_features % 128 == 0 and gemm.MODE == "auto" and
+                gemm.OWN_KERNEL == "f16x3" and rows > gemm.SMALL_M and q.is_contiguous()):
+            return cabi.ffn_fused_layernorm(q, gemm.split_weight_f16(self.linear1.weight), self.linear1.bias,
+                                            gemm.split_weight_f16(self.linear2.weight), self.linear2.bias, self.norm2.weight,
+                                            self.norm2.bias, self.norm2.eps, out=q)
+        if FFN_CHUNK_ROWS and relu and rows > FFN_CHUNK_ROWS + FFN_CHUNK_ROWS // 2:
             q2 = q.view(rows, q.shape[-1])
             f = torch.empty_like(q2)
             n_chunks = -(-rows // FFN_CHUNK_ROWS)
@@ -272,7 +281,10 @@ class SalienceTransformerEncoderLayer(nn.Module):
             f = f.view_as(q)
         else:
             h = gemm.linear(q, self.linear1.weight, self.linear1.bias)
-            f = gemm.linear(h, self.linear2.weight, self.linear2.bias, relu_input=True)  # ReLU fused into the operand split
+            if relu:
+                f = gemm.linear(h, self.linear2.weight, self.linear2.bias, relu_input=True)  # ReLU fused into the operand split
+            else:  # any other activation module of the reference's constructor argument
+                f = gemm.linear(self.activation(h), self.linear2.weight, self.linear2.bias)
         return cabi.add_layernorm(q, f, self.norm2.weight, self.norm2.bias, self.norm2.eps, out=q)
 
 

@@ -1152,3 +1152,53 @@ def test_salience_targets_kernel_vs_reference_golden(pkg):
     a = crit.mask_targets(shapes, t2, strides, sizes, torch.device(DEV)).cpu()
     w = crit.mask_targets(shapes, [{"boxes": torch.zeros(0, 4)}, {"boxes": many}], strides, sizes, torch.device("cpu"))
     assert a[0].abs().max() == 0 and (a - w).abs().max() < 1e-6
+
+
+def test_ffn_fused_layernorm(pkg):
+    """Fused FFN (hidden activations kept in tensor memory, sdetr_ffn_fused_layernorm) against an fp64 reference and against
+    the two-GEMM path: CTA ranges that cut panels (balanced) and whole-panel ranges, few / many CTAs (several units per CTA,
+    panels shared by three CTAs), ragged last panel, strided input rows, bare-FFN mode, in-place output, bit-reproducible."""
+    g = torch.Generator().manual_seed(11)
+    F = torch.nn.functional
+    lib = pkg.cabi.lib()
+    try:
+        for rows, hidden in [(128, 256), (1000, 2048), (22726, 2048), (19500, 1024), (300, 128), (4545, 2048)]:
+            x = torch.randn(rows, 256, generator=g).to(DEV)
+            w1 = (torch.randn(hidden, 256, generator=g) / 16).to(DEV)
+            b1 = torch.randn(hidden, generator=g).to(DEV)
+            w2 = (torch.randn(256, hidden, generator=g) / hidden ** 0.5).to(DEV)
+            b2 = torch.randn(256, generator=g).to(DEV)
+            gamma = (1 + 0.1 * torch.randn(256, generator=g)).to(DEV)
+            beta = (0.1 * torch.randn(256, generator=g)).to(DEV)
+            s1, s2 = pkg.cabi.split_f16_pair(w1), pkg.cabi.split_f16_pair(w2)
+            f64 = F.linear(F.relu(F.linear(x.double(), w1.double(), b1.double())), w2.double(), b2.double())
+            ref = F.layer_norm(x.double() + f64, (256,), gamma.double(), beta.double(), 1e-5)
+            two = pkg.cabi.gemm_f16x3_pre(pkg.cabi.gemm_f16x3_pre(x, *s1, b1, 0), *s2, b2, 1)
+            e_two = (two.double() - f64).abs().max().item()
+            for balance, ctas in [(1, 0), (0, 0), (1, 7), (0, 5), (1, 97), (1, 1)]:
+                lib.sdetr_ffn_fused_set_balance(balance)
+                lib.sdetr_ffn_fused_set_max_ctas(ctas)
+                bare = pkg.cabi.ffn_fused_layernorm(x, s1, b1, s2, b2)
+                err = (bare.double() - f64).abs().max().item()
+                assert err < 1e-4 and err < 4 * e_two + 1e-6, (rows, hidden, balance, ctas, err, e_two)
+                y = pkg.cabi.ffn_fused_layernorm(x, s1, b1, s2, b2, gamma, beta, 1e-5)
+                assert (y.double() - ref).abs().max().item() < 1e-4, (rows, hidden, balance, ctas)
+                assert torch.equal(pkg.cabi.ffn_fused_layernorm(x, s1, b1, s2, b2, gamma, beta, 1e-5), y)
+            lib.sdetr_ffn_fused_set_balance(1)
+            lib.sdetr_ffn_fused_set_max_ctas(0)
+            # in place (the layer's use) and strided input rows
+            xin = x.clone()
+            pkg.cabi.ffn_fused_layernorm(xin, s1, b1, s2, b2, gamma, beta, 1e-5, out=xin)
+            assert (xin.double() - ref).abs().max().item() < 1e-4
+            wide = torch.zeros(rows, 320, device=DEV)
+            wide[:, :256] = x
+            ys = pkg.cabi.ffn_fused_layernorm(wide[:, :256], s1, b1, s2, b2, gamma, beta, 1e-5)
+            assert (ys.double() - ref).abs().max().item() < 1e-4
+        # the documented value domain: large activations, six decades inside a row
+        x = (torch.randn(700, 256, generator=g) * torch.logspace(-3, 2, 256)).to(DEV)
+        f64 = F.linear(F.relu(F.linear(x.double(), w1.double(), b1.double())), w2.double(), b2.double())
+        bare = pkg.cabi.ffn_fused_layernorm(x, s1, b1, s2, b2)
+        assert ((bare.double() - f64).abs().max() / f64.abs().max()).item() < 2e-6
+    finally:
+        lib.sdetr_ffn_fused_set_balance(1)
+        lib.sdetr_ffn_fused_set_max_ctas(0)
