@@ -89,8 +89,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     uint8_t *panel = smem, *ring = smem + kFPanel;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kFPanel + kFRing);
     uint64_t *full = bars, *empty = bars + kFStages;
-    uint64_t *panel_full = bars + 2 * kFStages;  // the split x panel of the unit is written
-    uint64_t *panel_free = panel_full + 1, *acc1_full = panel_free + 1, *acc1_free = acc1_full + 1;
+    uint64_t *panel_full = bars + 2 * kFStages;  // [4]: k-block kb of the unit's split x panel is written
+    uint64_t *panel_free = panel_full + 4, *acc1_full = panel_free + 1, *acc1_free = acc1_full + 1;
     uint64_t *h_full = acc1_free + 1, *h_free = h_full + 1, *out_full = h_free + 1, *out_free = out_full + 1;
     uint64_t *x_full = out_free + 1;  // [4]: raw x k-block kb of the unit landed in the panel region
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(x_full + 4);
@@ -100,8 +100,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kFStages; ++s) mbar_init(full + s, 1), mbar_init(empty + s, 1);
-        mbar_init(panel_full, 256), mbar_init(panel_free, 1);
-        for (int kb = 0; kb < 4; ++kb) mbar_init(x_full + kb, 1);
+        mbar_init(panel_free, 1);
+        for (int kb = 0; kb < 4; ++kb) mbar_init(panel_full + kb, 256), mbar_init(x_full + kb, 1);
         mbar_init(acc1_full, 1), mbar_init(acc1_free, 256);
         mbar_init(h_full, 256), mbar_init(h_free, 1);
         mbar_init(out_full, 1), mbar_init(out_free, 128);
@@ -160,8 +160,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                         const uint32_t gg = g + j;
                         mbar_wait(acc1_free, (gg & 1) ^ 1);  // the converters have read the previous chunk's accumulator
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        if (j == 0) mbar_wait(panel_full, u & 1);
                         for (int kb = 0; kb < 4; ++kb, ++it) {
+                            if (j == 0) mbar_wait(panel_full + kb, u & 1);
                             const int s = it % kFStages;
                             mbar_wait(full + s, (it / kFStages) & 1);
                             FTRACE(0, it);
@@ -256,9 +256,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     *reinterpret_cast<uint4 *>(hrow + oc) = h;
                     *reinterpret_cast<uint4 *>(lrow + oc) = l;
                 }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA's reads
+                mbar_arrive(panel_full + kb);  // G1 of the first chunk starts on k-block 0 while the others are being split
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA's reads
-            mbar_arrive(panel_full);
             if (tc == 0) FTRACE(7, 4 * ux + 2);
         };
         FfnUnits un(p, blockIdx.x, gridDim.x);

@@ -1,15 +1,15 @@
 #!/bin/bash
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-for c in 1 0; do
-(SDETR_FUSED_FFN=$c timeout 600 python bench.py --skip-cpu-baseline > gpurun_out/r2_o_bench_$c.json) 2> gpurun_out/r2_o_bench_$c.err
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "ffn_fused" 2>&1 | tail -3
+timeout 300 python tools/bench_ffn.py 2>&1 | tee gpurun_out/r2_n_bench_ffn_v6.txt
+for d in 3 4; do
+(timeout 600 python bench.py --skip-cpu-baseline --pipeline-depth $d > gpurun_out/r2_o_bench_d$d.json) 2> gpurun_out/r2_o_bench_d$d.err
 done
-(timeout 900 python -m pytest tests -q -x -m gpu 2>&1 | tail -6) > gpurun_out/r2_o_tests.log
 python - <<'PY'
 import json
-for c in (1, 0):
+for c in (3, 4):
     try:
-        j=json.load(open(f'gpurun_out/r2_o_bench_{c}.json')); print(c, j['value'], j['ms_per_step'], j['e2e']['value'], j['gpu_launches_per_step'], j['roofline_gemm']['kernel_ms_per_step'], j['roofline_gemm']['frac'], j['clocks'])
+        j=json.load(open(f'gpurun_out/r2_o_bench_d{c}.json')); print(c, j['value'], j['ms_per_step'], j['e2e']['value'], j['gpu_launches_per_step'], j['roofline_gemm']['kernel_ms_per_step'], j['roofline_gemm']['frac'], j['clocks'])
     except Exception as e: print(c, 'ERR', e)
 PY
-tail -4 gpurun_out/r2_o_tests.log
