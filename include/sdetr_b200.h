@@ -236,6 +236,9 @@ int sdetr_flatten_tokens(const float *const *feats_host, const float *const *pos
 int sdetr_flatten_tokens_pos(const float *const *feats_host, const float *pos_tokens, const float *level_embeds,
                              const float *keep, const int32_t *level_size_host, int batch, int channels, int num_levels,
                              float *feat_tok, float *lpos_tok, float *x_tok, sdetr_stream_t stream);
+/* testing knob: 1 (default) = levels with a token count % 4 == 0 use the vectorised register-transpose kernel; 0 = all levels
+ * through the 32x32 shared-memory tile kernel.  Results are bit-identical. */
+int sdetr_flatten_set_vectorized(int enable);
 
 /* Salience supervision targets (training side of the filter; SalienceCriterion.get_mask_single_level with noise_scale 0,
  * models/detectors/salience_detr.py:64-114): target[b,t] = max over the boxes that contain the token's pixel centre
@@ -375,6 +378,23 @@ int sdetr_gemm_f16x3_set_trace(long long *device_buffer);
 /* benchmarking knob: 1 = clusters of two CTAs (adjacent 128-row panels, same output columns) share the weight k-blocks by
  * TMA multicast (measured slower, off by default); 0 (default) = independent CTAs */
 int sdetr_gemm_f16x3_set_cluster(int enable);
+
+/* ---- MaskPredictor of one small feature level in two launches ---------------------------------------------------------------
+ * Replaces, for a level of few token rows, score modulation + MaskPredictor (models/bricks/salience_transformer.py:16-47, :134-143):
+ * x = m + m * bilinear(coarse_score, align_corners=True) * alpha[alpha_index] (coarse_score NULL: x = m), LayerNorm, Linear(C,C),
+ * GELU, token mean of the upper half of the channels (over the H*W tokens of each image), Linear(C,C/2), GELU, Linear(C/2,C/4),
+ * GELU, Linear(C/4,1).  channels must be 256.  fp32 FMA arithmetic.
+ * mem: first token row of the level in image 0, rows of `channels` floats, images mem_batch_stride floats apart;
+ * weights TRANSPOSED to (in, out) row-major: w1_t (C,C), w2a_t (C,C/2), w2b_t (C/2,C/4); w2c (C/4);
+ * out: the level's raw scores, H*W per image, images out_batch_stride floats apart;
+ * workspace: sdetr_mask_predictor_level_workspace_floats(batch, H, W) floats. */
+int64_t sdetr_mask_predictor_level_workspace_floats(int batch, int H, int W);
+int sdetr_mask_predictor_level(const float *mem, int64_t mem_batch_stride, int batch, int H, int W, int channels,
+                               const float *coarse_score, int64_t coarse_batch_stride, int Hc, int Wc, const float *alpha,
+                               int alpha_index, const float *ln_gamma, const float *ln_beta, float eps, const float *w1_t,
+                               const float *b1, const float *w2a_t, const float *b2a, const float *w2b_t, const float *b2b,
+                               const float *w2c, const float *b2c, float *workspace, int64_t workspace_floats, float *out,
+                               int64_t out_batch_stride, sdetr_stream_t stream);
 
 /* ---- fused encoder FFN: y = LayerNorm(x + linear2(ReLU(linear1(x)))) ------------------------------------------------------
  * Replaces `forward_ffn` + `norm2` of the encoder layer (models/bricks/salience_transformer.py:347-351, :391) for embed_dim 256:

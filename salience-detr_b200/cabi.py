@@ -68,10 +68,14 @@ SIGNATURES = {
     "sdetr_gemm_f16x3_set_epilogue_warps": (_i, [_i]),
     "sdetr_gemm_f16x3_set_trace": (_i, [_vp]),
     "sdetr_gemm_f16x3_pre": (_i, [_vp, _i64, _vp, _vp, _f, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "sdetr_mask_predictor_level_workspace_floats": (_i64, [_i, _i, _i]),
+    "sdetr_mask_predictor_level": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _i64, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp,
+                                        _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "sdetr_ffn_fused_workspace_floats": (_i64, [_i, _i]),
     "sdetr_ffn_fused_set_balance": (_i, [_i]),
     "sdetr_ffn_fused_layernorm": (_i, [_vp, _i64, _vp, _vp, _f, _vp, _vp, _vp, _f, _vp, _vp, _vp, _f, _i, _i, _vp, _i64, _vp, _vp]),
     "sdetr_ffn_fused_set_trace": (_i, [_vp]),
+    "sdetr_flatten_set_vectorized": (_i, [_i]),
     "sdetr_ffn_fused_set_max_ctas": (_i, [_i]),
     "sdetr_flatten_tokens": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "sdetr_attention_small": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -376,6 +380,33 @@ def score_modulate(mem_all, level_start: int, H: int, W: int, coarse_score, Hc: 
         _stream())
     _check(rc, "sdetr_score_modulate")
     return out
+
+
+def mask_predictor_level(mem_all, level_start: int, H: int, W: int, coarse_score, Hc: int, Wc: int, alpha, alpha_index: int,
+                         ln_gamma, ln_beta, eps: float, w1_t, b1, w2a_t, b2a, w2b_t, b2b, w2c, b2c, raw, out_start: int):
+    """Score modulation + MaskPredictor of one level in two launches.  mem_all (b,Nv,256) contiguous, the level's tokens start at
+    ``level_start``; coarse_score: (b,Hc*Wc) rows of the next coarser level's raw scores (any batch stride) or None; weights
+    transposed to (in, out); writes raw[:, out_start:out_start + H*W] (raw (b,Nv) contiguous)."""
+    b, nv, c = mem_all.shape
+    if coarse_score is not None:
+        if not (coarse_score.is_cuda and coarse_score.stride(1) == 1 and coarse_score.dtype == torch.float32):
+            raise RuntimeError("coarse_score rows must be contiguous CUDA float32")
+        if not 0 <= alpha_index < alpha.numel():
+            raise IndexError(f"alpha has {alpha.numel()} entries, level {alpha_index} asked for")
+    if not (raw.is_cuda and raw.dtype == torch.float32 and raw.is_contiguous() and tuple(raw.shape) == (b, nv)):
+        raise RuntimeError("raw must be a contiguous CUDA float32 (b, Nv) tensor")
+    ws = torch.empty(int(lib().sdetr_mask_predictor_level_workspace_floats(b, H, W)), device=mem_all.device, dtype=torch.float32)
+    rc = lib().sdetr_mask_predictor_level(
+        _req(mem_all, "mem", torch.float32) + 4 * level_start * c, nv * c, b, H, W, c,
+        coarse_score.data_ptr() if coarse_score is not None else None, coarse_score.stride(0) if coarse_score is not None else 0,
+        Hc, Wc, _req(alpha, "alpha", torch.float32) if coarse_score is not None else None, alpha_index,
+        _req(ln_gamma, "ln_gamma", torch.float32), _req(ln_beta, "ln_beta", torch.float32), float(eps),
+        _req(w1_t, "w1_t", torch.float32), _req(b1, "b1", torch.float32), _req(w2a_t, "w2a_t", torch.float32),
+        _req(b2a, "b2a", torch.float32), _req(w2b_t, "w2b_t", torch.float32), _req(b2b, "b2b", torch.float32),
+        _req(w2c, "w2c", torch.float32), _req(b2c, "b2c", torch.float32), ws.data_ptr(), ws.numel(),
+        raw.data_ptr() + 4 * out_start, nv, _stream())
+    _check(rc, "sdetr_mask_predictor_level")
+    return raw
 
 
 def zero_masked_rows_(buf, row_stride: int, row_floats: int, mask_u8, num_rows: int, offset_floats: int = 0):

@@ -47,6 +47,9 @@ MHA_GEMM_TENSOR_CORE = False  # projections of the 600 rows on the tensor-core G
 OVERLAP_PROJ = False  # (measured: 763 vs 773 images/s, e2e 918 vs 942 -- the extra launches and stream joins cost more than the overlap buys)
 # the offsets|logits GEMM of ALL rows runs on a side stream beside the (latency-bound, few-CTA) class-max /
 # top-300 / pre-attention chain, from the gather's q + pos; the 300 rows the pre-attention rewrites are recomputed afterwards
+FUSED_SMALL_PREDICTOR = __import__("os").environ.get("SDETR_FUSED_SMALL_PREDICTOR", "1") != "0"  # score modulation + MaskPredictor of a
+# level with at most PREDICTOR_SMALL_ROWS token rows as two fp32 kernels (csrc/predictor_small.cu) instead of ~15 latency-bound launches
+PREDICTOR_SMALL_ROWS = 4096
 FUSED_FFN = __import__("os").environ.get("SDETR_FUSED_FFN", "1") != "0"  # C = 256: linear1 -> ReLU -> linear2 -> +residual -> norm2 as ONE
 # tensor-core kernel that keeps the hidden activations in tensor memory (csrc/ffn_fused.cu) + a row kernel, instead of two GEMMs
 # writing / reading the (rows x d_ffn) hidden tensor and an add+LayerNorm launch
@@ -78,6 +81,19 @@ class MaskPredictor(nn.Module):
         half = self.h_dim // 2
         z = torch.cat([z[..., :half], z[..., half:].mean(dim=1, keepdim=True).expand(-1, z.shape[1], -1)], dim=-1)
         return self.layer2(z)
+
+    def transposed_weights(self):
+        """(W1^T, b1, W2a^T, b2a, W2b^T, b2b, w2c, b2c) with the weights in (in, out) layout, cached per parameter version
+        (sdetr_mask_predictor_level streams weight rows)."""
+        lins = [self.layer1[1], self.layer2[0], self.layer2[2], self.layer2[4]]
+        key = tuple((m.weight.data_ptr(), m.weight._version, m.bias.data_ptr(), m.bias._version) for m in lins)
+        if getattr(self, "_t_key", None) != key:
+            with torch.no_grad():
+                self._t = (lins[0].weight.detach().t().contiguous(), lins[0].bias.detach(), lins[1].weight.detach().t().contiguous(),
+                           lins[1].bias.detach(), lins[2].weight.detach().t().contiguous(), lins[2].bias.detach(),
+                           lins[3].weight.detach().reshape(-1).contiguous(), lins[3].bias.detach())
+            self._t_key = key
+        return self._t
 
     def forward_fast(self, x):
         """Inference: same math; projections on the tensor cores, GELUs fused into the next GEMM's operand load,
@@ -600,9 +616,19 @@ class SalienceTransformer(nn.Module):
                                      self.enc_output_norm.eps, out=mem)
         raw = torch.empty(b, nv, device=feat.device, dtype=torch.float32)
         prev = None
+        mp = self.enc_mask_predictor
+        small_ok = (not grad and FUSED_SMALL_PREDICTOR and c == 256 and mp.h_dim == 256 and mp.layer1[1].in_features == 256 and
+                    mem.is_contiguous())
         for lvl in range(L - 1, -1, -1):
             h, w = plan.shapes_list[lvl]
             s0 = plan.level_start[lvl]
+            if small_ok and b * h * w <= PREDICTOR_SMALL_ROWS:  # few rows: launch latency, not arithmetic -- two fused launches
+                hc, wc = plan.shapes_list[lvl + 1] if lvl != L - 1 else (0, 0)
+                coarse = raw[:, plan.level_start[lvl + 1]:plan.level_start[lvl + 1] + hc * wc] if lvl != L - 1 else None
+                ln = mp.layer1[0]
+                cabi.mask_predictor_level(mem, s0, h, w, coarse, hc, wc, self.alpha, lvl, ln.weight, ln.bias, ln.eps,
+                                          *mp.transposed_weights(), raw, s0)
+                continue
             m_l = mem[:, s0:s0 + h * w]
             if lvl != L - 1:
                 hc, wc = plan.shapes_list[lvl + 1]

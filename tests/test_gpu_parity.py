@@ -378,6 +378,28 @@ def test_flatten_tokens(pkg):
     f, p_, x = pkg.cabi.flatten_tokens([t.to(DEV) for t in feats], [t.to(DEV) for t in pos], emb.to(DEV), keep.to(DEV))
     assert torch.equal(f.cpu(), want_f) and torch.equal(p_.cpu(), want_p)
     assert torch.equal(x.cpu(), (want_f + want_p) * keep[..., None])
+    # vectorised register-transpose kernel (levels with a token count % 4 == 0) mixed with the tile kernel (the others), wide C,
+    # both position-embedding layouts: identical to the oracle and to the tile kernel alone
+    for C, shapes in [(256, [(12, 20), (7, 11), (4, 6), (2, 3)]), (320, [(8, 8), (4, 4)]), (32, [(5, 4), (3, 3), (2, 2)])]:
+        feats = [torch.randn(b, C, h, w, generator=g) for h, w in shapes]
+        pos = [torch.randn(b, C, h, w, generator=g) for h, w in shapes]
+        emb = torch.randn(len(shapes), C, generator=g)
+        nv = sum(h * w for h, w in shapes)
+        keep = (torch.rand(b, nv, generator=g) > 0.2).float()
+        want_f = orc.flatten_levels(feats)
+        want_p = orc.flatten_levels([p + e.view(1, -1, 1, 1) for p, e in zip(pos, emb)])
+        pos_tok = orc.flatten_levels(pos)
+        outs = []
+        for vec in (1, 0):
+            pkg.cabi.lib().sdetr_flatten_set_vectorized(vec)
+            try:
+                o1 = pkg.cabi.flatten_tokens([t.to(DEV) for t in feats], [t.to(DEV) for t in pos], emb.to(DEV), keep.to(DEV))
+                o2 = pkg.cabi.flatten_tokens_pos([t.to(DEV) for t in feats], pos_tok.to(DEV), emb.to(DEV), keep.to(DEV))
+            finally:
+                pkg.cabi.lib().sdetr_flatten_set_vectorized(1)
+            for o in (o1, o2):
+                assert torch.equal(o[0].cpu(), want_f) and torch.equal(o[1].cpu(), want_p), (C, vec)
+                assert torch.equal(o[2].cpu(), (want_f + want_p) * keep[..., None]), (C, vec)
 
 
 def test_attention_small(pkg):
@@ -1202,3 +1224,45 @@ def test_ffn_fused_layernorm(pkg):
     finally:
         lib.sdetr_ffn_fused_set_balance(1)
         lib.sdetr_ffn_fused_set_max_ctas(0)
+
+
+def test_mask_predictor_level(pkg):
+    """Score modulation + MaskPredictor of a small level as two launches (sdetr_mask_predictor_level) against the module's own
+    torch forward on the modulated tokens (reference :16-47, :134-143) in fp64; ragged last tile, with / without a coarser level,
+    bit-reproducible."""
+    g = torch.Generator().manual_seed(21)
+    F = torch.nn.functional
+    mp = pkg.salience_transformer.MaskPredictor(256, 256)
+    with torch.no_grad():
+        for p_ in mp.parameters():
+            p_.copy_(torch.randn(p_.shape, generator=g) * (0.08 if p_.dim() > 1 else 0.2) + (1.0 if p_.dim() == 1 and p_.numel() == 256 and p_ is mp.layer1[0].weight else 0.0))
+    mp64 = __import__("copy").deepcopy(mp).double()
+    mp = mp.to(DEV)
+    alpha = torch.tensor([0.3, -0.2, 0.7], device=DEV)
+    for b, (h, w), (hc, wc) in [(2, (13, 21), (0, 0)), (2, (25, 42), (13, 21)), (3, (7, 9), (4, 5)), (1, (1, 5), (1, 3)), (2, (50, 84), (25, 42))]:
+        lead, tail = 37, 11
+        nv = lead + h * w + hc * wc + tail
+        mem = torch.randn(b, nv, 256, generator=g).to(DEV)
+        raw = torch.zeros(b, nv, device=DEV)
+        coarse = None
+        if hc:
+            raw[:, lead + h * w:lead + h * w + hc * wc] = torch.randn(b, hc * wc, generator=g).to(DEV)
+            coarse = raw[:, lead + h * w:lead + h * w + hc * wc]
+        ln = mp.layer1[0]
+        keep = raw.clone()
+        pkg.cabi.mask_predictor_level(mem, lead, h, w, coarse, hc, wc, alpha, 1, ln.weight, ln.bias, ln.eps, *mp.transposed_weights(), raw, lead)
+        m = mem[:, lead:lead + h * w].double().cpu()
+        if hc:
+            up = F.interpolate(coarse.double().cpu().reshape(b, 1, hc, wc), size=(h, w), mode="bilinear", align_corners=True)
+            m = m + m * up.view(b, 1, h * w).transpose(1, 2) * float(alpha[1])
+        with torch.no_grad():
+            want = mp64(m).squeeze(-1)
+        got = raw[:, lead:lead + h * w]
+        assert (got.double().cpu() - want).abs().max().item() < 3e-5, (b, h, w)
+        outside = torch.ones(nv, dtype=torch.bool)
+        outside[lead:lead + h * w] = False
+        assert torch.equal(raw[:, outside], keep[:, outside])  # nothing but the level's slice is written
+        again = keep.clone()
+        pkg.cabi.mask_predictor_level(mem, lead, h, w, again[:, lead + h * w:lead + h * w + hc * wc] if hc else None, hc, wc, alpha, 1,
+                                      ln.weight, ln.bias, ln.eps, *mp.transposed_weights(), again, lead)
+        assert torch.equal(again, raw)
