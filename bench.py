@@ -493,6 +493,8 @@ def main():
     ap.add_argument("--gemm", default="auto", choices=["auto", "tcgen05", "3xtf32", "fp32", "tf32"])
     ap.add_argument("--mode", default="forward", choices=["forward", "train"])
     ap.add_argument("--bucket-mb", type=int, default=32)
+    ap.add_argument("--e2e-persistent-ctas", type=int, default=0,
+                    help="cap of the persistent GEMM / FFN kernels during the e2e (multi-lane) measurement; 0 = one CTA per SM")
     ap.add_argument("--pipeline-depth", type=int, default=4, help="lanes of the host-buffer pipeline (e2e)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -590,6 +592,7 @@ def main():
     stream_keep, stream = stream, host_runner.stream
     e2e_serial_ms = timed(host_runner.run_host, args.steps, 3)
     stream = stream_keep
+    pkg.cabi.lib().sdetr_set_persistent_ctas(args.e2e_persistent_ctas)  # grid sizes are fixed when the lanes' graphs are captured
     pipe = HostPipeline(model, feats, masks, None, depth=args.pipeline_depth, use_graph=not args.no_graph, use_order=not args.no_order)
     host_batch = ([t.pin_memory() for t in feats_h], None)
     pipe.run([host_batch] * 4)  # warm-up
@@ -602,6 +605,7 @@ def main():
     t1.record()
     barrier()
     e2e_ms = sdist.max_over_ranks(t0.elapsed_time(t1), dev)
+    pkg.cabi.lib().sdetr_set_persistent_ctas(0)
     e2e_val = sdist.aggregate_throughput(bsz, e2e_steps, world, e2e_ms)
 
     # fresh masks every step: nothing derived from the masks is reused -- masks H2D, plan (two launches + one host
@@ -671,7 +675,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": round(e2e_val, 2), "unit": "images/s", "h2d_bytes_per_step": host_runner.h2d_bytes,
                     "d2h_bytes_per_step": host_runner.d2h_bytes, "ms_per_step": round(e2e_ms / e2e_steps, 4), "steps": e2e_steps,
-                    "pipeline_depth": args.pipeline_depth,
+                    "pipeline_depth": args.pipeline_depth, "persistent_ctas": args.e2e_persistent_ctas or "one per SM",
                     "api": "salience_detr_b200.runner.HostPipeline.run (pinned host feature maps in, memory out, double-buffered: "
                            "H2D, forward and D2H of consecutive batches overlap; the sine position embedding is derived from "
                            "the padding masks on the device, as in the detector, salience_detr.py:172-176)",

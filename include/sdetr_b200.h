@@ -38,6 +38,10 @@ int sdetr_version(void);
 const char *sdetr_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py "gpu_launches") */
 unsigned long long sdetr_launch_count(void);
+/* The persistent tensor-core kernels (sdetr_gemm_f16x3_pre, sdetr_ffn_fused_layernorm) launch one CTA per SM and leave no room
+ * for anything else on it; n > 0 caps them at n CTAs so that concurrently running streams (other lanes of a pipeline) find free
+ * SMs for their small kernels.  0 (default) = every SM.  Process-wide. */
+int sdetr_set_persistent_ctas(int n);
 
 /* process-wide tuning knobs (benchmark sweeps): "msda_min_blocks" (2..4 resident CTAs/SM the specialised
  * MSDA kernel is compiled for), "msda_chunk" (queries per CTA in the head-major schedule). */

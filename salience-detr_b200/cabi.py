@@ -27,6 +27,7 @@ SIGNATURES = {
     "sdetr_version": (_i, []),
     "sdetr_last_error": (ctypes.c_char_p, []),
     "sdetr_launch_count": (ctypes.c_ulonglong, []),
+    "sdetr_set_persistent_ctas": (_i, [_i]),
     "sdetr_set_option": (_i, [ctypes.c_char_p, _i]),
     "sdetr_msda_forward": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
     "sdetr_msda_forward_ex": (_i, [_vp, _i64, _i64] + [_vp] * 5 + [_i] * 7 + [_vp, _i, _vp]),

@@ -26,9 +26,18 @@ int sm_count() {
     }
     return v;
 }
+static std::atomic<int> g_persistent_cap{0};
+int persistent_ctas() {
+    const int cap = g_persistent_cap.load(std::memory_order_relaxed), sms = sm_count();
+    return cap > 0 && cap < sms ? cap : sms;
+}
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 }  // namespace sdetr
 
+extern "C" int sdetr_set_persistent_ctas(int n) {
+    sdetr::g_persistent_cap.store(n > 0 ? n : 0, std::memory_order_relaxed);
+    return SDETR_OK;
+}
 extern "C" int sdetr_version(void) { return 100; }  // 0.1.0
 extern "C" const char *sdetr_last_error(void) { return sdetr::g_error; }
 extern "C" unsigned long long sdetr_launch_count(void) { return sdetr::g_launches.load(std::memory_order_relaxed); }

@@ -55,6 +55,7 @@ struct PerDeviceOnce {
     } while (0)
 
 int sm_count();  // SMs of the CURRENT device (cached per device ordinal; api.cu)
+int persistent_ctas();  // CTAs of a persistent one-per-SM kernel: sm_count(), or the cap of sdetr_set_persistent_ctas
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

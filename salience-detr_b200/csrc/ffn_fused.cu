@@ -433,7 +433,7 @@ extern "C" int sdetr_ffn_fused_set_balance(int enable /* 1 (default): equal chun
 // persistent CTAs for M rows: one per SM, but at least two chunks each (balance) / one panel each (whole panels)
 static int ffn_grid(int M, int chunks, int balance) {
     const int cap = g_ffn_max_ctas.load();
-    const long long sms = cap > 0 && cap < sm_count() ? cap : sm_count();
+    const long long sms = cap > 0 && cap < persistent_ctas() ? cap : persistent_ctas();
     const long long panels = (M + 127) / 128, most = balance ? (panels * chunks + 1) / 2 : panels;
     return (int)(most < sms ? (most > 0 ? most : 1) : sms);
 }

@@ -628,7 +628,7 @@ extern "C" int sdetr_gemm_f16x3_pre(const float *A, int64_t lda, const void *W_h
     SDETR_OPT_IN_SMEM(once_8, (gemm_f16x3_kernel<false, 8>), kHSmem, "gemm_f16x3_pre");
     SDETR_OPT_IN_SMEM(once_cl, (gemm_f16x3_kernel<true, 4>), kHSmem, "gemm_f16x3_pre");
     SDETR_OPT_IN_SMEM(once_as, gemm_f16x3_as_kernel, kAsSmem, "gemm_f16x3_pre");
-    const int sms = sm_count();
+    const int sms = persistent_ctas();
     HGemmParams p{bias, C, ldc, M, N, K, act, use_tma_store, 1.f / (kActScale * w_scale), g_f16_epi.load(), g_f16_dbg.load()};
     const int n_tiles = (N + kHN - 1) / kHN, m_tiles = (M + kHM - 1) / kHM;
     const int group = (g_f16_as.load() && K <= kMaxKb * kHK) ? pick_group(m_tiles, n_tiles, sms) : 1;
