@@ -23,6 +23,9 @@ def init_from_env(backend: Optional[str] = None, device: Optional[torch.device] 
         return False
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29500")
+    # NCCL's version banner / NCCL_DEBUG output goes to stdout by default; callers that print machine-readable results there
+    # (bench.py: ONE JSON line) need it on stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
     kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
     dist.init_process_group(backend, rank=rank, world_size=world, **kw)
