@@ -118,17 +118,30 @@ def _check(rc: int, what: str):
         raise RuntimeError(f"{what} failed (rc={rc}): {lib().sdetr_last_error().decode()}")
 
 
+# The eager path issues ~120 launches per forward from Python; `torch.cuda.current_stream()` / `current_device()` cost several
+# microseconds each (device-index resolution, Stream object construction) and were a third of the host time per forward
+# (tools/profile_eager_cpu.py).  The raw accessors below return the same values.
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def _stream() -> int:
+    if _raw_stream is not None and _raw_device is not None:
+        return _raw_stream(_raw_device())
     return torch.cuda.current_stream().cuda_stream
+
+
+def _current_device() -> int:
+    return _raw_device() if _raw_device is not None else torch.cuda.current_device()
 
 
 def _req(t: torch.Tensor, name: str, dtype=None):
     # same contract as the reference's AT_ASSERTM checks -> RuntimeError
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor")
-    if t.device.index != torch.cuda.current_device():
+    if t.device.index != _current_device():
         # the call launches on the CURRENT device's current stream; a tensor of another device would be dereferenced there
-        raise RuntimeError(f"{name} lives on {t.device} but cuda:{torch.cuda.current_device()} is current: "
+        raise RuntimeError(f"{name} lives on {t.device} but cuda:{_current_device()} is current: "
                            f"wrap the call in `with torch.cuda.device({t.device.index}):`")
     if not t.is_contiguous():
         raise RuntimeError(f"{name} tensor has to be contiguous")

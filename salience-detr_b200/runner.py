@@ -76,6 +76,88 @@ class HostPipeline:
         return n
 
 
+class FreshMaskPipeline:
+    """Host -> device -> host streaming for batches whose PADDING MASKS DIFFER from batch to batch (the detector's normal input:
+    every batch is padded to its own largest image).  Nothing derived from the masks can be reused, and the top-k sizes of the
+    plan are host integers, so a captured graph cannot be replayed: each batch runs ``make_plan`` (two launches + one small
+    device -> host copy) and an EAGER ``forward_encoder``.  What can still overlap does: the H2D copy of batch i+1 (copy
+    stream), the plan of batch i+1 (its own stream, so the host round trip waits for the mask copy and two small kernels only, not
+    for the forwards in flight), the forward of batch i (lane stream) and the D2H copy of batch i-1 (second copy stream).  The host
+    issues ~120 launches per forward, which is what bounds the rate once the copies are hidden (tools/profile_eager_cpu.py).
+
+    All batches must have the padded geometry (level shapes, batch size) of the ``feats`` / ``masks`` given here."""
+
+    def __init__(self, model: SalienceTransformer, feats, masks, depth: int = 3, use_order: bool = True):
+        self.model = model.eval()
+        self.dev = feats[0].device
+        self.use_order = use_order
+        self.depth = depth
+        self.feats = [[torch.empty_like(f) for f in feats] for _ in range(depth)]
+        self.masks = [[torch.empty_like(m) for m in masks] for _ in range(depth)]
+        self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(depth)]
+        self.h2d = torch.cuda.Stream(device=self.dev)
+        self.d2h = torch.cuda.Stream(device=self.dev)
+        self.plan_stream = torch.cuda.Stream(device=self.dev, priority=-1)
+        self.done = [None] * depth
+        self.computed = [None] * depth
+        self.keep = [None] * depth       # the lane's plan / output tensors stay referenced until its buffers are reused
+        self.host_out = None
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in list(feats) + list(masks))
+        self.d2h_bytes = 0
+
+    def run(self, batches, on_output=None):
+        """batches: iterable of (feats_host, masks_host) pinned-memory level lists.  ``on_output(i, host_memory)`` as in
+        ``HostPipeline.run``.  Returns the number processed."""
+        n = 0
+        for i, (feats_h, masks_h) in enumerate(batches):
+            k = i % self.depth
+            if self.computed[k] is not None:
+                self.h2d.wait_event(self.computed[k])
+            if self.done[k] is not None:
+                self.done[k].synchronize()       # also bounds how far the host runs ahead of the device
+                if on_output is not None:
+                    on_output(i - self.depth, self.host_out[k])
+            with torch.cuda.stream(self.h2d):
+                for dst, src in zip(self.masks[k], masks_h):   # masks first: the plan needs only them
+                    dst.copy_(src, non_blocking=True)
+                masks_ready = torch.cuda.Event()
+                masks_ready.record(self.h2d)
+                for dst, src in zip(self.feats[k], feats_h):
+                    dst.copy_(src, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(self.h2d)
+            self.plan_stream.wait_event(masks_ready)
+            with torch.cuda.stream(self.plan_stream), torch.no_grad():
+                plan = self.model.make_plan(self.masks[k])   # host round trip: waits for the mask copy and the plan kernels only
+                planned = torch.cuda.Event()
+                planned.record(self.plan_stream)
+            s = self.streams[k]
+            s.wait_event(planned)
+            s.wait_event(ready)
+            with torch.cuda.stream(s), torch.no_grad():
+                mem, _ = self.model.forward_encoder(self.feats[k], self.masks[k], None, plan=plan, use_order=self.use_order)
+                computed = torch.cuda.Event()
+                computed.record(s)
+            self.computed[k] = computed
+            if self.host_out is None:
+                self.host_out = [torch.empty(mem.shape, dtype=torch.float32, pin_memory=True) for _ in range(self.depth)]
+                self.d2h_bytes = mem.numel() * 4
+            self.d2h.wait_event(computed)
+            with torch.cuda.stream(self.d2h):
+                self.host_out[k].copy_(mem, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.d2h)
+            self.done[k] = ev
+            self.keep[k] = (plan, mem)
+            n += 1
+        for i in range(max(0, n - self.depth), n):
+            k = i % self.depth
+            self.done[k].synchronize()
+            if on_output is not None:
+                on_output(i, self.host_out[k])
+        return n
+
+
 class EncoderRunner:
     def __init__(self, model: SalienceTransformer, feats: Sequence[torch.Tensor], masks: Sequence[torch.Tensor],
                  pos: Sequence[torch.Tensor], use_graph: bool = True, use_order: bool = True, warmup: int = 2):

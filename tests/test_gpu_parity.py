@@ -914,6 +914,36 @@ def test_encoder_runner_graph_matches_eager(pkg):
         assert torch.equal(h.to(DEV), want)
 
 
+def test_fresh_mask_pipeline(pkg):
+    """FreshMaskPipeline: batches with DIFFERENT padding masks (each pays its own plan and an eager forward; copies, plans and
+    forwards of consecutive batches overlap) give exactly the eager result of their own masks, in order."""
+    from salience_detr_b200.runner import FreshMaskPipeline
+    from salience_detr_b200.position_encoding import PositionEmbeddingSine
+    g, sd = load_golden("encoder_tiny_ragged")
+    tr = _tiny_model(pkg, sd)
+    tr.attach_position_embedding(PositionEmbeddingSine(tr.embed_dim // 2, temperature=10000, normalize=True, offset=-0.5))
+    feats, masks, _ = _golden_inputs(g)
+    masks_b = [torch.zeros_like(m) for m in masks]                     # no padding at all
+    masks_c = [m.clone() for m in masks]
+    for m in masks_c:                                                  # a different ragged padding: last column block padded
+        m[:, :, -max(1, m.shape[2] // 3):] = True
+    feats2 = [f * 0.5 + 0.1 for f in feats]
+    variants = [(feats, masks), (feats2, masks_b), (feats, masks_c), (feats2, masks)]
+    wants = []
+    with torch.no_grad():
+        for f, m in variants:
+            wants.append(tr.forward_encoder(f, m, None)[0].clone())
+    assert not torch.equal(wants[0], wants[2])
+    pipe = FreshMaskPipeline(tr, feats, masks, depth=2)
+    pin = lambda ts: [t.cpu().pin_memory() for t in ts]  # noqa: E731
+    batches = [(pin(f), pin(m)) for f, m in variants] * 2
+    outs = {}
+    n = pipe.run(batches, on_output=lambda i, h: outs.__setitem__(i, h.clone()))
+    assert n == 8 and sorted(outs) == list(range(8))
+    for i in range(8):
+        assert torch.equal(outs[i].to(DEV), wants[i % 4]), i
+
+
 def test_encoder_training_path_gradients(pkg):
     """Training path (torch autograd around the MSDA forward / backward kernels) against the REFERENCE's own autograd
     (tests/golden/encoder_tiny_even_grads.npz, oracle/make_golden.py::make_encoder_tiny_grads): loss and the gradient of

@@ -1,13 +1,9 @@
 #!/bin/bash
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-for c in 0 140 132 120; do
-(timeout 600 python bench.py --skip-cpu-baseline --e2e-persistent-ctas $c > gpurun_out/r2_o_bench_c$c.json) 2> gpurun_out/r2_o_bench_c$c.err
-done
+timeout 300 python tools/profile_eager_cpu.py 2>&1 | tail -45 > gpurun_out/r2_eager_cpu_profile2.txt; head -36 gpurun_out/r2_eager_cpu_profile2.txt | cut -c1-150
+(timeout 600 python bench.py --skip-cpu-baseline > gpurun_out/r2_o_bench_f.json) 2> gpurun_out/r2_o_bench_f.err
 python - <<'PY'
 import json
-for c in (0, 140, 132, 120):
-    try:
-        j=json.load(open(f'gpurun_out/r2_o_bench_c{c}.json')); print(c, j['value'], j['ms_per_step'], j['e2e']['value'], j['e2e']['serial_value'], j['e2e']['fresh_masks_value'])
-    except Exception as e: print(c, 'ERR', e)
+j=json.load(open('gpurun_out/r2_o_bench_f.json')); print(j['value'], j['ms_per_step'], 'e2e', j['e2e']['value'], 'serial', j['e2e']['serial_value'], 'fresh', j['e2e']['fresh_masks_value'], 'fresh serial', j['e2e']['fresh_masks_serial_value'])
 PY
