@@ -367,6 +367,17 @@ int sdetr_split_f16_pair(const float *W, int64_t count, float scale, void *W_hi,
  * C row pitch ldc (TMA stores when ldc % 4 == 0). */
 int sdetr_gemm_f16x3_pre(const float *A, int64_t lda, const void *W_hi, const void *W_lo, float w_scale, const float *bias,
                          float *C, int64_t ldc, int M, int N, int K, int act, sdetr_stream_t stream);
+/* The same product with BOTH scales as device scalars (powers of two; sdetr_pow2_scale): the kernel multiplies A by *a_scale_dev
+ * instead of the fixed 16 (activations of unknown magnitude: gradients), the weight pair was split with *w_scale_dev
+ * (sdetr_split_f16_pair_dev: weights that change every training step, no host read of max|W|), and the epilogue divides both out.
+ * No host synchronisation anywhere.  No fused input activation. */
+int sdetr_gemm_f16x3_scaled(const float *A, int64_t lda, const float *a_scale_dev, const void *W_hi, const void *W_lo,
+                            const float *w_scale_dev, const float *bias, float *C, int64_t ldc, int M, int N, int K,
+                            sdetr_stream_t stream);
+int sdetr_split_f16_pair_dev(const float *W, int64_t count, const float *scale_dev, void *W_hi, void *W_lo, sdetr_stream_t stream);
+/* *scale = 2^s with max|x| * 2^s in [2^(target_log2 - 1), 2^target_log2) (1 for an all-zero x); one launch, deterministic.
+ * state: 8 bytes of device memory, zero before the first call (the kernel leaves them zero). */
+int sdetr_pow2_scale(const float *x, int64_t count, int target_log2, void *state, float *scale, sdetr_stream_t stream);
 /* benchmarking knob: 0 (default) = always the streaming kernel, 1 = K <= 256 and >= 2 output tiles per work unit use the
  * activation-stationary kernel (the split activation panel stays in tensor memory across the unit's output tiles) */
 int sdetr_gemm_f16x3_set_as(int enable);

@@ -69,6 +69,9 @@ SIGNATURES = {
     "sdetr_gemm_f16x3_set_epilogue_warps": (_i, [_i]),
     "sdetr_gemm_f16x3_set_trace": (_i, [_vp]),
     "sdetr_gemm_f16x3_pre": (_i, [_vp, _i64, _vp, _vp, _f, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "sdetr_gemm_f16x3_scaled": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp]),
+    "sdetr_split_f16_pair_dev": (_i, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "sdetr_pow2_scale": (_i, [_vp, _i64, _i, _vp, _vp, _vp]),
     "sdetr_mask_predictor_level_workspace_floats": (_i64, [_i, _i, _i]),
     "sdetr_mask_predictor_level": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _i64, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
@@ -724,6 +727,53 @@ def ffn_fused_layernorm(x, w1, b1, w2, b2, gamma=None, beta=None, eps: float = 1
         y.data_ptr(), _stream())
     _check(rc, "sdetr_ffn_fused_layernorm")
     return y if out is not None else y.reshape(x.shape)
+
+
+_pow2_state = {}
+
+
+def pow2_scale(x, target_log2: int = 12):
+    """Device scalar 2^s with max|x| * 2^s in [2^(target_log2 - 1), 2^target_log2); no host synchronisation."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+        raise RuntimeError("pow2_scale needs a contiguous CUDA float32 tensor")
+    key = (x.device.index, _stream())
+    st = _pow2_state.get(key)
+    if st is None:
+        st = _pow2_state[key] = torch.zeros(2, device=x.device, dtype=torch.int32)  # per (device, stream): calls are stream-ordered
+    out = torch.empty(1, device=x.device, dtype=torch.float32)
+    _check(lib().sdetr_pow2_scale(x.data_ptr(), x.numel(), int(target_log2), st.data_ptr(), out.data_ptr(), _stream()), "sdetr_pow2_scale")
+    return out
+
+
+def split_f16_pair_dev(w, scale=None):
+    """(W_hi, W_lo, scale) with the power-of-two scale computed and kept ON THE DEVICE (training: the weights change every step)."""
+    w = w if w.is_contiguous() else w.contiguous()
+    scale = pow2_scale(w, 14) if scale is None else scale
+    hi = torch.empty(w.shape, device=w.device, dtype=torch.float16)
+    lo = torch.empty_like(hi)
+    _check(lib().sdetr_split_f16_pair_dev(_req(w, "w", torch.float32), w.numel(), scale.data_ptr(), hi.data_ptr(), lo.data_ptr(), _stream()),
+           "sdetr_split_f16_pair_dev")
+    return hi, lo, scale
+
+
+def gemm_f16x3_scaled(x, a_scale, w_hi, w_lo, w_scale, bias=None):
+    """y = x @ W.T + bias; ``a_scale`` / ``w_scale``: device scalars (pow2_scale / split_f16_pair_dev) -- no host synchronisation."""
+    K = x.shape[-1]
+    N = w_hi.shape[0]
+    if not (x.is_cuda and x.dtype == torch.float32 and x.stride(-1) == 1):
+        raise RuntimeError("gemm_f16x3_scaled needs a CUDA float32 input with unit last stride")
+    x2 = x if x.dim() == 2 else x.reshape(-1, K)
+    M = x2.shape[0]
+    ldc = (N + 3) // 4 * 4
+    # the result must not be a view (autograd Functions hand it out, and in-place ops on it are legal): final shape when N % 4 == 0
+    y = torch.empty(*x.shape[:-1], N, device=x.device, dtype=torch.float32) if ldc == N else torch.empty(M, ldc, device=x.device, dtype=torch.float32)
+    rc = lib().sdetr_gemm_f16x3_scaled(x2.data_ptr(), x2.stride(0) if M > 1 else K, _req(a_scale, "a_scale", torch.float32),
+                                       _req(w_hi, "w_hi", torch.float16), _req(w_lo, "w_lo", torch.float16),
+                                       _req(w_scale, "w_scale", torch.float32),
+                                       _req(bias, "bias", torch.float32) if bias is not None else None, y.data_ptr(), ldc, M, N, K,
+                                       _stream())
+    _check(rc, "sdetr_gemm_f16x3_scaled")
+    return y if ldc == N else y[:, :N].contiguous().reshape(*x.shape[:-1], N)
 
 
 def rows_gather_add(src, pos, index):

@@ -55,6 +55,9 @@ struct HGemmParams {
     int64_t ldc;
     int M, N, K, act, use_tma_store;
     float out_scale;  // 1 / (kActScale * weight scale), a power of two
+    const float *a_scale_dev;  // optional device scalars (powers of two): activation scale replacing kActScale (activations of
+    const float *w_scale_dev;  // unknown magnitude: gradients) and the scale the weight pair was split with (weights that change
+                               // every step: no host read of max|W|); the epilogue then uses 1 / (a * w)
     int epilogue;     // streaming kernel: 0 = shared boxes + TMA stores, 1 = warp-private boxes + coalesced 128-bit global stores
     long long *dbg;   // optional clock64() trace of CTA 0: [event][index < 256] (sdetr_gemm_f16x3_set_trace, tools/gemm_trace2.py; 10 events)
 };
@@ -177,6 +180,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     } else if (warp >= 4 && warp < 12) {
         // ===== converters: landed fp32 A boxes -> scaled, split, packed f16x2 -> TMEM slot =====
         const int q = warp & 3, half = (warp - 4) >> 2, r_in = q * 32 + lane;
+        const float ascale = p.a_scale_dev ? __ldg(p.a_scale_dev) : kActScale;
         uint32_t it = 0;
         for (int tile = first; tile < tiles; tile += step) {
             for (int kb = 0; kb < nk; ++kb, ++it) {
@@ -193,8 +197,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     } else if (p.act == 2) {
                         x.x = gelu_erf(x.x), x.y = gelu_erf(x.y), x.z = gelu_erf(x.z), x.w = gelu_erf(x.w);
                     }
-                    split2(x.x * kActScale, x.y * kActScale, hi[2 * c], lo[2 * c]);
-                    split2(x.z * kActScale, x.w * kActScale, hi[2 * c + 1], lo[2 * c + 1]);
+                    split2(x.x * ascale, x.y * ascale, hi[2 * c], lo[2 * c]);
+                    split2(x.z * ascale, x.w * ascale, hi[2 * c + 1], lo[2 * c + 1]);
                 }
                 const uint32_t slot = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + 64u * (uint32_t)s + 16u * (uint32_t)half;
                 tmem_st16u(slot, hi);
@@ -215,7 +219,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const bool tracer = threadIdx.x == 12 * 32;
         constexpr int kBlocksPerGroup = (kHN / 32) / (EW / 4);
         const int c_begin = grp * kBlocksPerGroup, c_end = c_begin + kBlocksPerGroup;
-        const float sc = p.out_scale;
+        const float sc = p.a_scale_dev ? 1.f / (__ldg(p.a_scale_dev) * __ldg(p.w_scale_dev)) : p.out_scale;
         uint32_t tc = 0, box_it = 0;
         uint8_t *wbox = boxes + (warp - 12) * 4096;  // epilogue variant 1: this warp's private 32-row x 128-byte box
         const int et = threadIdx.x - 12 * 32;        // 0 .. 32 * EW - 1 within the epilogue warps
@@ -604,9 +608,9 @@ extern "C" int sdetr_split_f16_pair(const float *w, int64_t count, float scale, 
     return check_launch("split_f16_pair");
 }
 
-extern "C" int sdetr_gemm_f16x3_pre(const float *A, int64_t lda, const void *W_hi, const void *W_lo, float w_scale,
-                                    const float *bias, float *C, int64_t ldc, int M, int N, int K, int act,
-                                    sdetr_stream_t stream) {
+static int gemm_f16x3_impl(const float *A, int64_t lda, const void *W_hi, const void *W_lo, float w_scale, const float *a_scale_dev,
+                           const float *w_scale_dev,
+                           const float *bias, float *C, int64_t ldc, int M, int N, int K, int act, sdetr_stream_t stream) {
     SDETR_REQUIRE(A && W_hi && W_lo && C, SDETR_ERR_INVALID_ARG, "gemm_f16x3_pre: null pointer");
     SDETR_REQUIRE(M >= 0 && N > 0 && K > 0 && act >= 0 && act <= 2, SDETR_ERR_INVALID_ARG, "gemm_f16x3_pre: bad sizes / activation");
     SDETR_REQUIRE(K % kHK == 0, SDETR_ERR_UNSUPPORTED, "gemm_f16x3_pre: K=%d must be a multiple of %d", K, kHK);
@@ -629,9 +633,9 @@ extern "C" int sdetr_gemm_f16x3_pre(const float *A, int64_t lda, const void *W_h
     SDETR_OPT_IN_SMEM(once_cl, (gemm_f16x3_kernel<true, 4>), kHSmem, "gemm_f16x3_pre");
     SDETR_OPT_IN_SMEM(once_as, gemm_f16x3_as_kernel, kAsSmem, "gemm_f16x3_pre");
     const int sms = persistent_ctas();
-    HGemmParams p{bias, C, ldc, M, N, K, act, use_tma_store, 1.f / (kActScale * w_scale), g_f16_epi.load(), g_f16_dbg.load()};
+    HGemmParams p{bias, C, ldc, M, N, K, act, use_tma_store, 1.f / (kActScale * w_scale), a_scale_dev, w_scale_dev, g_f16_epi.load(), g_f16_dbg.load()};
     const int n_tiles = (N + kHN - 1) / kHN, m_tiles = (M + kHM - 1) / kHM;
-    const int group = (g_f16_as.load() && K <= kMaxKb * kHK) ? pick_group(m_tiles, n_tiles, sms) : 1;
+    const int group = (g_f16_as.load() && !a_scale_dev && K <= kMaxKb * kHK) ? pick_group(m_tiles, n_tiles, sms) : 1;  // (the AS variant has the fixed activation scale only)
     if (group >= 2) {  // a one-tile unit re-uses nothing: the streaming kernel pipelines it better
         const long long units = (long long)m_tiles * ((n_tiles + group - 1) / group);
         gemm_f16x3_as_kernel<<<(int)(units < sms ? units : sms), kHThreads, kAsSmem, (cudaStream_t)stream>>>(ma, mh, ml, mc, p, group);
@@ -658,4 +662,93 @@ extern "C" int sdetr_gemm_f16x3_pre(const float *A, int64_t lda, const void *W_h
     else
         gemm_f16x3_kernel<false, 4><<<tiles < sms ? tiles : sms, kHThreads, kHSmem, (cudaStream_t)stream>>>(ma, mh, ml, mc, p);
     return check_launch("gemm_f16x3_pre");
+}
+
+extern "C" int sdetr_gemm_f16x3_pre(const float *A, int64_t lda, const void *W_hi, const void *W_lo, float w_scale,
+                                    const float *bias, float *C, int64_t ldc, int M, int N, int K, int act,
+                                    sdetr_stream_t stream) {
+    return gemm_f16x3_impl(A, lda, W_hi, W_lo, w_scale, nullptr, nullptr, bias, C, ldc, M, N, K, act, stream);
+}
+
+extern "C" int sdetr_gemm_f16x3_scaled(const float *A, int64_t lda, const float *a_scale_dev, const void *W_hi, const void *W_lo,
+                                       const float *w_scale_dev, const float *bias, float *C, int64_t ldc, int M, int N, int K,
+                                       sdetr_stream_t stream) {
+    SDETR_REQUIRE(a_scale_dev && w_scale_dev, SDETR_ERR_INVALID_ARG, "gemm_f16x3_scaled: null scale pointer");
+    return gemm_f16x3_impl(A, lda, W_hi, W_lo, 1.f, a_scale_dev, w_scale_dev, bias, C, ldc, M, N, K, 0, stream);
+}
+
+namespace sdetr {
+__global__ void split_f16_pair_dev_kernel(const float *__restrict__ w, int64_t n, const float *__restrict__ scale_dev,
+                                          __half *__restrict__ hi, __half *__restrict__ lo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = w[i] * __ldg(scale_dev);
+    const __half h = __float2half_rn(x);
+    hi[i] = h, lo[i] = __float2half_rn(x - __half2float(h));
+}
+}  // namespace sdetr
+
+extern "C" int sdetr_split_f16_pair_dev(const float *w, int64_t count, const float *scale_dev, void *w_hi, void *w_lo,
+                                        sdetr_stream_t stream) {
+    SDETR_REQUIRE(w && scale_dev && w_hi && w_lo, SDETR_ERR_INVALID_ARG, "split_f16_pair_dev: null pointer");
+    if (count <= 0) return SDETR_OK;
+    split_f16_pair_dev_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        w, count, scale_dev, reinterpret_cast<__half *>(w_hi), reinterpret_cast<__half *>(w_lo));
+    return check_launch("split_f16_pair_dev");
+}
+
+// ---- power-of-two scale that brings max|x| to [2^(t-1), 2^t): one launch (the last block to finish publishes the result) ----
+namespace sdetr {
+__global__ void __launch_bounds__(256) pow2_scale_kernel(const float *__restrict__ x, int64_t n, int target_log2,
+                                                         unsigned int *__restrict__ state /* [0] max bits, [1] blocks done */,
+                                                         float *__restrict__ scale) {
+    float m = 0.f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 3 < n) {
+            const float4 v = ld_stream_f4(x + i);
+            m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        } else {
+            for (int64_t j = i; j < n; ++j) m = fmaxf(m, fabsf(x[j]));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float wm[8];
+    __shared__ bool last;
+    if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, wm[w]);
+        if (!(m <= 3.0e38f)) m = 3.0e38f;                 // NaN / inf: the GEMM propagates them whatever the scale
+        atomicMax(state, __float_as_uint(m));             // non-negative floats order like their bit patterns
+        __threadfence();
+        last = atomicAdd(state + 1, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        const float amax = __uint_as_float(atomicAdd(state, 0u));
+        int e = 0;
+        float s = 1.f;
+        if (amax > 0.f) {
+            frexpf(amax, &e);                              // amax = f * 2^e, f in [0.5, 1)
+            int sh = target_log2 - e;                      // amax * 2^sh in [2^(t-1), 2^t)
+            sh = sh > 60 ? 60 : (sh < -60 ? -60 : sh);         // the product of two such scales stays finite
+            s = ldexpf(1.f, sh);
+        }
+        *scale = s;
+        state[0] = 0u, state[1] = 0u;                      // ready for the next call on this stream
+    }
+}
+}  // namespace sdetr
+
+extern "C" int sdetr_pow2_scale(const float *x, int64_t count, int target_log2, void *state /* 8 zeroed bytes */, float *scale,
+                                sdetr_stream_t stream) {
+    SDETR_REQUIRE(x && state && scale, SDETR_ERR_INVALID_ARG, "pow2_scale: null pointer");
+    SDETR_REQUIRE(count > 0 && target_log2 >= -100 && target_log2 <= 100 && aligned16(x), SDETR_ERR_INVALID_ARG, "pow2_scale: bad arguments");
+    const int64_t want = (count / 4 + 255) / 256;
+    const int blocks = (int)(want < 1 ? 1 : (want > 4 * sm_count() ? 4 * sm_count() : want));
+    pow2_scale_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, count, target_log2, reinterpret_cast<unsigned int *>(state), scale);
+    return check_launch("pow2_scale");
 }

@@ -157,3 +157,96 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, relu_input:
             for c in range(1, K // kc):
                 y.addmm_(x3[:, 3 * kc * c:3 * kc * (c + 1)], w3[:, 3 * kc * c:3 * kc * (c + 1)].t())
     return y.view(*x.shape[:-1], weight.shape[0])
+
+
+# ---- training path: tensor-core Linear with autograd ---------------------------------------------------------------------------
+TRAIN_TENSOR_CORE = __import__("os").environ.get("SDETR_TRAIN_TENSOR_CORE", "1") != "0"
+_train_cache: Dict[int, tuple] = {}
+_const16: Dict[int, Tensor] = {}
+
+
+def _train_splits(weight: Tensor):
+    """Per parameter VERSION (the optimizer bumps it every step): device-side power-of-two scale, the 3xFP16 split of W (for y)
+    and of W^T (for dx).  Everything stays on the device -- no host read of max|W|, unlike ``split_weight_f16``."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape))
+    hit = _train_cache.get(id(weight))
+    capturing = weight.is_cuda and torch.cuda.is_current_stream_capturing()
+    # inside a CUDA-graph capture of a training step the split kernels must be PART of the graph (the optimizer rewrites the
+    # weights on every replay, and no Python runs then): never serve a capture from the cache, never cache what it produced
+    if capturing or hit is None or hit[0] != key or hit[2]() is not weight:
+        with torch.no_grad():
+            w = weight.detach()
+            scale = cabi.pow2_scale(w if w.is_contiguous() else w.contiguous(), 14)
+            fwd = cabi.split_f16_pair_dev(w, scale)
+            bwd = cabi.split_f16_pair_dev(w.t().contiguous(), scale) if w.shape[0] % 64 == 0 else None
+        hit = (key, (fwd, bwd), weakref.ref(weight))
+        if capturing:
+            return hit[1]
+        _prune(_train_cache)
+        _train_cache[id(weight)] = hit
+    return hit[1]
+
+
+class _LinearF16x3(torch.autograd.Function):
+    """y = x W^T + b on the 3xFP16 tensor-core kernel, forward AND the input gradient (dx = dy W: the same kernel on W^T, with dy
+    scaled by a device-side power of two -- gradients are far below the fixed activation range of the inference entry point);
+    dW = dy^T x stays on cuBLAS fp32 (a K = rows reduction into a small output: split-K territory, which the persistent kernel
+    does not do)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        (w_hi, w_lo, w_scale), ctx.bwd = _train_splits(weight)   # the W^T split rides along for the input gradient
+        c16 = _const16.get(x.device.index)
+        if c16 is None:
+            c16 = _const16[x.device.index] = torch.full((1,), 16.0, device=x.device)
+        x2 = x if x.stride(-1) == 1 else x.contiguous()
+        y = cabi.gemm_f16x3_scaled(x2, c16, w_hi, w_lo, w_scale, bias)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        dy2 = dy2 if dy2.is_contiguous() else dy2.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            bwd = ctx.bwd
+            if bwd is not None:
+                dx = cabi.gemm_f16x3_scaled(dy2, cabi.pow2_scale(dy2, 12), bwd[0], bwd[1], bwd[2]).reshape(x.shape)
+            else:
+                dx = (dy2 @ weight).reshape(x.shape)
+        if ctx.needs_input_grad[1]:
+            dw = dy2.t() @ x.reshape(-1, x.shape[-1])
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy2.sum(0)
+        return dx, dw, db
+
+
+def linear_train(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tensor:
+    """Differentiable ``F.linear`` for the training path: tensor cores where the shapes allow (K % 64 == 0, more than SMALL_M
+    rows, fp32 CUDA), ``F.linear`` otherwise."""
+    rows = x.numel() // max(x.shape[-1], 1)
+    if (TRAIN_TENSOR_CORE and MODE == "auto" and OWN_KERNEL == "f16x3" and x.is_cuda and x.dtype == torch.float32 and
+            weight.dtype == torch.float32 and x.shape[-1] % 64 == 0 and rows > SMALL_M and weight.dim() == 2):
+        return _LinearF16x3.apply(x, weight, bias)
+    return _orig_linear(x, weight, bias)
+
+
+_orig_linear = F.linear
+
+
+@contextlib.contextmanager
+def tensor_core_linears():
+    """Inside: every ``torch.nn.functional.linear`` (``nn.Linear.forward``, ``nn.MultiheadAttention``) of the training path goes
+    through ``linear_train``.  Used by ``SalienceTransformer.forward_encoder`` when gradients are enabled."""
+    if not TRAIN_TENSOR_CORE:
+        yield
+        return
+    prev = torch.nn.functional.linear
+    torch.nn.functional.linear = linear_train
+    try:
+        yield
+    finally:
+        torch.nn.functional.linear = prev

@@ -359,15 +359,16 @@ class SalienceTransformerEncoder(nn.Module):
 
     def forward(self, query, spatial_shapes, level_start_index, valid_ratios, query_pos=None,
                 query_key_padding_mask=None, foreground_score=None, focus_token_nums=None, foreground_inds=None,
-                multi_level_masks=None, query_orders=None, value_buffer=None):
-        """Reference signature (:434-447) + optional ``query_orders`` (per-layer int32 processing orders).
+                multi_level_masks=None, query_orders=None, value_buffer=None, focus_host=None):
+        """Reference signature (:434-447) + optional ``query_orders`` (per-layer int32 processing orders) and ``focus_host`` (the
+        focus counts as host ints: the training path then needs no device -> host copy and can be captured in a CUDA graph).
 
         query/query_pos (b,Nv,C); foreground_inds: list of (b,Nq_j) int64 (prefix views of one selected_inds);
         focus_token_nums (b,) int; -> encoder memory (b,Nv,C)."""
         if torch.is_grad_enabled() and (query.requires_grad or any(p.requires_grad for p in self.parameters())):
             return self._forward_autograd(query, spatial_shapes, level_start_index, valid_ratios, query_pos,
                                           query_key_padding_mask, foreground_score, focus_token_nums, foreground_inds,
-                                          multi_level_masks)
+                                          multi_level_masks, focus_host)
         b, nv, c = query.shape
         L = spatial_shapes.shape[0]
         M = self.layers[0].self_attn.num_heads
@@ -429,13 +430,16 @@ class SalienceTransformerEncoder(nn.Module):
         return out
 
     def _forward_autograd(self, query, spatial_shapes, level_start_index, valid_ratios, query_pos,
-                          query_key_padding_mask, foreground_score, focus_token_nums, foreground_inds, multi_level_masks):
-        """Training path: torch autograd around the custom MSDA Function (forward + backward kernels)."""
+                          query_key_padding_mask, foreground_score, focus_token_nums, foreground_inds, multi_level_masks,
+                          focus_host=None):
+        """Training path: torch autograd around the custom MSDA Function (forward + backward kernels).  With the level shapes
+        (from the masks) and ``focus_host`` known on the host there is no device -> host copy in it."""
         b, nv, c = query.shape
-        ref = self.get_reference_points(spatial_shapes, valid_ratios, query.device)
+        shapes = [tuple(m.shape[-2:]) for m in multi_level_masks] if multi_level_masks is not None else spatial_shapes
+        ref = self.get_reference_points(shapes, valid_ratios, query.device)
         L = ref.shape[2]
         value = output = query
-        focus = focus_token_nums.tolist()
+        focus = list(focus_host) if focus_host is not None else focus_token_nums.tolist()
         inds = None
         for j, layer in enumerate(self.layers):
             inds = foreground_inds[j]
@@ -652,7 +656,16 @@ class SalienceTransformer(nn.Module):
                         plan: Optional[EncoderPlan] = None, use_order: bool = True):
         """(b,C,H_l,W_l) feats, (b,H_l,W_l) bool masks, (b,C,H_l,W_l) pos -> memory (b,Nv,C) + aux dict.
 
-        Reference lines 106-183.  Pass a cached ``plan`` (``make_plan``) to run with no host sync."""
+        Reference lines 106-183.  Pass a cached ``plan`` (``make_plan``) to run with no host sync.  With gradients enabled (training
+        path: torch autograd around the MSDA kernels) the ``nn.Linear`` layers run on the 3xFP16 tensor-core GEMM in forward and
+        input-gradient (``gemm.tensor_core_linears``)."""
+        grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if grad and multi_level_feats[0].is_cuda:
+            with gemm.tensor_core_linears():
+                return self._forward_encoder(multi_level_feats, multi_level_masks, multi_level_pos_embeds, plan, use_order)
+        return self._forward_encoder(multi_level_feats, multi_level_masks, multi_level_pos_embeds, plan, use_order)
+
+    def _forward_encoder(self, multi_level_feats, multi_level_masks, multi_level_pos_embeds, plan, use_order):
         if plan is None:
             plan = self.make_plan(multi_level_masks)
         grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
@@ -688,7 +701,7 @@ class SalienceTransformer(nn.Module):
             query=feat, query_pos=lpos, query_key_padding_mask=plan.mask_flat, spatial_shapes=plan.spatial_shapes,
             level_start_index=plan.level_start_index, valid_ratios=plan.valid_ratios, foreground_score=fg,
             focus_token_nums=plan.focus_token_nums, foreground_inds=layer_inds, multi_level_masks=multi_level_masks,
-            query_orders=orders, value_buffer=vbuf)
+            query_orders=orders, value_buffer=vbuf, focus_host=plan.focus_host)
         aux = dict(raw_score=raw, selected_inds=inds, selected_score=score, foreground_score=fg, plan=plan)
         return memory, aux
 

@@ -1296,3 +1296,48 @@ def test_mask_predictor_level(pkg):
         pkg.cabi.mask_predictor_level(mem, lead, h, w, again[:, lead + h * w:lead + h * w + hc * wc] if hc else None, hc, wc, alpha, 1,
                                       ln.weight, ln.bias, ln.eps, *mp.transposed_weights(), again, lead)
         assert torch.equal(again, raw)
+
+
+def test_linear_train_tensor_core(pkg):
+    """Training-path Linear on the 3xFP16 kernel (forward and input gradient with DEVICE-side power-of-two scales; weight gradient on
+    cuBLAS) against fp64 autograd: activations O(1), gradients of 1e-8 .. 1e+3 (far outside the fixed range of the inference entry
+    point), ragged N, bias / no bias, non-contiguous upstream gradient; pow2_scale itself; fallback shapes."""
+    g = torch.Generator().manual_seed(31)
+    F = torch.nn.functional
+    for n, tgt in [(1000, 12), (70001, 14), (3, 0)]:
+        x = (torch.randn(n, generator=g) * 10.0 ** float(torch.randint(-9, 4, (1,), generator=g))).to(DEV)
+        s = pkg.cabi.pow2_scale(x, tgt).item()
+        amax = x.abs().max().item()
+        assert 2.0 ** (tgt - 1) <= amax * s < 2.0 ** tgt and s == 2.0 ** round(__import__("math").log2(s))
+    assert pkg.cabi.pow2_scale(torch.zeros(100, device=DEV), 12).item() == 1.0
+    for rows, k, n, gscale, bias in [(3000, 256, 2048, 1e-7, True), (5000, 2048, 256, 3e2, True), (2500, 256, 384, 1e-3, False),
+                                     (4097, 64, 91, 1.0, True), (2400, 128, 64, 1e-5, True)]:
+        x = torch.randn(rows, k, generator=g).to(DEV).requires_grad_(True)
+        w = (torch.randn(n, k, generator=g) / k ** 0.5).to(DEV).requires_grad_(True)
+        b = torch.randn(n, generator=g).to(DEV).requires_grad_(True) if bias else None
+        dy = (torch.randn(n, rows, generator=g) * gscale).to(DEV).t()  # non-contiguous upstream gradient
+        y = pkg.gemm.linear_train(x, w, b)
+        assert y.grad_fn is not None and "LinearF16x3" in type(y.grad_fn).__name__
+        y.backward(dy)
+        x64, w64 = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+        b64 = b.detach().double().requires_grad_(True) if bias else None
+        y64 = F.linear(x64, w64, b64)
+        y64.backward(dy.double())
+        assert (y.detach().double() - y64.detach()).abs().max().item() < 2e-5 * y64.detach().abs().max().item()
+        for got, want in [(x.grad, x64.grad), (w.grad, w64.grad)] + ([(b.grad, b64.grad)] if bias else []):
+            err = (got.double() - want).abs().max().item()
+            assert err <= 3e-5 * want.abs().max().item(), (rows, k, n, gscale, err, want.abs().max().item())
+    # shapes the kernel does not take fall back to F.linear: few rows, K not a multiple of 64
+    for rows, k in [(100, 256), (5000, 100)]:
+        x = torch.randn(rows, k, device=DEV, requires_grad=True)
+        w = torch.randn(32, k, device=DEV, requires_grad=True)
+        y = pkg.gemm.linear_train(x, w, None)
+        assert "LinearF16x3" not in type(y.grad_fn).__name__
+    # the context manager routes nn.Linear through it and restores F.linear afterwards
+    lin = torch.nn.Linear(256, 512).to(DEV)
+    xin = torch.randn(4000, 256, device=DEV)
+    with pkg.gemm.tensor_core_linears():
+        out = lin(xin)
+    assert "LinearF16x3" in type(out.grad_fn).__name__ and torch.nn.functional.linear is pkg.gemm._orig_linear
+    assert (out - F.linear(xin, lin.weight, lin.bias)).abs().max().item() < 3e-5
+    torch.relu_(out)  # the Function's output is not a view: in-place ops on it are legal (the FFN's ReLU(inplace=True))

@@ -1,9 +1,15 @@
 #!/bin/bash
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 300 python tools/profile_eager_cpu.py 2>&1 | tail -45 > gpurun_out/r2_eager_cpu_profile2.txt; head -36 gpurun_out/r2_eager_cpu_profile2.txt | cut -c1-150
-(timeout 600 python bench.py --skip-cpu-baseline > gpurun_out/r2_o_bench_f.json) 2> gpurun_out/r2_o_bench_f.err
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "linear_train or training_path" 2>&1 | tail -8
+for c in 1 0; do
+(SDETR_TRAIN_TENSOR_CORE=$c timeout 600 python bench.py --mode train --steps 10 --warmup 3 > gpurun_out/r2_o_train_$c.json) 2> gpurun_out/r2_o_train_$c.err
+done
 python - <<'PY'
 import json
-j=json.load(open('gpurun_out/r2_o_bench_f.json')); print(j['value'], j['ms_per_step'], 'e2e', j['e2e']['value'], 'serial', j['e2e']['serial_value'], 'fresh', j['e2e']['fresh_masks_value'], 'fresh serial', j['e2e']['fresh_masks_serial_value'])
+for c in (1, 0):
+    try:
+        j=json.loads([l for l in open(f'gpurun_out/r2_o_train_{c}.json') if l.startswith('{')][-1]); print(c, j['value'], j['ms_per_step'], j['loss'], j['gpu_launches_per_step'])
+    except Exception as e: print(c, 'ERR', e)
 PY
+tail -3 gpurun_out/r2_o_train_1.err
