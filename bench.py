@@ -30,6 +30,25 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+# ONE JSON line on stdout, whatever the libraries print: NCCL writes its version banner (and NCCL_DEBUG output) to file descriptor 1
+# from C, past sys.stdout.  The real stdout is kept aside for the result line and descriptor 1 is pointed at stderr for the rest of
+# the process.
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: str):
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (line + "\n").encode())
+
+
 WORKLOAD = "resnet50_800_1333_bs2"
 METRIC = "images/sec encoder-fwd @ 800x1333 bs=2/GPU"
 L2_FLUSH_BYTES = 256 << 20
@@ -403,7 +422,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": kind,
                              "sample": f"{args.steps} full bs={b} encoder forwards"},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 def run_train(args, rank, world, local):
@@ -494,7 +513,7 @@ def run_train(args, rank, world, local):
     launches = pkg.cabi.launch_count() - n0
     reached = sum(p.numel() * 4 for p in params if p.grad is not None and bool((p.grad != 0).any()))
     if rank == 0:
-        print(json.dumps({
+        emit(json.dumps({
             "metric": "images/sec encoder fwd+bwd+grad-allreduce+SGD @ 800x1333 bs=2/GPU (training path)",
             "value": round(sdist.aggregate_throughput(bsz, steps, world, ms), 2), "unit": "images/s", "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": round(ms / steps, 3), "higher_is_better": True,
@@ -508,7 +527,7 @@ def run_train(args, rank, world, local):
                           "ms_per_step_without_allreduce": round(ms_nocomm / steps, 3),
                           "exposed_ms_per_step": round((ms - ms_nocomm) / steps, 3),
                           "bytes_with_nonzero_gradient": reached},
-            "gpu_launches_per_step": launches, "loss": float(loss.detach())}), flush=True)
+            "gpu_launches_per_step": launches, "loss": float(loss.detach())}))
     sys.stdout.flush()
     # Tear-down: graphs that captured NCCL kernels must die BEFORE the communicator (a process group destroyed first left the
     # N = 2 run hanging until the timeout killed it), and nothing after the result line may hang the launcher: a watchdog ends the
@@ -542,6 +561,7 @@ def main():
                     help="cap of the persistent GEMM / FFN kernels during the e2e (multi-lane) measurement; 0 = one CTA per SM")
     ap.add_argument("--pipeline-depth", type=int, default=4, help="lanes of the host-buffer pipeline (e2e)")
     args = ap.parse_args()
+    _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -773,7 +793,7 @@ def main():
         if world == 1 and not args.skip_cpu_baseline:
             line["gpu_comparator"] = gpu_comparator(model, feats, masks, pos)
             line["cpu_baseline"] = cpu_baseline(pkg, model)
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -1,12 +1,11 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-(timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --mode train --steps 10 --warmup 3 > gpurun_out/r2_train_n2_final.json) 2> gpurun_out/r2_train_n2_final.err
+(timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r2_scale_n2_final.json) 2> gpurun_out/r2_scale_n2_final.err
 echo "rc=$?"
 python - <<'PY'
 import json
-for f in ('r2_train_n2_final',):
-    try:
-        j=json.loads([l for l in open(f'gpurun_out/{f}.json') if l.startswith('{')][-1]); print(f, j['value'], j['ms_per_step'], j['config'].get('cuda_graph'), j.get('allreduce'), j['gpu_launches_per_step'])
-    except Exception as e: print(f, 'ERR', e)
+lines=open('gpurun_out/r2_scale_n2_final.json').read().splitlines()
+print('stdout lines:', len(lines))
+j=json.loads(lines[-1]); print(j['value'], j['ms_per_step'], 'e2e', j['e2e']['value'], 'fresh', j['e2e']['fresh_masks_value'], j['clocks'])
 PY
-grep -v "Warn\|^$\|\*\*\*\|OMP_NUM\|Consider\|gpu_launches" gpurun_out/r2_train_n2_final.err | tail -5
+grep -v "Warn\|^$\|\*\*\*\|OMP_NUM" gpurun_out/r2_scale_n2_final.err | tail -4
