@@ -130,3 +130,41 @@ def test_load_reference_checkpoint_layouts():
     m = fresh()
     rep = pkg.load_reference_checkpoint(m, bad)
     assert rep["mismatched"] == ["alpha"] and m.alpha.shape == (3,)
+
+
+def test_tensor_core_linears_context_on_cpu():
+    """gemm.tensor_core_linears routes torch.nn.functional.linear through gemm.linear_train and restores it (also on an exception);
+    tensors the kernel does not take (CPU, few rows, K % 64 != 0) fall back to the original F.linear with ordinary autograd."""
+    import torch
+    import salience_detr_b200 as pkg
+    F = torch.nn.functional
+    orig = F.linear
+    lin = torch.nn.Linear(64, 8)
+    x = torch.randn(5, 64, requires_grad=True)
+    with pkg.gemm.tensor_core_linears():
+        assert F.linear is pkg.gemm.linear_train
+        y = lin(x)
+    assert F.linear is orig
+    assert "LinearF16x3" not in type(y.grad_fn).__name__ and torch.allclose(y, orig(x, lin.weight, lin.bias))
+    y.sum().backward()
+    assert x.grad is not None and lin.weight.grad is not None
+    try:
+        with pkg.gemm.tensor_core_linears():
+            raise KeyError("boom")
+    except KeyError:
+        pass
+    assert F.linear is orig
+
+
+def test_masked_predictor_transposed_weight_cache_follows_updates():
+    """MaskPredictor.transposed_weights (the (in, out) weights sdetr_mask_predictor_level streams) is rebuilt when a parameter changes."""
+    import torch
+    from salience_detr_b200.salience_transformer import MaskPredictor
+    mp = MaskPredictor(256, 256)
+    t0 = mp.transposed_weights()
+    assert t0[0].shape == (256, 256) and t0[2].shape == (256, 128) and t0[4].shape == (128, 64) and t0[6].shape == (64,)
+    assert torch.equal(t0[0], mp.layer1[1].weight.t()) and mp.transposed_weights() is t0
+    with torch.no_grad():
+        mp.layer2[0].weight.add_(1.0)
+    t1 = mp.transposed_weights()
+    assert t1 is not t0 and torch.equal(t1[2], mp.layer2[0].weight.t())
