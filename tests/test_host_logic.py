@@ -168,3 +168,19 @@ def test_masked_predictor_transposed_weight_cache_follows_updates():
         mp.layer2[0].weight.add_(1.0)
     t1 = mp.transposed_weights()
     assert t1 is not t0 and torch.equal(t1[2], mp.layer2[0].weight.t())
+
+
+def test_bench_stdout_carries_only_the_result_line():
+    """bench.py's stdout contract: ONE JSON line, whatever libraries print.  After `_claim_stdout()` file descriptor 1 points at stderr
+    (NCCL writes its version banner there from C, past sys.stdout) and only `emit()` reaches the real stdout."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench._claim_stdout(); "
+            "os.write(1, b'banner from a C library\\n'); print('a python print'); bench.emit('{\"ok\": 1}')" % root)
+    p = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, cwd=root)
+    assert p.returncode == 0, p.stderr.decode()[-800:]
+    assert p.stdout.decode() == '{"ok": 1}\n'
+    err = p.stderr.decode()
+    assert "banner from a C library" in err and "a python print" in err
