@@ -32,7 +32,9 @@ from torch.nn import functional as F
 from . import cabi, gemm
 from .ms_deform_attn import MultiScaleDeformableAttention
 
-OVERLAP_VALUE_PROJ = True  # inside a graph capture: all-layer value projection as a parallel branch beside the salience filter
+OVERLAP_VALUE_PROJ = True  # all-layer value projection as a parallel branch (graph capture) / on a side stream (eager) beside the salience filter
+OVERLAP_VALUE_PROJ_EAGER = __import__("os").environ.get("SDETR_OVERLAP_EAGER", "0") != "0"  # eager too: measured on the fresh-mask
+# pipeline, 760 vs 781-795 images/s -- the extra stream operations cost the (host-bound) eager path more than the overlap returns: off
 VALUE_PROJ_PER_LAYER = False  # (measured, profiles/r2_msda_probe_v1.txt: L2-warm value buys the sampling kernel 2 %; one N=1536 GEMM is 1.5x cheaper than six N=256 ones)
 # each layer's value_proj as its own GEMM on a side stream beside that layer's (latency-bound)
 # pre-attention, joined right before the sampling kernel: the 45.7 MB it writes are still in the 126 MB L2 when the
@@ -513,8 +515,10 @@ class SalienceTransformer(nn.Module):
         self.alpha.data.uniform_(-0.3, 0.3)
 
     def _side_stream(self, device):
+        """One side stream per (device, CURRENT stream): lanes that run the model eagerly on their own streams (FreshMaskPipeline)
+        must not meet on a shared side stream, which would order their value projections one after the other."""
         streams = self.__dict__.setdefault("_side_streams", {})
-        key = str(device)
+        key = (str(device), torch.cuda.current_stream(device).cuda_stream)
         if key not in streams:
             streams[key] = torch.cuda.Stream(device=device)
         return streams[key]
@@ -683,9 +687,10 @@ class SalienceTransformer(nn.Module):
                                                 [p.contiguous() for p in multi_level_pos_embeds],
                                                 self.level_embeds.detach().contiguous(), plan.keep.view(plan.keep.shape[0], -1))
         vbuf = None
-        if OVERLAP_VALUE_PROJ and not VALUE_PROJ_PER_LAYER and not grad and feat.is_cuda and torch.cuda.is_current_stream_capturing():
+        if (OVERLAP_VALUE_PROJ and not VALUE_PROJ_PER_LAYER and not grad and feat.is_cuda and
+                (OVERLAP_VALUE_PROJ_EAGER or torch.cuda.is_current_stream_capturing())):
             # fork: the (large) value projection only needs the tokens, so it becomes a parallel branch of the captured
-            # CUDA graph, running beside the salience filter's many small kernels (eager calls stay on one stream)
+            # CUDA graph -- or, eagerly, runs on a side stream -- beside the salience filter's many small kernels
             cur = torch.cuda.current_stream(feat.device)
             side = self._side_stream(feat.device)
             side.wait_stream(cur)
