@@ -422,6 +422,9 @@ int sdetr_mask_predictor_level(const float *mem, int64_t mem_batch_stride, int b
  * workspace: sdetr_ffn_fused_workspace_floats(M, hidden) floats (partial sums of panels shared by two CTAs: the persistent
  * CTAs take equal numbers of 128-hidden-unit chunks of the (panel, chunk) sequence, whatever the panel count). */
 int64_t sdetr_ffn_fused_workspace_floats(int M, int hidden);
+/* host-side view of the work decomposition (for tests): lo[i] = first item of CTA i in the panel-major (panel, chunk) sequence,
+ * lo[G] = #panels * hidden / 128; returns the CTA count G (or -G when `capacity` < G + 1, 0 for bad sizes) */
+int sdetr_ffn_fused_ranges(int M, int hidden, int64_t *lo, int capacity);
 int sdetr_ffn_fused_layernorm(const float *x, int64_t ldx, const void *W1_hi, const void *W1_lo, float w1_scale, const float *b1,
                               const void *W2_hi, const void *W2_lo, float w2_scale, const float *b2, const float *gamma,
                               const float *beta, float eps, int M, int hidden, float *workspace, int64_t workspace_floats, float *y,

@@ -76,6 +76,7 @@ SIGNATURES = {
     "sdetr_mask_predictor_level": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _i64, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "sdetr_ffn_fused_workspace_floats": (_i64, [_i, _i]),
+    "sdetr_ffn_fused_ranges": (_i, [_i, _i, _vp, _i]),
     "sdetr_ffn_fused_set_balance": (_i, [_i]),
     "sdetr_ffn_fused_layernorm": (_i, [_vp, _i64, _vp, _vp, _f, _vp, _vp, _vp, _f, _vp, _vp, _vp, _f, _i, _i, _vp, _i64, _vp, _vp]),
     "sdetr_ffn_fused_set_trace": (_i, [_vp]),

@@ -438,6 +438,15 @@ static int ffn_grid(int M, int chunks, int balance) {
     return (int)(most < sms ? (most > 0 ? most : 1) : sms);
 }
 
+// host-side view of the decomposition, for tests: lo[i] = first (panel, chunk) item of CTA i, lo[G] = panels * chunks; returns G
+extern "C" int sdetr_ffn_fused_ranges(int M, int hidden, int64_t *lo, int capacity) {
+    if (M <= 0 || hidden <= 0 || hidden % 128 || !lo) return 0;
+    const int chunks = hidden / 128, balance = g_ffn_balance.load(), G = ffn_grid(M, chunks, balance);
+    if (capacity < G + 1) return -G;
+    for (int i = 0; i <= G; ++i) lo[i] = ffn_range_lo((M + 127) / 128, chunks, G, balance, i);
+    return G;
+}
+
 extern "C" int64_t sdetr_ffn_fused_workspace_floats(int M, int hidden) {
     if (M <= 0 || hidden <= 0 || hidden % 128) return 0;
     const int balance = g_ffn_balance.load();

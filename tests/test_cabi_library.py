@@ -101,3 +101,41 @@ def test_argument_validation_of_the_later_entry_points(pkg):
     assert lib.sdetr_gelu_colmean_workspace(2, 16800, 256, 128) >= 2 * 296 * 128 * 4
     rc = lib.sdetr_gemm_3xtf32_pre(p, 40, p, p, None, p, 8, 4, 8, 40, 0, None)
     assert rc != 0 and b"multiple of 32" in lib.sdetr_last_error()
+
+
+def test_ffn_fused_work_decomposition_host_view():
+    """The fused FFN's persistent CTAs split the panel-major (panel, chunk) sequence into contiguous ranges (csrc/ffn_fused.cu).  Host
+    view, no GPU: the ranges partition the sequence, are balanced to +-1 item (balanced mode) or made of whole panels, the partial
+    slot `CTA + panel` is unique along the sequence, and the advertised workspace holds every slot."""
+    import ctypes
+    import salience_detr_b200 as pkg
+    lib = pkg.cabi.lib()
+    try:
+        for balance in (1, 0):
+            lib.sdetr_ffn_fused_set_balance(balance)
+            for cap in (0, 1, 7, 97):
+                lib.sdetr_ffn_fused_set_max_ctas(cap)
+                for rows, hidden in [(1, 128), (128, 256), (129, 2048), (4545, 2048), (22726, 2048), (18181, 1024), (100000, 2048)]:
+                    chunks, panels = hidden // 128, (rows + 127) // 128
+                    buf = (ctypes.c_int64 * 400)()
+                    G = lib.sdetr_ffn_fused_ranges(rows, hidden, buf, 400)
+                    assert 1 <= G <= 148 and (cap == 0 or G <= cap)
+                    lo = list(buf[:G + 1])
+                    assert lo[0] == 0 and lo[-1] == panels * chunks and all(a <= b for a, b in zip(lo, lo[1:]))
+                    sizes = [b - a for a, b in zip(lo, lo[1:])]
+                    if balance:
+                        assert max(sizes) - min(sizes) <= 1 and min(sizes) >= 1
+                    else:
+                        assert all(a % chunks == 0 for a in lo)
+                    slots = []
+                    for cta in range(G):                     # the units of a CTA: one per panel its range touches
+                        pos = lo[cta]
+                        while pos < lo[cta + 1]:
+                            panel = pos // chunks
+                            slots.append(cta + panel)
+                            pos = min(lo[cta + 1], (panel + 1) * chunks)
+                    assert slots == sorted(set(slots))       # strictly increasing: no two units share a slot
+                    assert (max(slots) + 1) * 128 * 256 <= lib.sdetr_ffn_fused_workspace_floats(rows, hidden)
+    finally:
+        lib.sdetr_ffn_fused_set_balance(1)
+        lib.sdetr_ffn_fused_set_max_ctas(0)
