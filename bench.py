@@ -747,7 +747,9 @@ def main():
                                          "hand-written persistent tcgen05.mma.kind::f16 GEMM" if pkg.gemm.OWN_KERNEL == "f16x3" else
                                          "3xTF32 (fp32-class accuracy): hand-written persistent tcgen05.mma.kind::tf32 GEMM") +
                                         " (TMA, pre-split weight, activation split in the kernel into tensor memory, double-buffered TMEM "
-                                        "accumulator, TMA-store epilogue) for every projection; GEMMs of <= 2304 rows (latency-bound) on cuBLAS fp32",
+                                        "accumulator, TMA-store epilogue) for every projection; linear1 -> ReLU -> linear2 -> +residual -> LayerNorm of the encoder "
+                                        "layers as ONE tensor-core kernel with the hidden activations in tensor memory; GEMMs of <= 2304 rows "
+                                        "(latency-bound) on cuBLAS fp32 or the two-launch small-level predictor kernels",
                                 "tcgen05": "hand-written tcgen05.mma.kind::tf32 GEMM (TMA, in-kernel 3xTF32 split, TMEM accumulator; fp32-class accuracy)",
                                 "3xtf32": "cuBLAS TF32 tensor cores on 3-way split operands (3xTF32, fp32-class accuracy)",
                                 "fp32": "cuBLAS fp32 SIMT", "tf32": "cuBLAS TF32 (reduced precision)"}[pkg.gemm.MODE], "cuda_graph": runner.graph is not None,
